@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""Headline benchmark: rays/s rendered by the full-paper NeRF (BASELINE.json config 2):
+800x800 frame, 64 coarse + 128 fine samples, two 8x256 skip-4 FlexibleNeRFModels (L=10/4, view
+directions), T=20 Dex-NeRF thresholds, validation mode, random-init weights, synthetic camera.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" renders one frame.  With N GPUs the image rows are block-partitioned over the ranks
+(no collective on the data path; total work fixed -> "scaling": "strong").  The timed region is
+bracketed by barrier + synchronize; the JSON line carries the device-timed throughput (`value`),
+the end-to-end throughput through the public `nerf` API with host buffers (`e2e`), the roofline
+of the dominant kernel (the fine-pass MLP query) and the CPU oracle timed on this box.
+`--impl reference` times the reference's CPU algorithm (the oracle port; the Python reference
+itself cannot travel to the GPU box) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "dex-nerf_b200"))
+
+import torch  # noqa: E402
+
+H = W = 800
+NC, NF = 64, 128
+NEAR, FAR = 2.0, 6.0
+FX = 1111.1
+THRESHOLDS = [float(m) for m in range(5, 105, 5)]
+FLOP_PER_EVAL = 2 * 593408                        # SURVEY.md section 8(d), unpadded
+FLOP_PER_RAY = (NC + NC + NF) * FLOP_PER_EVAL     # 303 824 896
+CPU_SAMPLE_RAYS = 16384
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"],
+                    source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+def camera():
+    from oracle.nerf_oracle import pose_spherical_world2cam
+    T = pose_spherical_world2cam(30.0, -30.0, 4.0)
+    K = torch.tensor([[FX, 0.0, W / 2.0], [0.0, FX, H / 2.0], [0.0, 0.0, 1.0]])
+    return T, K
+
+
+def make_cfg(nerf):
+    mode = dict(chunksize=1 << 30, perturb=False, num_coarse=NC, num_fine=NF, white_background=False,
+                radiance_field_noise_std=0.0, lindisp=False)
+    return nerf.CfgNode(dict(dataset=dict(no_ndc=True, near=NEAR, far=FAR),
+                             nerf=dict(use_viewdirs=True, train=dict(mode), validation=dict(mode))))
+
+
+def state_dicts():
+    """Random-init weights of the C2 pair, drawn on the CPU under torch.manual_seed(42) exactly as
+    the reference scripts would construct them (coarse first, then fine)."""
+    import nerf
+    torch.manual_seed(42)
+    mc = nerf.FlexibleNeRFModel(8, 256, 4, 10, 4)
+    mf = nerf.FlexibleNeRFModel(8, 256, 4, 10, 4)
+    return mc, mf
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc, self.idx = None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(smax) if smax else None,
+                    samples=len(sm), reasons=sorted(reasons))
+
+
+def cpu_oracle_rays_per_s(n_rays=CPU_SAMPLE_RAYS, reps=1):
+    """The oracle (CPU port of the reference's algorithm) on a bounded sample of the C2 workload:
+    `n_rays` rays from the centre rows of the 800x800 camera, all host threads."""
+    from oracle import nerf_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    T, K = camera()
+    ro, rd = O.get_ray_bundle(H, W, None, T, K)
+    ro, rd = ro.reshape(-1, 3), rd.reshape(-1, 3)
+    start = (H // 2) * W
+    mc, mf = state_dicts()
+    sdc = {k: v.detach() for k, v in mc.state_dict().items()}
+    sdf = {k: v.detach() for k, v in mf.state_dict().items()}
+    opts = O.RenderOptions(near=NEAR, far=FAR, num_coarse=NC, num_fine=NF, Lx=10, Ld=4, chunksize=65536)
+    fc, ff = (lambda x: O.flexible_forward(sdc, x)), (lambda x: O.flexible_forward(sdf, x))
+    with torch.no_grad():
+        O.render_rays(ro[start:start + 128], rd[start:start + 128], fc, ff, opts, THRESHOLDS)   # warm-up
+        times = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            O.render_rays(ro[start:start + n_rays], rd[start:start + n_rays], fc, ff, opts, THRESHOLDS)
+            times.append(time.perf_counter() - t0)
+    return n_rays / statistics.median(times), torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    T = []
+    cores = os.cpu_count() or 1
+    for i in range(args.warmup + args.steps):
+        v, cores = cpu_oracle_rays_per_s(CPU_SAMPLE_RAYS, reps=1)
+        if i >= args.warmup:
+            T.append(CPU_SAMPLE_RAYS / v)
+    ms = 1e3 * sum(T) / len(T)
+    value = CPU_SAMPLE_RAYS / (ms / 1e3)
+    sample = "%d rays of the 800x800 C2 frame (centre rows) per step, full 64+128 / 8x256 pipeline" % CPU_SAMPLE_RAYS
+    print(json.dumps({
+        "impl": "reference", "metric": "rays/sec render (64+128 samples, 8x256 MLP)", "value": value,
+        "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def workload_config(n_gpus):
+    return {"workload": "C2: full-paper NeRF render 800x800, 64 coarse + 128 fine samples, two 8x256 skip-4 "
+                        "FlexibleNeRFModels (L=10/4, viewdirs), T=20 Dex thresholds, validation mode, random-init",
+            "rays_per_step": H * W, "rows_per_gpu": H // n_gpus, "parallelism": "rows%d" % n_gpus,
+            "l2": "per-step intermediates (z_fine + radiance field, >2 GB/GPU at N=1) exceed the 126 MB L2; "
+                  "a 256 MB buffer is also rewritten between steps"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=None, choices=[None, "bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import nerf
+    from nerf import _lib as L
+    from nerf import train_utils as TU
+    if args.precision:
+        nerf.set_precision(args.precision)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_gpus = world
+    dev = torch.device("cuda", local)
+
+    rows = H // n_gpus
+    row0 = rank * rows
+    if rank == n_gpus - 1:
+        rows = H - row0
+    mc, mf = state_dicts()
+    mc, mf = mc.to(dev), mf.to(dev)
+    cfg = make_cfg(nerf)
+    ex, ed = nerf.get_embedding_function(10, True, True), nerf.get_embedding_function(4, True, True)
+    T_cpu, K_cpu = camera()
+    T_dev, K_dev = T_cpu.to(dev), K_cpu.to(dev)
+    T_pin, K_pin = T_cpu.pin_memory(), K_cpu.pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(T_, K_):
+        ro, rd = nerf.get_ray_bundle(H, W, None, T_, K_, row_start=row0, row_count=rows)
+        with torch.no_grad():
+            return nerf.run_one_iter_of_nerf(H, W, FX, mc, mf, ro, rd, cfg, mode="validation",
+                                             encode_position_fn=ex, encode_direction_fn=ed,
+                                             m_thres_cand=THRESHOLDS)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ------------------------------------------------------------------ device-resident timing
+    for _ in range(args.warmup):
+        step(T_dev, K_dev)
+        flush.zero_()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    TU.kernel_event_log = []
+    launches0 = L.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(T_dev, K_dev)
+        flush.zero_()
+    e1.record()
+    barrier()
+    launches = L.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_dev = reduce_max(e0.elapsed_time(e1) / args.steps)
+    log, TU.kernel_event_log = TU.kernel_event_log, None
+    fine = [(a.elapsed_time(b), n, S, nm) for nm, a, b, n, S in log if S == NC + NF]
+    kern_ms = sum(x[0] for x in fine) / len(fine)
+    kern_name = fine[0][3]
+    all_mlp_ms = sum(a.elapsed_time(b) for _, a, b, _, _ in log) / args.steps
+
+    # ------------------------------------------------------------------ end to end (host buffers)
+    out_pin = None
+    def e2e_step():
+        nonlocal out_pin
+        res = step(T_pin.to(dev, non_blocking=True), K_pin.to(dev, non_blocking=True))
+        if out_pin is None:
+            out_pin = [torch.empty(r.shape, dtype=r.dtype).pin_memory() for r in res]
+        for dst, src in zip(out_pin, res):
+            dst.copy_(src, non_blocking=True)
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    ms_e2e = reduce_max(e0.elapsed_time(e1) / args.steps)
+    d2h = sum(o.numel() * o.element_size() for o in out_pin)
+    h2d = (T_pin.numel() + K_pin.numel()) * 4
+
+    if rank == 0:
+        pk = peaks()
+        rays = H * W
+        kern_rays = rows
+        flop_launch = float(fine[0][1]) * fine[0][2] * FLOP_PER_EVAL
+        achieved = flop_launch / (kern_ms * 1e-3) / 1e12
+        peak = pk["tf_sustained"]
+        line = {
+            "metric": "rays/sec render (64+128 samples, 8x256 MLP)", "value": rays / (ms_dev * 1e-3),
+            "unit": "rays/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16" if kern_name == "mlp_tc" else "f32", "data": "synthetic",
+            "config": workload_config(n_gpus),
+            "e2e": {"value": rays / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": kern_name + " (fine pass, %d samples/ray)" % (NC + NF),
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "peak_source": pk["source"] + " bf16 sustained", "traffic": None,
+                         "kernel_ms": kern_ms, "mlp_share_of_step": all_mlp_ms / ms_dev,
+                         "flop_per_launch": flop_launch},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline:
+            v, cores = cpu_oracle_rays_per_s()
+            line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
+                                    "sample": "%d rays of the same C2 frame (centre rows), 1 repetition after "
+                                              "a 128-ray warm-up" % CPU_SAMPLE_RAYS}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,222 @@
+// Alpha compositing with the Dex-NeRF first-crossing depth, and the stand-alone
+// cumprod_exclusive.
+//
+// Reference: nerf/volume_rendering_utils.py:6-70, nerf/nerf_helpers.py:43-64.
+// Arithmetic contract: oracle/nerf_oracle.py volume_render_radiance_field / cumprod_exclusive
+// (fp32 element ops in the reference's order; transmittance product and the per-ray sums
+// accumulated in fp64 and rounded once).
+//
+// Layout: one warp per ray, lane l owns samples l, l+32, l+64, ... so that every global access of
+// the (n,S,4) field, the (n,S) depths and the (n,S) weights is a fully coalesced 128/512-byte
+// warp transaction.  The transmittance T_i = prod_{j<i}(1-alpha_j+1e-10) is a warp-level
+// exclusive product scan (__shfl_up_sync) with a running carry between 32-sample chunks - this
+// replaces the reference's cumprod -> roll -> overwrite sequence.  The first sample with
+// sigma > m comes from __ballot_sync + __ffs per threshold.  A CTA of 8 warps covers 32
+// consecutive rays; per-ray results are staged in shared memory and written as 128-byte rows.
+// HBM-bound: 24*S + 36 + 4*T algorithmic bytes per ray.
+#include "common.cuh"
+
+namespace dexnerf {
+
+constexpr int kCompositeWarps = 8;
+constexpr int kRaysPerCta = 32;
+constexpr int kRaysPerWarp = kRaysPerCta / kCompositeWarps;
+constexpr int kMaxThresholds = 64;
+
+__device__ __forceinline__ double shfl_up_f64(double v, int d) {
+  return __shfl_up_sync(0xffffffffu, v, d);
+}
+
+// Inclusive product scan over the 32 lanes.
+__device__ __forceinline__ double warp_inclusive_product(double v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const double o = shfl_up_f64(v, d);
+    if (lane >= d) v *= o;
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(kCompositeWarps * 32)
+composite_kernel(const float4* __restrict__ rf, const float* __restrict__ z,
+                 const float* __restrict__ rd, const float* __restrict__ noise, int64_t n, int S,
+                 int white_background, const float* __restrict__ thresholds, int T,
+                 float* __restrict__ rgb_out, float* __restrict__ disp_out,
+                 float* __restrict__ acc_out, float* __restrict__ weights_out,
+                 float* __restrict__ depth_out, float* __restrict__ dex_depth,
+                 int64_t* __restrict__ dex_index) {
+  extern __shared__ float smem[];
+  // staging: [6 + 2T][32]: rgb0 rgb1 rgb2 disp acc depth | dex depth (T) | dex index (T, as int)
+  float* s_thr = smem;                          // T (padded to kMaxThresholds)
+  float* s_out = smem + kMaxThresholds;         // (6 + 2T) * 32
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) s_thr[t] = thresholds[t];
+  __syncthreads();
+
+  for (int64_t base = (int64_t)blockIdx.x * kRaysPerCta; base < n;
+       base += (int64_t)gridDim.x * kRaysPerCta) {
+    for (int rr = 0; rr < kRaysPerWarp; ++rr) {
+      const int slot = warp * kRaysPerWarp + rr;
+      const int64_t ray = base + slot;
+      if (ray >= n) break;  // warp-uniform
+      const float dx = rd[ray * 3], dy = rd[ray * 3 + 1], dz = rd[ray * 3 + 2];
+      const float norm =
+          (float)sqrt((double)dx * (double)dx + (double)dy * (double)dy + (double)dz * (double)dz);
+      const float4* rf_row = rf + ray * S;
+      const float* z_row = z + ray * S;
+      double carry = 1.0, s_acc = 0.0, s_depth = 0.0, s_r = 0.0, s_g = 0.0, s_b = 0.0;
+      int found0 = -1, found1 = -1;  // lane l owns thresholds l and l + 32
+      int n_found = 0;
+      for (int c0 = 0; c0 < S; c0 += 32) {
+        const int j = c0 + lane;
+        const bool valid = j < S;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        float zj = 0.f, zn = 0.f, nz = 0.f;
+        if (valid) {
+          v = rf_row[j];
+          zj = z_row[j];
+          if (j + 1 < S) zn = z_row[j + 1];
+          if (noise) nz = noise[ray * S + j];
+        }
+        float dist = (j + 1 < S) ? __fsub_rn(zn, zj) : 1e10f;
+        dist = __fmul_rn(dist, norm);
+        const float sigma = fmaxf(__fadd_rn(v.w, nz), 0.0f);
+        const float alpha = valid ? __fsub_rn(1.0f, expf(-__fmul_rn(sigma, dist))) : 0.0f;
+        const float x = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
+        const double incl = warp_inclusive_product(valid ? (double)x : 1.0, lane);
+        double excl = shfl_up_f64(incl, 1);
+        if (lane == 0) excl = 1.0;
+        const float trans = (float)(carry * excl);
+        carry *= __shfl_sync(0xffffffffu, incl, 31);
+        const float w = __fmul_rn(alpha, trans);
+        if (valid) {
+          if (weights_out) weights_out[ray * S + j] = w;
+          const double wd = (double)w;
+          s_acc += wd;
+          s_depth += wd * (double)zj;
+          s_r += wd * (double)(1.0f / (1.0f + expf(-v.x)));
+          s_g += wd * (double)(1.0f / (1.0f + expf(-v.y)));
+          s_b += wd * (double)(1.0f / (1.0f + expf(-v.z)));
+        }
+        if (n_found < T) {
+          for (int t = 0; t < T; ++t) {
+            const unsigned hit = __ballot_sync(0xffffffffu, valid && sigma > s_thr[t]);
+            if (hit) {
+              const int first = c0 + __ffs(hit) - 1;
+              const bool mine = (t & 31) == lane;
+              const int cur = __shfl_sync(0xffffffffu, (t < 32) ? found0 : found1, t & 31);
+              if (cur < 0) {
+                if (mine) { if (t < 32) found0 = first; else found1 = first; }
+                ++n_found;
+              }
+            }
+          }
+        }
+      }
+      s_acc = warp_sum_f64(s_acc);
+      s_depth = warp_sum_f64(s_depth);
+      s_r = warp_sum_f64(s_r);
+      s_g = warp_sum_f64(s_g);
+      s_b = warp_sum_f64(s_b);
+      if (lane == 0) {
+        const float acc = (float)s_acc, depth = (float)s_depth;
+        float r = (float)s_r, g = (float)s_g, b = (float)s_b;
+        const float q = __fdiv_rn(depth, acc);
+        const float m = (q != q) ? q : fmaxf(1e-10f, q);  // torch.max propagates NaN (acc == 0)
+        if (white_background) {
+          const float bg = __fsub_rn(1.0f, acc);
+          r = __fadd_rn(r, bg); g = __fadd_rn(g, bg); b = __fadd_rn(b, bg);
+        }
+        s_out[0 * 32 + slot] = r;
+        s_out[1 * 32 + slot] = g;
+        s_out[2 * 32 + slot] = b;
+        s_out[3 * 32 + slot] = __fdiv_rn(1.0f, m);
+        s_out[4 * 32 + slot] = acc;
+        s_out[5 * 32 + slot] = depth;
+      }
+      for (int t = lane; t < T; t += 32) {
+        int idx = (t < 32) ? found0 : found1;
+        if (idx < 0) idx = 0;  // argmax of an all-zero row (volume_rendering_utils.py:56)
+        s_out[(6 + t) * 32 + slot] = z_row[idx];
+        reinterpret_cast<int*>(s_out)[(6 + T + t) * 32 + slot] = idx;
+      }
+    }
+    __syncthreads();
+    // coalesced write-back of the 32-ray block
+    const int64_t left = n - base;
+    const int cnt = left < kRaysPerCta ? (int)left : kRaysPerCta;
+    for (int e = threadIdx.x; e < (6 + 2 * T) * 32; e += blockDim.x) {
+      const int plane = e >> 5, slot = e & 31;
+      if (slot >= cnt) continue;
+      const int64_t ray = base + slot;
+      const float val = s_out[e];
+      if (plane < 3) { if (rgb_out) rgb_out[ray * 3 + plane] = val; }
+      else if (plane == 3) { if (disp_out) disp_out[ray] = val; }
+      else if (plane == 4) { if (acc_out) acc_out[ray] = val; }
+      else if (plane == 5) { if (depth_out) depth_out[ray] = val; }
+      else if (plane < 6 + T) { if (dex_depth) dex_depth[(int64_t)(plane - 6) * n + ray] = val; }
+      else if (dex_index) dex_index[(int64_t)(plane - 6 - T) * n + ray] =
+          (int64_t) reinterpret_cast<const int*>(s_out)[e];
+    }
+    __syncthreads();
+  }
+}
+
+// Stand-alone cumprod_exclusive (nerf/nerf_helpers.py:43-64): one warp per row.
+__global__ void __launch_bounds__(256) cumprod_exclusive_kernel(const float* __restrict__ x,
+                                                                int64_t n, int S,
+                                                                float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n;
+       row += warps) {
+    double carry = 1.0;
+    for (int c0 = 0; c0 < S; c0 += 32) {
+      const int j = c0 + lane;
+      const bool valid = j < S;
+      const double incl = warp_inclusive_product(valid ? (double)x[row * S + j] : 1.0, lane);
+      double excl = shfl_up_f64(incl, 1);
+      if (lane == 0) excl = 1.0;
+      if (valid) out[row * S + j] = (float)(carry * excl);
+      carry *= __shfl_sync(0xffffffffu, incl, 31);
+    }
+  }
+}
+
+}  // namespace dexnerf
+
+using namespace dexnerf;
+
+extern "C" DEXNERF_API int dexnerf_volume_render(const float* rf, const float* z, const float* rd,
+                                     const float* noise, int64_t n, int S, int white_background,
+                                     const float* thresholds, int T, float* rgb, float* disp,
+                                     float* acc, float* weights, float* depth, float* dex_depth,
+                                     int64_t* dex_index, void* stream) {
+  DN_REQUIRE(rf && z && rd, "volume_render: null input");
+  DN_REQUIRE(S >= 1, "volume_render: S < 1");
+  DN_REQUIRE(T >= 0 && T <= kMaxThresholds, "volume_render: at most %d thresholds", kMaxThresholds);
+  DN_REQUIRE(T == 0 || thresholds, "volume_render: thresholds is null");
+  DN_REQUIRE((reinterpret_cast<uintptr_t>(rf) & 15) == 0, "volume_render: rf must be 16-byte aligned");
+  if (n <= 0) return 0;
+  const size_t smem = sizeof(float) * (kMaxThresholds + (6 + 2 * (size_t)T) * 32);
+  int64_t blocks = ceil_div64(n, kRaysPerCta);
+  const int64_t cap = (int64_t)kNumSMs * 8 * 4;
+  if (blocks > cap) blocks = cap;
+  composite_kernel<<<(int)blocks, kCompositeWarps * 32, smem, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(rf), z, rd, noise, n, S, white_background, thresholds, T, rgb,
+      disp, acc, weights, depth, dex_depth, dex_index);
+  DN_CHECK_LAUNCH("volume_render");
+  return 0;
+}
+
+extern "C" DEXNERF_API int dexnerf_cumprod_exclusive(const float* x, int64_t n, int S, float* out, void* stream) {
+  DN_REQUIRE(x && out, "cumprod_exclusive: null pointer");
+  DN_REQUIRE(S >= 1, "cumprod_exclusive: S < 1");
+  if (n <= 0) return 0;
+  int64_t blocks = ceil_div64(n, 8);
+  const int64_t cap = (int64_t)kNumSMs * 8 * 4;
+  if (blocks > cap) blocks = cap;
+  cumprod_exclusive_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, S, out);
+  DN_CHECK_LAUNCH("cumprod_exclusive");
+  return 0;
+}

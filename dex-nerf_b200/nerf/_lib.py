@@ -1,0 +1,108 @@
+"""ctypes binding of libdexnerf.so (include/dexnerf.h) - the only bridge between the Python
+namespace and the CUDA kernels.  There is no fallback: if the library is missing or a tensor is
+not a contiguous fp32 CUDA tensor, the call raises."""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libdexnerf.so")
+
+MAX_OPS = 16
+ENC_XYZ, ENC_DIR, BUF_A, BUF_B, OUT_RGB, OUT_SIGMA, OUT_ALL, NONE = 0, 1, 2, 3, 4, 5, 6, -1
+
+
+class Op(C.Structure):
+    _fields_ = [("src0", C.c_int32), ("src0_dim", C.c_int32), ("src1", C.c_int32), ("src1_dim", C.c_int32),
+                ("dst", C.c_int32), ("out_dim", C.c_int32), ("relu", C.c_int32), ("pad_", C.c_int32),
+                ("w_off", C.c_int64), ("b_off", C.c_int64)]
+
+
+class Program(C.Structure):
+    _fields_ = [("n_ops", C.c_int32), ("dim_xyz", C.c_int32), ("dim_dir", C.c_int32), ("max_width", C.c_int32),
+                ("Lx", C.c_int32), ("Ld", C.c_int32), ("include_xyz", C.c_int32), ("include_dir", C.c_int32),
+                ("log_xyz", C.c_int32), ("log_dir", C.c_int32), ("pad_", C.c_int32 * 2),
+                ("ops", Op * MAX_OPS)]
+
+
+class FlexibleSpec(C.Structure):
+    _fields_ = [("hidden", C.c_int32), ("n_trunk", C.c_int32), ("skip_every", C.c_int32),
+                ("dim_xyz", C.c_int32), ("dim_dir", C.c_int32), ("Lx", C.c_int32), ("Ld", C.c_int32),
+                ("include_xyz", C.c_int32), ("include_dir", C.c_int32), ("log_xyz", C.c_int32),
+                ("log_dir", C.c_int32), ("pad_", C.c_int32)]
+
+
+_P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_SIGS = {
+    "dexnerf_abi_version": (C.c_int, []),
+    "dexnerf_last_error": (C.c_char_p, []),
+    "dexnerf_ray_bundle": (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
+    "dexnerf_ndc_rays": (C.c_int, [_P, _P, _L, _I, _I, _F, _F, _P, _P, _P]),
+    "dexnerf_positional_encoding": (C.c_int, [_P, _L, _I, _I, _I, _P, _P]),
+    "dexnerf_stratified_z": (C.c_int, [_L, _I, _F, _F, _P, _P, _I, _P, _P, _P]),
+    "dexnerf_cumprod_exclusive": (C.c_int, [_P, _L, _I, _P, _P]),
+    "dexnerf_volume_render": (C.c_int, [_P, _P, _P, _P, _L, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "dexnerf_sample_pdf": (C.c_int, [_P, _P, _L, _I, _I, _P, _P, _P, _P]),
+    "dexnerf_resample_merge": (C.c_int, [_P, _P, _L, _I, _I, _P, _P, _P]),
+    "dexnerf_mlp_forward": (C.c_int, [C.POINTER(Program), _P, _P, _L, _P, _P]),
+    "dexnerf_mlp_query": (C.c_int, [C.POINTER(Program), _P, _P, _P, _P, _P, _L, _I, _P, _P]),
+    "dexnerf_tc_packed_bytes": (C.c_int64, [C.POINTER(FlexibleSpec)]),
+    "dexnerf_tc_pack": (C.c_int, [C.POINTER(FlexibleSpec), C.POINTER(Program), _P, _P, _P]),
+    "dexnerf_tc_query": (C.c_int, [C.POINTER(FlexibleSpec), _P, _P, _P, _P, _P, _L, _I, _P, _P]),
+}
+
+_lib = None
+
+
+class DexNerfError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libdexnerf.so once.  Raises (loudly) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise DexNerfError(
+                "libdexnerf.so not found at %s - build it with `python dex-nerf_b200/build.py` "
+                "(there is no CPU or PyTorch fallback)" % LIB_PATH)
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+launch_count = 0   # C-ABI calls made so far; every call is exactly one kernel launch
+
+
+def check(rc, what):
+    global launch_count
+    launch_count += 1
+    if rc != 0:
+        raise DexNerfError("%s failed (%d): %s" % (what, rc, lib().dexnerf_last_error().decode()))
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dev_f32(t, name, allow_none=False):
+    """Validate a tensor argument: contiguous fp32 on CUDA.  No silent copies to/from the host."""
+    if t is None:
+        if allow_none:
+            return None
+        raise ValueError("%s is required" % name)
+    if not isinstance(t, torch.Tensor):
+        raise ValueError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise ValueError("%s must be a CUDA tensor (this build has no CPU path)" % name)
+    if t.dtype != torch.float32:
+        raise ValueError("%s must be float32, got %s" % (name, t.dtype))
+    return t.contiguous()
+
+
+def ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())

@@ -1,0 +1,213 @@
+"""Drop-in for the render driver of the reference's nerf/train_utils.py:72-288
+(run_network, predict_and_render_radiance, run_one_iter_of_nerf).
+
+The reference evaluates a ray chunk as ~200 eager ATen kernels and materialises the positional
+encoding of every sample (10 GB for an 800x800 frame).  Here a chunk is six launches
+(coarse depths, coarse MLP query, coarse compositing, resample+merge, fine MLP query, fine
+compositing); encodings never leave the SM.  Return tuples, shapes and quirks follow the reference.
+"""
+import os
+
+import torch
+
+from . import _lib as L
+from .nerf_helpers import _Embedder, get_minibatches, ndc_rays
+from .nerf_helpers import sample_pdf_2 as sample_pdf  # the reference re-binds the name (train_utils.py:6)
+from .volume_rendering_utils import _thresholds_tensor, render_maps, volume_render_radiance_field
+
+# "bf16": tcgen05 tensor-core MLP (bf16 operands, fp32 accumulate) where the model is supported;
+# "fp32": CUDA-core MLP with the reference's fp32 arithmetic.  DEXNERF_PRECISION overrides.
+_precision = os.environ.get("DEXNERF_PRECISION", "bf16")
+
+
+def set_precision(p):
+    global _precision
+    if p not in ("bf16", "fp32"):
+        raise ValueError("precision must be 'bf16' or 'fp32'")
+    _precision = p
+
+
+def get_precision():
+    return _precision
+
+
+def _fusable(model, embed_fn, embeddirs_fn):
+    return (hasattr(model, "program") and isinstance(embed_fn, _Embedder)
+            and (embeddirs_fn is None or isinstance(embeddirs_fn, _Embedder))
+            and embed_fn.out_dim == model.dim_xyz
+            and (model.dim_dir == 0 or (embeddirs_fn is not None and embeddirs_fn.out_dim == model.dim_dir)))
+
+
+kernel_event_log = None   # bench.py sets this to a list to collect (name, start_evt, end_evt, n, S)
+
+
+def query_field(model, ro, rd, viewdirs, z, embed_fn, embeddirs_fn):
+    """pts = ro + rd*z -> encode -> model, fused in one kernel.  ro, rd, viewdirs (n,3), z (n,S)
+    -> raw radiance field (n,S,4)."""
+    n, S = z.shape
+    rf = torch.empty((n, S, 4), dtype=torch.float32, device=z.device)
+    if n == 0:
+        return rf
+    prog = model.program(embed_fn, embeddirs_fn if model.dim_dir else None)
+    vd = viewdirs if model.dim_dir else None
+    log = kernel_event_log
+    if log is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    used = "mlp_simt"
+    if _precision == "bf16" and _tc_query(model, prog, ro, rd, vd, z, rf):
+        used = "mlp_tc"
+    else:
+        L.check(L.lib().dexnerf_mlp_query(prog, L.ptr(model.packed_params()), L.ptr(ro), L.ptr(rd), L.ptr(vd),
+                                          L.ptr(z), n, S, L.ptr(rf), L.stream_ptr()), "mlp_query")
+    if log is not None:
+        e1.record()
+        log.append((used, e0, e1, n, S))
+    return rf
+
+
+def _tc_query(model, prog, ro, rd, vd, z, rf):
+    from . import tensorcore
+    if not tensorcore.supported(model, prog):
+        return False
+    tensorcore.query(model, prog, ro, rd, vd, z, rf)
+    return True
+
+
+def run_network(network_fn, pts, ray_batch, chunksize, embed_fn, embeddirs_fn):
+    """train_utils.py:72-89, for callers that hand in explicit points: encode, append the encoded
+    view directions (last three ray columns, :77), chunked model calls, reshape."""
+    pts_flat = pts.reshape((-1, pts.shape[-1]))
+    embedded = embed_fn(pts_flat)
+    if embeddirs_fn is not None:
+        viewdirs = ray_batch[..., None, -3:]
+        input_dirs_flat = viewdirs.expand(pts.shape).reshape((-1, 3))
+        embedded = torch.cat((embedded, embeddirs_fn(input_dirs_flat.contiguous())), dim=-1)
+    preds = [network_fn(batch) for batch in get_minibatches(embedded, chunksize=chunksize)]
+    radiance_field = torch.cat(preds, dim=0)
+    return radiance_field.reshape(list(pts.shape[:-1]) + [radiance_field.shape[-1]])
+
+
+def _coarse_depths(n, near, far, num_coarse, lindisp, t_rand, device):
+    z = torch.empty((n, num_coarse), dtype=torch.float32, device=device)
+    if n:
+        L.check(L.lib().dexnerf_stratified_z(n, num_coarse, 0.0, 0.0, L.ptr(near), L.ptr(far), int(bool(lindisp)),
+                                             L.ptr(t_rand), L.ptr(z), L.stream_ptr()), "stratified_z")
+    return z
+
+
+def _field(model, ro, rd, viewdirs, z, ray_batch, chunksize, embed_fn, embeddirs_fn):
+    if _fusable(model, embed_fn, embeddirs_fn):
+        return query_field(model, ro, rd, viewdirs, z, embed_fn, embeddirs_fn)
+    # arbitrary callables: same dataflow as the reference, each step one of our kernels
+    pts = ro[..., None, :] + rd[..., None, :] * z[..., :, None]
+    return run_network(model, pts, ray_batch, chunksize, embed_fn, embeddirs_fn).contiguous()
+
+
+def predict_and_render_radiance(ray_batch, model_coarse, model_fine, options, mode="train",
+                                encode_position_fn=None, encode_direction_fn=None, m_thres_cand=None,
+                                rng=None):
+    """train_utils.py:92-202.  ray_batch (n, 8 | 11) = [ro, rd, near, far, (viewdir)].
+    Returns (rgb_coarse, depth_coarse, acc_coarse, rgb_fine, depth_fine, acc_fine, *depth_fine_dex).
+    `rng` (extension): dict with any of t_rand (n,Nc), u (n,Nf), noise_coarse (n,Nc),
+    noise_fine (n,Nc+Nf) to replay the reference's four random draws."""
+    rng = rng or {}
+    opt = getattr(options.nerf, mode)
+    rays = L.dev_f32(ray_batch, "ray_batch")
+    n = rays.shape[0]
+    dev = rays.device
+    ro, rd = rays[:, 0:3].contiguous(), rays[:, 3:6].contiguous()
+    near, far = rays[:, 6].contiguous(), rays[:, 7].contiguous()
+    viewdirs = rays[:, -3:].contiguous() if rays.shape[1] > 8 else None
+    thr, T = _thresholds_tensor(m_thres_cand, dev)
+    Nc, Nf = int(opt.num_coarse), int(opt.num_fine)
+    std = float(opt.radiance_field_noise_std)
+
+    t_rand = None
+    if opt.perturb:
+        t_rand = rng.get("t_rand")
+        if t_rand is None:
+            t_rand = torch.rand((n, Nc), dtype=torch.float32, device=dev)
+        t_rand = L.dev_f32(t_rand, "t_rand")
+    z = _coarse_depths(n, near, far, Nc, opt.lindisp, t_rand, dev)
+
+    rf = _field(model_coarse, ro, rd, viewdirs, z, rays, opt.chunksize, encode_position_fn, encode_direction_fn)
+    noise = rng.get("noise_coarse")
+    if noise is None and std > 0.0:
+        noise = torch.randn((n, Nc), dtype=torch.float32, device=dev) * std
+    c = render_maps(rf, z, rd, noise, opt.white_background, thr, T)
+    rgb_coarse, acc_coarse, depth_coarse = c["rgb"], c["acc"], c["depth"]
+
+    if Nf <= 0:
+        # the reference builds its return from depth_fine_dex, which only exists after the fine pass
+        raise NameError("name 'depth_fine_dex' is not defined")
+    u = rng.get("u")
+    if u is None and opt.perturb != 0.0:       # det = (perturb == 0.0), train_utils.py:169
+        u = torch.rand((n, Nf), dtype=torch.float32, device=dev)
+    u = L.dev_f32(u, "u", allow_none=True)
+    z_fine = torch.empty((n, Nc + Nf), dtype=torch.float32, device=dev)
+    if n:
+        L.check(L.lib().dexnerf_resample_merge(L.ptr(z), L.ptr(c["weights"]), n, Nc, Nf, L.ptr(u), L.ptr(z_fine),
+                                               L.stream_ptr()), "resample_merge")
+    rf_f = _field(model_fine, ro, rd, viewdirs, z_fine, rays, opt.chunksize, encode_position_fn,
+                  encode_direction_fn)
+    noise = rng.get("noise_fine")
+    if noise is None and std > 0.0:
+        noise = torch.randn((n, Nc + Nf), dtype=torch.float32, device=dev) * std
+    f = render_maps(rf_f, z_fine, rd, noise, opt.white_background, thr, T, want_weights=False)
+    dex = [f["dex"][t] for t in range(T)]
+    return tuple([rgb_coarse, depth_coarse, acc_coarse, f["rgb"], f["depth"], f["acc"]] + dex)
+
+
+def run_one_iter_of_nerf(height, width, focal_length, model_coarse, model_fine, ray_origins, ray_directions,
+                         options, mode="train", encode_position_fn=None, encode_direction_fn=None,
+                         m_thres_cand=None, rng=None):
+    """train_utils.py:205-288.  Slots 1 and 4 of the result are the EXPECTED depth (:201), the
+    Dex-NeRF threshold depths of the fine pass follow from slot 6.  In "validation" mode outputs
+    are reshaped back to the shape of `ray_directions`.  The ray chunk size of the YAML
+    (`chunksize`) still bounds the rays per launch; the per-sample chunking of the reference's
+    run_network is unnecessary because no per-sample tensor but (r,g,b,sigma) exists."""
+    rd_in = L.dev_f32(ray_directions, "ray_directions")
+    ro_in = L.dev_f32(ray_origins, "ray_origins")
+    viewdirs = None
+    if options.nerf.use_viewdirs:
+        viewdirs = rd_in / rd_in.norm(p=2, dim=-1).unsqueeze(-1)
+        viewdirs = viewdirs.reshape((-1, 3))
+    restore_shapes = [rd_in.shape, rd_in.shape[:-1], rd_in.shape[:-1]]
+    if model_fine:
+        restore_shapes += restore_shapes
+        for _ in m_thres_cand:
+            restore_shapes += [rd_in.shape[:-1]]
+    if options.dataset.no_ndc is False:
+        ro, rd = ndc_rays(height, width, focal_length, 1.0, ro_in, rd_in)
+        ro, rd = ro.reshape((-1, 3)), rd.reshape((-1, 3))
+    else:
+        ro, rd = ro_in.reshape((-1, 3)), rd_in.reshape((-1, 3))
+    near = options.dataset.near * torch.ones_like(rd[..., :1])
+    far = options.dataset.far * torch.ones_like(rd[..., :1])
+    rays = torch.cat((ro, rd, near, far), dim=-1)
+    if options.nerf.use_viewdirs:
+        rays = torch.cat((rays, viewdirs), dim=-1)
+
+    chunk = getattr(options.nerf, mode).chunksize
+    pred = []
+    for start in range(0, rays.shape[0], chunk):
+        sub = None
+        if rng:
+            sub = {k: v[start:start + chunk] for k, v in rng.items() if v is not None}
+        pred.append(predict_and_render_radiance(rays[start:start + chunk], model_coarse, model_fine, options,
+                                                mode=mode, encode_position_fn=encode_position_fn,
+                                                encode_direction_fn=encode_direction_fn,
+                                                m_thres_cand=m_thres_cand, rng=sub))
+    if len(pred) == 1:
+        synthesized_images = list(pred[0])
+    else:
+        synthesized_images = [torch.cat(image, dim=0) if image[0] is not None else None
+                              for image in zip(*pred)]
+    if mode == "validation":
+        synthesized_images = [image.view(shape) if image is not None else None
+                              for (image, shape) in zip(synthesized_images, restore_shapes)]
+        if model_fine:
+            return tuple(synthesized_images)
+        return tuple(synthesized_images + [None, None, None])
+    return tuple(synthesized_images)

@@ -153,7 +153,8 @@ def volume_render_radiance_field(radiance_field: torch.Tensor, depth_values: tor
     if m_thres_cand is None:
         raise TypeError("m_thres_cand is required (the reference iterates over it, :53)")
     z = depth_values
-    rd_norm = torch.sqrt((ray_directions * ray_directions).to(F64).sum(-1)).to(F32)
+    rd64 = ray_directions.to(F64)
+    rd_norm = torch.sqrt((rd64 * rd64).sum(-1)).to(F32)
     dists = torch.cat((z[..., 1:] - z[..., :-1], torch.full_like(z[..., :1], 1e10)), dim=-1)
     dists = dists * rd_norm[..., None]
     rgb = torch.sigmoid(radiance_field[..., :3])
@@ -338,7 +339,8 @@ def render_rays(ro: torch.Tensor, rd: torch.Tensor, model_coarse, model_fine, o:
     rd = rd.reshape(-1, 3)
     viewdirs = None
     if o.use_viewdirs:
-        nrm = torch.sqrt((rd * rd).to(F64).sum(-1, keepdim=True)).to(F32)
+        rd64 = rd.to(F64)
+        nrm = torch.sqrt((rd64 * rd64).sum(-1, keepdim=True)).to(F32)
         viewdirs = rd / nrm
     if not o.no_ndc:
         ro, rd = ndc_rays(height, width, focal, 1.0, ro, rd)

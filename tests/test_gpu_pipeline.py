@@ -1,0 +1,183 @@
+"""GPU parity of the whole render path (run_one_iter_of_nerf) through the C ABI: against the
+golden outputs of the reference (small synthetic scene, trained lego checkpoint, NDC, replayed
+train-mode RNG) and against the CPU oracle at BASELINE config sizes."""
+import numpy as np
+import pytest
+import torch
+
+import nerf
+from oracle import nerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+t = torch.from_numpy
+NAMES = ["rgb_c", "depth_c", "acc_c", "rgb_f", "depth_f", "acc_f"]
+
+
+def close(a, b, rtol, atol):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol, equal_nan=True)
+
+
+def make_cfg(num_coarse, num_fine, near, far, perturb=False, noise_std=0.0, white_bg=False, lindisp=False,
+             no_ndc=True, use_viewdirs=True, chunksize=1 << 20):
+    mode = dict(chunksize=chunksize, perturb=perturb, num_coarse=num_coarse, num_fine=num_fine,
+                white_background=white_bg, radiance_field_noise_std=noise_std, lindisp=lindisp)
+    return nerf.CfgNode(dict(dataset=dict(no_ndc=no_ndc, near=near, far=far),
+                             nerf=dict(use_viewdirs=use_viewdirs, train=dict(mode, num_random_rays=64),
+                                       validation=dict(mode))))
+
+
+def load(model, g, prefix):
+    model.load_state_dict({k[len(prefix):]: t(g[k]) for k in g.files if k.startswith(prefix)})
+    return model.cuda()
+
+
+def check(res, g, tag, rtol=3e-4, atol=3e-5, dex_exact=0.9):
+    for name, v in zip(NAMES, res[:6]):
+        assert v.shape == g[f"{tag}_{name}"].shape, name
+        close(v, g[f"{tag}_{name}"], rtol, atol)
+    dex = torch.stack(res[6:], 0).cpu().numpy()
+    ref = g[f"{tag}_dex"]
+    close(dex, ref, 1e-5, 1e-5)
+    assert (dex == ref).mean() > dex_exact
+
+
+@pytest.fixture(autouse=True)
+def fp32_precision():
+    """These tests pin the reference's fp32 arithmetic; the tensor-core path has its own file."""
+    old = nerf.get_precision()
+    nerf.set_precision("fp32")
+    yield
+    nerf.set_precision(old)
+
+
+def small_models(g):
+    mk = lambda: nerf.FlexibleNeRFModel(num_layers=5, hidden_size=32, skip_connect_every=2,
+                                        num_encoding_fn_xyz=6, num_encoding_fn_dir=4)
+    return load(mk(), g, "coarse."), load(mk(), g, "fine.")
+
+
+def test_small_scene_validation(golden):
+    g = golden("pipeline_small")
+    mc, mf = small_models(g)
+    H, W = map(int, g["HW"])
+    ro, rd = nerf.get_ray_bundle(H, W, None, t(g["T"]).cuda(), t(g["K"]).cuda())
+    ex, ed = nerf.get_embedding_function(6, True, True), nerf.get_embedding_function(4, True, True)
+    thr = g["thr"].tolist()
+    res = nerf.run_one_iter_of_nerf(H, W, 9.0, mc, mf, ro, rd, make_cfg(16, 24, 2.0, 6.0), mode="validation",
+                                    encode_position_fn=ex, encode_direction_fn=ed, m_thres_cand=thr)
+    assert len(res) == 6 + len(thr) and res[0].shape == (H, W, 3) and res[1].shape == (H, W)
+    check(res, g, "val")
+    res = nerf.run_one_iter_of_nerf(H, W, 9.0, mc, mf, ro, rd,
+                                    make_cfg(16, 24, 2.0, 6.0, white_bg=True, lindisp=True), mode="validation",
+                                    encode_position_fn=ex, encode_direction_fn=ed, m_thres_cand=thr)
+    check(res, g, "val_wl")
+    # ray chunking (chunksize smaller than the ray count) must not change anything
+    res2 = nerf.run_one_iter_of_nerf(H, W, 9.0, mc, mf, ro, rd,
+                                     make_cfg(16, 24, 2.0, 6.0, white_bg=True, lindisp=True, chunksize=7),
+                                     mode="validation", encode_position_fn=ex, encode_direction_fn=ed,
+                                     m_thres_cand=thr)
+    for a, b in zip(res, res2):
+        assert torch.equal(a, b)
+
+
+def test_small_scene_train_replayed_rng(golden):
+    g = golden("pipeline_small")
+    mc, mf = small_models(g)
+    H, W = map(int, g["HW"])
+    ex, ed = nerf.get_embedding_function(6, True, True), nerf.get_embedding_function(4, True, True)
+    rng = dict(t_rand=t(g["train_t_rand"]).cuda(), u=t(g["train_u"]).cuda(),
+               noise_coarse=t(g["train_noise_c"]).cuda(), noise_fine=t(g["train_noise_f"]).cuda())
+    res = nerf.run_one_iter_of_nerf(H, W, 9.0, mc, mf, t(g["ro"]).reshape(-1, 3).cuda(),
+                                    t(g["rd"]).reshape(-1, 3).cuda(),
+                                    make_cfg(16, 24, 2.0, 6.0, perturb=True, noise_std=0.2), mode="train",
+                                    encode_position_fn=ex, encode_direction_fn=ed, m_thres_cand=g["thr"].tolist(),
+                                    rng=rng)
+    assert res[0].shape == (H * W, 3)                       # train mode stays flat
+    check(res, g, "train")
+    # without replay it must still run (Philox draws on the device) and give finite outputs
+    res = nerf.run_one_iter_of_nerf(H, W, 9.0, mc, mf, t(g["ro"]).reshape(-1, 3).cuda(),
+                                    t(g["rd"]).reshape(-1, 3).cuda(),
+                                    make_cfg(16, 24, 2.0, 6.0, perturb=True, noise_std=0.2), mode="train",
+                                    encode_position_fn=ex, encode_direction_fn=ed, m_thres_cand=g["thr"].tolist())
+    assert all(torch.isfinite(v).all() for v in res)
+
+
+def test_small_scene_ndc_no_viewdirs(golden):
+    g = golden("pipeline_small")
+    mk = lambda: nerf.FlexibleNeRFModel(num_layers=4, hidden_size=32, num_encoding_fn_xyz=6,
+                                        num_encoding_fn_dir=4, use_viewdirs=False)
+    mc, mf = load(mk(), g, "ndc_coarse."), load(mk(), g, "ndc_fine.")
+    H, W = map(int, g["HW"])
+    res = nerf.run_one_iter_of_nerf(H, W, 9.0, mc, mf, t(g["ndc_ro"]).cuda(), t(g["ndc_rd"]).cuda(),
+                                    make_cfg(16, 24, 0.0, 1.0, no_ndc=False, use_viewdirs=False), mode="validation",
+                                    encode_position_fn=nerf.get_embedding_function(6, True, True),
+                                    encode_direction_fn=None, m_thres_cand=g["thr"].tolist())
+    check(res, g, "ndc")
+
+
+def test_lego_checkpoint(golden):
+    """Trained 4x128 checkpoint from pretrained/lego-lowres: the thresholds are really crossed."""
+    g = golden("lego_lowres")
+    mk = lambda: nerf.FlexibleNeRFModel(num_encoding_fn_xyz=10, num_encoding_fn_dir=4)
+    mc, mf = load(mk(), g, "coarse."), load(mk(), g, "fine.")
+    H, W = map(int, g["HW"])
+    ro, rd = nerf.get_ray_bundle(H, W, None, t(g["T"]).cuda(), t(g["K"]).cuda())
+    res = nerf.run_one_iter_of_nerf(H, W, 14.0, mc, mf, ro, rd, make_cfg(64, 64, 2.0, 6.0, white_bg=True),
+                                    mode="validation",
+                                    encode_position_fn=nerf.get_embedding_function(10, True, True),
+                                    encode_direction_fn=nerf.get_embedding_function(4, True, True),
+                                    m_thres_cand=g["thr"].tolist())
+    for name, v in zip(NAMES, res[:6]):
+        close(v, g[name], 1e-3, 1e-4)
+    dex = torch.stack(res[6:], 0).cpu().numpy()
+    assert (dex == g["dex"]).mean() > 0.97
+    close(dex, g["dex"], 0, 0.07)            # a flipped sample index moves the depth by one spacing
+
+
+def test_generic_callable_path(golden):
+    """Encoders given as plain callables (not get_embedding_function objects) take the un-fused
+    dataflow of the reference; results must agree with the fused path."""
+    g = golden("pipeline_small")
+    mc, mf = small_models(g)
+    H, W = map(int, g["HW"])
+    ro, rd = nerf.get_ray_bundle(H, W, None, t(g["T"]).cuda(), t(g["K"]).cuda())
+    thr = g["thr"].tolist()
+    res = nerf.run_one_iter_of_nerf(H, W, 9.0, mc, mf, ro, rd, make_cfg(16, 24, 2.0, 6.0), mode="validation",
+                                    encode_position_fn=lambda x: nerf.positional_encoding(x, 6),
+                                    encode_direction_fn=lambda x: nerf.positional_encoding(x, 4), m_thres_cand=thr)
+    check(res, g, "val")
+
+
+def test_c2_shape_8x256_fp32_vs_oracle():
+    """BASELINE config 2 network and sampling (8x256 skip-4, L=10/4, 64+128, T=20) on 256 rays of
+    the 800x800 camera, fp32 path against the oracle end to end."""
+    torch.manual_seed(42)
+    mc = nerf.FlexibleNeRFModel(8, 256, 4, 10, 4)
+    mf = nerf.FlexibleNeRFModel(8, 256, 4, 10, 4)
+    with torch.no_grad():                # random init gives sigma ~ 0; make the field absorb
+        for m in (mc, mf):
+            m.fc_alpha.weight.mul_(150.0)
+            m.fc_alpha.bias.fill_(2.0)
+    sdc = {k: v.detach().clone() for k, v in mc.state_dict().items()}
+    sdf = {k: v.detach().clone() for k, v in mf.state_dict().items()}
+    T = O.pose_spherical_world2cam(30.0, -30.0, 4.0)
+    K = torch.tensor([[1111.1, 0, 400.0], [0, 1111.1, 400.0], [0, 0, 1]])
+    ro, rd = nerf.get_ray_bundle(800, 800, None, T.cuda(), K.cuda(), row_start=400, row_count=1)
+    ro, rd = ro[:, 272:528].contiguous(), rd[:, 272:528].contiguous()
+    thr = [float(m) for m in range(5, 105, 5)]
+    res = nerf.run_one_iter_of_nerf(800, 800, 1111.1, mc.cuda(), mf.cuda(), ro, rd, make_cfg(64, 128, 2.0, 6.0),
+                                    mode="validation",
+                                    encode_position_fn=nerf.get_embedding_function(10, True, True),
+                                    encode_direction_fn=nerf.get_embedding_function(4, True, True),
+                                    m_thres_cand=thr)
+    opts = O.RenderOptions(near=2.0, far=6.0, num_coarse=64, num_fine=128, Lx=10, Ld=4)
+    ref = O.render_rays(ro.cpu(), rd.cpu(), lambda x: O.flexible_forward(sdc, x), lambda x: O.flexible_forward(sdf, x),
+                        opts, thr)
+    for a, b in zip(res[:6], ref[:6]):
+        close(a.reshape(b.shape), b, 2e-3, 2e-4)
+    dex = torch.stack(res[6:], 0).reshape(20, -1).cpu()
+    rdex = torch.stack(ref[6:], 0)
+    assert (dex == rdex).float().mean() > 0.95
+    assert float(res[5].mean()) > 0.05       # the field does absorb

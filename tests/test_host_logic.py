@@ -1,0 +1,163 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol the header
+declares, the Python namespace mirrors the reference's, models lower to the right layer programs
+and initialise exactly like the reference's classes, and nothing falls back to the CPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import nerf
+from nerf import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "dexnerf.h")).read()
+    declared = sorted(set(re.findall(r"DEXNERF_API\s+[\w\s\*]+?\b(dexnerf_\w+)\s*\(", hdr)))
+    assert len(declared) >= 15
+    handle = ctypes.CDLL(L.LIB_PATH)
+    for name in declared:
+        assert hasattr(handle, name), name
+    assert sorted(L._SIGS) == declared          # the ctypes table binds exactly the header
+    assert L.lib().dexnerf_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(L.Op) == 48
+    assert ctypes.sizeof(L.Program) == 48 + 48 * L.MAX_OPS
+    assert ctypes.sizeof(L.FlexibleSpec) == 48
+
+
+def test_namespace_matches_reference():
+    # names the reference scripts import (train_dexnerf_rgb.py:15-19, tiny_nerf.py:9)
+    for name in ["CfgNode", "get_embedding_function", "get_ray_bundle", "img2mse", "meshgrid_xy", "models",
+                 "mse2psnr", "run_one_iter_of_nerf", "cumprod_exclusive", "get_minibatches",
+                 "positional_encoding", "sample_pdf", "volume_render_radiance_field", "ndc_rays",
+                 "predict_and_render_radiance", "run_network", "FlexibleNeRFModel", "PaperNeRFModel"]:
+        assert hasattr(nerf, name), name
+    assert nerf.sample_pdf is nerf.sample_pdf_2      # the re-binding must be kept
+    for cls in ["VeryTinyNeRFModel", "MultiHeadNeRFModel", "ReplicateNeRFModel", "PaperNeRFModel",
+                "FlexibleNeRFModel"]:
+        assert isinstance(getattr(nerf.models, cls)(), torch.nn.Module)
+
+
+def test_no_cpu_fallback():
+    with pytest.raises(ValueError):
+        nerf.positional_encoding(torch.zeros(4, 3))
+    with pytest.raises(ValueError):
+        nerf.cumprod_exclusive(torch.ones(2, 3))
+    with pytest.raises(ValueError):
+        nerf.sample_pdf(torch.zeros(2, 5), torch.zeros(2, 4), 8, det=True)
+    with pytest.raises(ValueError):
+        nerf.volume_render_radiance_field(torch.zeros(2, 3, 4), torch.zeros(2, 3), torch.zeros(2, 3),
+                                          m_thres_cand=[5.0])
+    with pytest.raises(ValueError):
+        nerf.FlexibleNeRFModel()(torch.zeros(3, 66))
+    with pytest.raises(TypeError):     # the reference iterates over None (volume_rendering_utils.py:53)
+        nerf.volume_render_radiance_field(torch.zeros(2, 3, 4), torch.zeros(2, 3), torch.zeros(2, 3))
+
+
+def _digest(module):
+    acc, k = 0.0, 1
+    for _, p in module.state_dict().items():
+        v = p.detach().double().flatten()
+        acc += float((v * torch.arange(1, v.numel() + 1, dtype=torch.float64)).sum()) * k
+        k += 1
+    return acc
+
+
+def test_models_initialise_like_the_reference(golden):
+    g = golden("models")
+    torch.manual_seed(42)
+    m = nerf.FlexibleNeRFModel(num_layers=8, hidden_size=256, skip_connect_every=4,
+                               num_encoding_fn_xyz=10, num_encoding_fn_dir=4)
+    assert list(m.state_dict().keys()) == g["flex8x256_keys"].tolist()
+    assert sum(p.numel() for p in m.parameters()) == int(g["flex8x256_nparams"]) == 595844
+    assert _digest(m) == float(g["flex8x256_digest"])
+    torch.manual_seed(42)
+    m = nerf.FlexibleNeRFModel(num_layers=8, hidden_size=128, skip_connect_every=3,
+                               num_encoding_fn_xyz=10, num_encoding_fn_dir=4)
+    assert _digest(m) == float(g["flex8x128s3_digest"])
+    torch.manual_seed(42)
+    m = nerf.FlexibleNeRFModel(num_encoding_fn_xyz=10, num_encoding_fn_dir=4)
+    assert _digest(m) == float(g["flex4x128_digest"])
+    torch.manual_seed(42)
+    m = nerf.PaperNeRFModel(num_encoding_fn_xyz=10, num_encoding_fn_dir=4)
+    assert list(m.state_dict().keys()) == g["paper_keys"].tolist()
+    assert _digest(m) == float(g["paper_digest"])
+    torch.manual_seed(42)
+    m = nerf.FlexibleNeRFModel(num_encoding_fn_xyz=6, num_encoding_fn_dir=4, use_viewdirs=False)
+    assert _digest(m) == float(g["flex_noview_digest"])
+
+
+def test_pretrained_checkpoint_keys_load(golden):
+    g = golden("lego_lowres")
+    m = nerf.FlexibleNeRFModel(num_encoding_fn_xyz=10, num_encoding_fn_dir=4)
+    sd = {k[len("coarse."):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("coarse.")}
+    m.load_state_dict(sd)   # strict: names and shapes are the compat contract
+
+
+def test_program_lowering_flexible_8x256():
+    m = nerf.FlexibleNeRFModel(8, 256, 4, 10, 4)
+    p = m.program(nerf.get_embedding_function(10, True, True), nerf.get_embedding_function(4, True, True))
+    ops = [p.ops[i] for i in range(p.n_ops)]
+    assert p.n_ops == 12 and p.dim_xyz == 63 and p.dim_dir == 27 and p.max_width == 256
+    assert (ops[0].src0, ops[0].relu, ops[0].out_dim) == (L.ENC_XYZ, 0, 256)        # layer1, no ReLU
+    skips = [i for i, o in enumerate(ops) if o.src1 == L.ENC_XYZ]
+    assert skips == [5] and ops[5].src0_dim == 256 and ops[5].src1_dim == 63       # layers_xyz[4] = cat(x, xyz)
+    assert ops[8].dst == L.OUT_SIGMA and ops[8].src0 == ops[9].src0                # alpha from the trunk
+    assert (ops[10].src1, ops[10].src1_dim, ops[10].out_dim) == (L.ENC_DIR, 27, 128)
+    assert ops[11].dst == L.OUT_RGB
+    macs = sum((o.src0_dim + o.src1_dim) * o.out_dim for o in ops)
+    assert macs == 593408
+    total = ops[-1].b_off + ops[-1].out_dim
+    assert total == 595844
+    assert (p.Lx, p.Ld, p.include_xyz, p.log_xyz) == (10, 4, 1, 1)
+
+
+def test_program_lowering_paper():
+    m = nerf.PaperNeRFModel(num_encoding_fn_xyz=10, num_encoding_fn_dir=4)
+    p = m.program()
+    ops = [p.ops[i] for i in range(p.n_ops)]
+    assert (ops[4].src0, ops[4].src1) == (L.ENC_XYZ, ops[3].dst)                   # cat((xyz, x))
+    macs = sum((o.src0_dim + o.src1_dim) * o.out_dim for o in ops)
+    assert macs == 626176                                                          # SURVEY.md section 8(a-3')
+    for o in ops:
+        assert o.dst != o.src0 and o.dst != o.src1
+
+
+def test_cfgnode_schema():
+    cfg = nerf.CfgNode({"experiment": {"id": "x"}, "models": {"coarse": {"type": "FlexibleNeRFModel"}},
+                        "nerf": {"use_viewdirs": True, "train": {"num_coarse": 64}, "validation": {"num_coarse": 64}}})
+    assert cfg.models.coarse.type == "FlexibleNeRFModel"
+    assert not hasattr(cfg.models, "fine") and hasattr(cfg.models, "coarse")
+    assert getattr(cfg.nerf, "train").num_coarse == 64
+    with pytest.raises(AttributeError):
+        cfg.nerf.nope
+    import yaml
+    assert yaml.safe_load(cfg.dump())["nerf"]["train"]["num_coarse"] == 64
+    assert getattr(nerf.models, cfg.models.coarse.type) is nerf.FlexibleNeRFModel
+
+
+def test_linspace_formula_matches_torch():
+    """The kernels rebuild torch.linspace in-register (csrc/common.cuh linspace_at); this pins the
+    formula they use against torch on the CPU."""
+    f32 = np.float32
+    for s, e, n in [(0, 1, 64), (0, 1, 128), (0, 1, 256), (0, 1, 24), (2, 6, 64), (0.3, 4, 64), (1, 32, 6), (0, 1, 17)]:
+        s32, e32 = f32(s), f32(e)
+        step = f32((e32 - s32) / f32(n - 1))
+        mine = np.array([f32(float(s32) + float(step) * i) if i < n // 2 else f32(float(e32) - float(step) * (n - 1 - i))
+                         for i in range(n)], dtype=f32)
+        assert np.array_equal(mine, torch.linspace(s, e, n, dtype=torch.float32).numpy()), (s, e, n)
+
+
+def test_meshgrid_and_helpers():
+    ii, jj = nerf.meshgrid_xy(torch.arange(3), torch.arange(4, 7))
+    a, b = np.meshgrid(np.arange(3), np.arange(4, 7), indexing="xy")
+    assert np.array_equal(ii.numpy(), a) and np.array_equal(jj.numpy(), b)
+    assert [c.shape[0] for c in nerf.get_minibatches(torch.zeros(10, 2), 4)] == [4, 4, 2]
+    assert nerf.mse2psnr(0) == 50.0
