@@ -48,8 +48,8 @@ _SIGS = {
     "dexnerf_mlp_forward": (C.c_int, [C.POINTER(Program), _P, _P, _L, _P, _P]),
     "dexnerf_mlp_query": (C.c_int, [C.POINTER(Program), _P, _P, _P, _P, _P, _L, _I, _P, _P]),
     "dexnerf_tc_packed_bytes": (C.c_int64, [C.POINTER(FlexibleSpec)]),
-    "dexnerf_tc_pack": (C.c_int, [C.POINTER(FlexibleSpec), C.POINTER(Program), _P, _P, _P]),
-    "dexnerf_tc_query": (C.c_int, [C.POINTER(FlexibleSpec), _P, _P, _P, _P, _P, _L, _I, _P, _P]),
+    "dexnerf_tc_pack": (C.c_int, [C.POINTER(FlexibleSpec), C.POINTER(Program), _P, _P, _P, _P]),
+    "dexnerf_tc_query": (C.c_int, [C.POINTER(FlexibleSpec), _P, _P, _P, _P, _P, _L, _I, _P, _P, _I, _I, _P]),
 }
 
 _lib = None

@@ -127,15 +127,21 @@ typedef struct {
   int32_t dim_xyz, dim_dir, Lx, Ld, include_xyz, include_dir, log_xyz, log_dir;
   int32_t pad_;
 } dexnerf_flexible_spec;
-/* size in bytes of the packed weight blob for `spec` */
+/* size in bytes of the packed weight blob for `spec` (negative on error) */
 DEXNERF_API int64_t dexnerf_tc_packed_bytes(const dexnerf_flexible_spec* spec /*host*/);
+#define DEXNERF_TC_PACK_WORKSPACE_BYTES 16384
 /* params: the fp32 program-layout buffer of the same model (as for dexnerf_mlp_query);
- * prog: the program it was built from.  packed: device blob of dexnerf_tc_packed_bytes(). */
+ * prog: the program it was built from.  packed: device blob of dexnerf_tc_packed_bytes();
+ * workspace: device scratch of DEXNERF_TC_PACK_WORKSPACE_BYTES.  Packing is the one entry point
+ * that synchronises the stream (once, to hand a small host table to the device). */
 DEXNERF_API int dexnerf_tc_pack(const dexnerf_flexible_spec* spec, const dexnerf_mlp_program* prog,
-                    const float* params, void* packed, void* stream);
+                    const float* params, void* packed, void* workspace, void* stream);
+/* run_network on tensor cores: ro, rd, viewdirs (n,3), z (n,S) -> rf (n,S,4).
+ * dbg (optional, may be NULL): raw fp32 accumulator of (dbg_layer, dbg_pass), [n*S rounded up to
+ * 128][128] floats - used by the kernel's own tests. */
 DEXNERF_API int dexnerf_tc_query(const dexnerf_flexible_spec* spec, const void* packed, const float* ro,
                      const float* rd, const float* viewdirs, const float* z, int64_t n, int S,
-                     float* rf, void* stream);
+                     float* rf, float* dbg, int dbg_layer, int dbg_pass, void* stream);
 
 #ifdef __cplusplus
 }

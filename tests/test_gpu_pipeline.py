@@ -132,8 +132,11 @@ def test_lego_checkpoint(golden):
     for name, v in zip(NAMES, res[:6]):
         close(v, g[name], 1e-3, 1e-4)
     dex = torch.stack(res[6:], 0).cpu().numpy()
-    assert (dex == g["dex"]).mean() > 0.97
-    close(dex, g["dex"], 0, 0.07)            # a flipped sample index moves the depth by one spacing
+    # the fine depths themselves carry fp32 last-bit differences (they come from the coarse net's
+    # weights), so "same sample" means equal to a few ulp; a flipped index moves the depth by at
+    # most about one sample spacing
+    assert (np.abs(dex - g["dex"]) <= 2e-6 * np.abs(g["dex"]) + 1e-6).mean() > 0.97
+    close(dex, g["dex"], 0, 0.07)
 
 
 def test_generic_callable_path(golden):
