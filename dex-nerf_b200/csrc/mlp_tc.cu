@@ -142,6 +142,43 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// split-phase accumulator load: issue now, make the registers valid later with tmem_ld32_wait
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+// the registers are listed as read-write so that no use of them can be scheduled above the wait
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.wait::ld.sync.aligned;"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+        "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+        "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+        "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+      :: "memory");
+}
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.wait::ld.sync.aligned;"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+        "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+      :: "memory");
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
@@ -185,6 +222,12 @@ __device__ __forceinline__ uint32_t instr_desc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 }
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------------ shared-memory map
 struct Smem {
   // offsets from the 1024-aligned base
@@ -208,8 +251,62 @@ __device__ __forceinline__ int B_dfree(int t) { return 2 * kNumSlots + 12 + t; }
 
 __device__ __forceinline__ int chunks_in_pass(const TcLayer& L) { return L.k_main / 64 + (L.smem_src ? 1 : 0); }
 
+// One epilogue pass over the 128-column accumulator of a tile (one thread per sample row):
+// + bias, optional sigma head, optional ReLU, pack to bf16, then either keep the packed words in
+// registers (first pass of a 256-wide layer) or store them as the next layer's A operand.
+template <int H, bool kRelu, bool kSig, bool kHold, bool kPark, bool kDbg>
+__device__ __forceinline__ void epilogue_pass(uint32_t d_tmem, uint32_t a_tmem, uint32_t a_col0, const float* bias,
+                                              const float* wa, float& sigma, uint32_t (&held)[H / 4],
+                                              uint32_t dfree_bar, float* dbg_dst) {
+  uint32_t v[2][16];      // double-buffered 16-column slices of the accumulator
+  tmem_ld16_issue(d_tmem, v[0]);
+  if (kPark) {
+    // the old A is dead now: park the first pass's half of the new A
+#pragma unroll
+    for (int j = 0; j < H / 64; ++j) tmem_st16(a_tmem + (uint32_t)(j * 16), &held[j * 16]);
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {     // 8 x 16 columns; unrolled so held[] has static indices
+    tmem_ld16_wait(v[c & 1]);
+    if (c + 1 < 8) tmem_ld16_issue(d_tmem + (uint32_t)((c + 1) * 16), v[(c + 1) & 1]);
+    if (kDbg && dbg_dst) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) dbg_dst[c * 16 + i] = __uint_as_float(v[c & 1][i]);
+    }
+    uint32_t pk[8];
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(bias + c * 16 + i);
+      const float x0 = __uint_as_float(v[c & 1][i]) + b4.x;
+      const float x1 = __uint_as_float(v[c & 1][i + 1]) + b4.y;
+      const float x2 = __uint_as_float(v[c & 1][i + 2]) + b4.z;
+      const float x3 = __uint_as_float(v[c & 1][i + 3]) + b4.w;
+      if (kSig) {   // fc_alpha on the rectified, unrounded trunk output
+        const float4 w4 = *reinterpret_cast<const float4*>(wa + c * 16 + i);
+        sigma = fmaf(fmaxf(x0, 0.0f), w4.x, sigma);
+        sigma = fmaf(fmaxf(x1, 0.0f), w4.y, sigma);
+        sigma = fmaf(fmaxf(x2, 0.0f), w4.z, sigma);
+        sigma = fmaf(fmaxf(x3, 0.0f), w4.w, sigma);
+      }
+      if (kHold) {
+        held[c * 8 + i / 2] = pack_bf16(x0, x1, kRelu);
+        held[c * 8 + i / 2 + 1] = pack_bf16(x2, x3, kRelu);
+      } else {
+        pk[i / 2] = pack_bf16(x0, x1, kRelu);
+        pk[i / 2 + 1] = pack_bf16(x2, x3, kRelu);
+      }
+    }
+    if (!kHold) tmem_st8(a_tmem + a_col0 + (uint32_t)(c * 8), pk);
+    if (c == 7) {
+      // accumulator fully read (the last wait::ld covered it): release it early
+      tc_fence_before();
+      mbar_arrive(dfree_bar);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ the kernel
-template <int H>
+template <int H, bool kDbg>
 __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -245,91 +342,126 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + Smem::tmem_ptr);
   const float* s_const = reinterpret_cast<const float*>(smem + Smem::consts);
 
-  // register budget per warpgroup (512 threads x 128 at launch): 96 / 160 / 160 / 96.
+  // register budget per warpgroup (512 threads x 128 at launch): 104 / 152 / 152 / 104.
   // Each setmaxnreg sits at the top of its role branch so that ptxas scopes the budget to it.
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
   if (warp == 0) {
     // =============================== weight producer ===============================
-    if (lane == 0) {
-      uint32_t cnt = 0;
-      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-        const uint8_t* src = P.weights;
-        for (int l = 0; l < P.n_layers; ++l) {
-          const TcLayer& L = P.layers[l];
-          const int np = L.n_out < 128 ? L.n_out : 128;
-          for (int p = 0; p < L.n_pass; ++p) {
-            const int nc = chunks_in_pass(L);
-            for (int c = 0; c < nc; ++c, ++cnt) {
-              const int kc = (c < L.k_main / 64) ? 64 : L.k_smem;
-              const uint32_t bytes = (uint32_t)(np * kc * 2);
-              const uint32_t slot = cnt % kNumSlots, ph = (cnt / kNumSlots) & 1;
-              mbar_wait(bar(B_wempty(slot)), ph ^ 1, 0);
+    const bool leader = elect_one();
+    uint32_t cnt = 0;
+#pragma unroll 1
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      const uint8_t* src = P.weights;
+#pragma unroll 1
+      for (int l = 0; l < P.n_layers; ++l) {
+        const TcLayer& L = P.layers[l];
+        const int np = L.n_out < 128 ? L.n_out : 128;
+        const int nc = chunks_in_pass(L);
+#pragma unroll 1
+        for (int p = 0; p < L.n_pass; ++p) {
+#pragma unroll 1
+          for (int c = 0; c < nc; ++c, ++cnt) {
+            const int kc = (c < L.k_main / 64) ? 64 : L.k_smem;
+            const uint32_t bytes = (uint32_t)(np * kc * 2);
+            const uint32_t slot = cnt % kNumSlots, ph = (cnt / kNumSlots) & 1;
+            mbar_wait(bar(B_wempty(slot)), ph ^ 1, 0);
+            if (leader) {
               mbar_arrive_expect_tx(bar(B_wfull(slot)), bytes);
               bulk_g2s(sbase + Smem::w_slots + slot * kSlotBytes, src, bytes, bar(B_wfull(slot)));
-              src += bytes;
             }
+            __syncwarp();
+            src += bytes;
           }
         }
       }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      uint32_t wcnt[2] = {0, 0};
-      uint32_t ph_dfree[2] = {0, 0}, ph_aready[2] = {0, 0};
-      uint32_t it = 0;
-      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const uint32_t pe_ph = (it >> 1) & 1;
-        for (int l = 0; l < P.n_layers; ++l) {
-          const TcLayer& L = P.layers[l];
-          const int np = L.n_out < 128 ? L.n_out : 128;
-          const uint32_t idesc = instr_desc(np);
-          const int n_main = L.k_main / 64;
-          for (int p = 0; p < L.n_pass; ++p) {
+    // The whole warp runs the (warp-uniform) control flow so that descriptors stay cheap to form;
+    // only the asynchronous instructions themselves are issued by one elected lane.  Tile 1 reuses
+    // the weight chunks tile 0 has just waited for (they stay resident until both tiles have
+    // committed), so only tile 0 polls the weight barriers.
+    const bool leader = elect_one();
+    uint32_t w_slot = 0, w_phase = 0;           // ring cursor of tile 0 (tile 1 trails by one pass)
+    uint32_t ph_dfree[2] = {0, 0}, ph_aready[2] = {0, 0};
+    uint32_t it = 0;
+    const uint64_t desc_hi = ((uint64_t)(128 >> 4) << 32) | (1ull << 46);   // SBO = 128 B, version 1
+    const uint32_t slot0_lo = ((sbase + Smem::w_slots) >> 4) & 0x3FFF;      // 16-byte units
+    constexpr int kMain = H / 64;               // 64-wide K chunks of a hidden-activation operand
+#pragma unroll 1
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t pe_ph = (it >> 1) & 1;
+#pragma unroll 1
+      for (int l = 0; l < P.n_layers; ++l) {
+        const TcLayer& L = P.layers[l];
+        const int np = L.n_out < 128 ? L.n_out : 128;
+        const uint32_t idesc = instr_desc(np);
+        const bool has_main = L.k_main != 0;
+        const uint32_t b_lbo16 = (uint32_t)np;            // LBO = np*16 bytes -> np in 16-byte units
+        const bool timing = kDbg && P.dbg_layer == -2 && blockIdx.x == 0 && it == 0 && leader;
+#pragma unroll 1
+        for (int p = 0; p < L.n_pass; ++p) {
+          const uint32_t slot_p = w_slot, phase_p = w_phase;   // first chunk of this pass
 #pragma unroll
-            for (int t = 0; t < 2; ++t) {
-              const uint32_t a_tmem = tmem_base + (uint32_t)(t * 256);
-              const uint32_t d_tmem = a_tmem + 128;
-              // the accumulator must have been drained by the previous epilogue pass of this tile
-              mbar_wait(bar(B_dfree(t)), ph_dfree[t] ^ 1, 1);
-              ph_dfree[t] ^= 1;
-              if (p == 0) {
-                if (l == 0) mbar_wait(bar(B_pefull(t, buf)), pe_ph, 2);
-                else { mbar_wait(bar(B_aready(t)), ph_aready[t], 3); ph_aready[t] ^= 1; }
-              }
-              tc_fence_after();
-              const int nc = n_main + (L.smem_src ? 1 : 0);
-              for (int c = 0; c < nc; ++c) {
-                const uint32_t slot = wcnt[t] % kNumSlots, ph = (wcnt[t] / kNumSlots) & 1;
-                ++wcnt[t];
-                mbar_wait(bar(B_wfull(slot)), ph, 4);
-                tc_fence_after();
-                const uint32_t b_addr = sbase + Smem::w_slots + slot * kSlotBytes;
-                const uint32_t b_lbo = (uint32_t)np * 16;
-                if (c < n_main) {
+          for (int t = 0; t < 2; ++t) {
+            const uint32_t a_tmem = tmem_base + (uint32_t)(t * 256);
+            const uint32_t d_tmem = a_tmem + 128;
+            // the accumulator must have been drained by the previous epilogue pass of this tile
+            mbar_wait(bar(B_dfree(t)), ph_dfree[t] ^ 1, 1);
+            ph_dfree[t] ^= 1;
+            if (p == 0) {
+              if (l == 0) mbar_wait(bar(B_pefull(t, buf)), pe_ph, 2);
+              else { mbar_wait(bar(B_aready(t)), ph_aready[t], 3); ph_aready[t] ^= 1; }
+            }
+            tc_fence_after();
+            if (timing) reinterpret_cast<long long*>(P.dbg)[((l * 2 + p) * 2 + t) * 2] = clock64();
+            uint32_t slot = slot_p, phase = phase_p;
+            if (has_main) {
 #pragma unroll
-                  for (int ks = 0; ks < 4; ++ks) {
-                    const uint64_t bd = smem_desc(b_addr + (uint32_t)ks * 2 * b_lbo, b_lbo, 128);
-                    mma_ts(d_tmem, a_tmem + (uint32_t)(c * 32 + ks * 8), bd, idesc, (c | ks) ? 1u : 0u);
-                  }
-                } else {
-                  const uint32_t a_addr = (L.smem_src == 1)
-                      ? sbase + Smem::pe_xyz + (uint32_t)(t * 2 + buf) * kPeXyzBytes
-                      : sbase + Smem::pe_dir + (uint32_t)(t * 2 + buf) * kPeDirBytes;
-                  const uint32_t a_lbo = kTileM * 16;
-                  for (int ks = 0; ks < L.k_smem / 16; ++ks) {
-                    const uint64_t ad = smem_desc(a_addr + (uint32_t)ks * 2 * a_lbo, a_lbo, 128);
-                    const uint64_t bd = smem_desc(b_addr + (uint32_t)ks * 2 * b_lbo, b_lbo, 128);
-                    mma_ss(d_tmem, ad, bd, idesc, (c | ks) ? 1u : 0u);
-                  }
+              for (int c = 0; c < kMain; ++c) {
+                if (t == 0) { mbar_wait(bar(B_wfull(slot)), phase, 4); tc_fence_after(); }
+                // descriptor low word: address (16-byte units) | LBO << 16; K-step advance = 2*LBO
+                const uint32_t b_lo = (slot0_lo + slot * (kSlotBytes >> 4)) | (b_lbo16 << 16);
+                if (leader) {
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks)
+                    mma_ts(d_tmem, a_tmem + (uint32_t)(c * 32 + ks * 8),
+                           desc_hi | (uint64_t)(b_lo + (uint32_t)ks * 2 * b_lbo16), idesc, (c | ks) ? 1u : 0u);
+                  tc_commit(bar(B_wempty(slot)));   // slot is refilled once both tiles' MMAs retire
                 }
-                tc_commit(bar(B_wempty(slot)));   // slot may be refilled once these MMAs retire
+                __syncwarp();
+                if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
               }
+            }
+            if (L.smem_src) {
+              if (t == 0) { mbar_wait(bar(B_wfull(slot)), phase, 4); tc_fence_after(); }
+              const uint32_t b_lo = (slot0_lo + slot * (kSlotBytes >> 4)) | (b_lbo16 << 16);
+              const uint32_t a_addr = (L.smem_src == 1)
+                  ? sbase + Smem::pe_xyz + (uint32_t)(t * 2 + buf) * kPeXyzBytes
+                  : sbase + Smem::pe_dir + (uint32_t)(t * 2 + buf) * kPeDirBytes;
+              const uint32_t a_lo = ((a_addr >> 4) & 0x3FFF) | ((uint32_t)kTileM << 16);   // LBO = 128*16 B
+              if (leader) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  if (ks * 16 < L.k_smem)
+                    mma_ss(d_tmem, desc_hi | (uint64_t)(a_lo + (uint32_t)ks * 2 * kTileM),
+                           desc_hi | (uint64_t)(b_lo + (uint32_t)ks * 2 * b_lbo16), idesc,
+                           (has_main || ks) ? 1u : 0u);
+                }
+                tc_commit(bar(B_wempty(slot)));
+              }
+              __syncwarp();
+              if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
+            }
+            if (leader) {
               tc_commit(bar(B_dfull(t)));
               if (l == P.n_layers - 1 && p == L.n_pass - 1) tc_commit(bar(B_peempty(t, buf)));
             }
+            __syncwarp();
+            if (timing) reinterpret_cast<long long*>(P.dbg)[((l * 2 + p) * 2 + t) * 2 + 1] = clock64();
+            if (t == 1) { w_slot = slot; w_phase = phase; }
           }
         }
       }
@@ -337,14 +469,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
   }
   } else if (warp < 12) {
     // =============================== epilogue ===============================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
     const int t = (warp - 4) >> 2, q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const uint32_t a_tmem = tmem_base + (uint32_t)(t * 256) + lane_base;
     const uint32_t d_tmem = a_tmem + 128;
+    const bool timing = kDbg && P.dbg_layer == -2 && blockIdx.x == 0 && q == 0 && lane == 0;
+    long long* tl = reinterpret_cast<long long*>(P.dbg);
     uint32_t ph_dfull = 0;
     uint32_t held[H / 4];   // first-pass results of a 2-pass layer (H/2 bf16 = H/4 words)
+    uint32_t v[2][16];
 #pragma unroll 1
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       const int64_t g = (pair * 2 + t) * kTileM + row;
@@ -357,29 +492,39 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
           mbar_wait(bar(B_dfull(t)), ph_dfull, 5);
           ph_dfull ^= 1;
           tc_fence_after();
+          if (timing && pair == blockIdx.x) tl[256 + ((l * 2) * 2 + t) * 2] = clock64();
           float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
           const float* bias = s_const + L.bias_off;
           const float* wr = s_const + P.off_wrgb;
           constexpr int hw = H / 2;
-#pragma unroll 1
+          tmem_ld16_issue(d_tmem, v[0]);
+#pragma unroll
           for (int c = 0; c < hw / 16; ++c) {
-            float v[16];
-            tmem_ld16(d_tmem + (uint32_t)(c * 16), v);
-            if (P.dbg && l == P.dbg_layer && g < P.m_total) {
+            tmem_ld16_wait(v[c & 1]);
+            if (c + 1 < hw / 16) tmem_ld16_issue(d_tmem + (uint32_t)((c + 1) * 16), v[(c + 1) & 1]);
+            if (kDbg && l == P.dbg_layer && g < P.m_total) {
               float* dst = P.dbg + g * 128 + c * 16;
 #pragma unroll
-              for (int i = 0; i < 16; ++i) dst[i] = v[i];
+              for (int i = 0; i < 16; ++i) dst[i] = __uint_as_float(v[c & 1][i]);
             }
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float x = fmaxf(v[i] + bias[c * 16 + i], 0.0f);
-              rgb0 = fmaf(x, wr[c * 16 + i], rgb0);
-              rgb1 = fmaf(x, wr[hw + c * 16 + i], rgb1);
-              rgb2 = fmaf(x, wr[2 * hw + c * 16 + i], rgb2);
+            for (int i = 0; i < 16; i += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias + c * 16 + i);
+              const float4 r4 = *reinterpret_cast<const float4*>(wr + c * 16 + i);
+              const float4 g4 = *reinterpret_cast<const float4*>(wr + hw + c * 16 + i);
+              const float4 u4 = *reinterpret_cast<const float4*>(wr + 2 * hw + c * 16 + i);
+              const float x0 = fmaxf(__uint_as_float(v[c & 1][i]) + b4.x, 0.0f);
+              const float x1 = fmaxf(__uint_as_float(v[c & 1][i + 1]) + b4.y, 0.0f);
+              const float x2 = fmaxf(__uint_as_float(v[c & 1][i + 2]) + b4.z, 0.0f);
+              const float x3 = fmaxf(__uint_as_float(v[c & 1][i + 3]) + b4.w, 0.0f);
+              rgb0 = fmaf(x0, r4.x, fmaf(x1, r4.y, fmaf(x2, r4.z, fmaf(x3, r4.w, rgb0))));
+              rgb1 = fmaf(x0, g4.x, fmaf(x1, g4.y, fmaf(x2, g4.z, fmaf(x3, g4.w, rgb1))));
+              rgb2 = fmaf(x0, u4.x, fmaf(x1, u4.y, fmaf(x2, u4.z, fmaf(x3, u4.w, rgb2))));
             }
           }
           tc_fence_before();
           mbar_arrive(bar(B_dfree(t)));
+          if (timing && pair == blockIdx.x) tl[256 + ((l * 2) * 2 + t) * 2 + 1] = clock64();
           if (g < P.m_total) {
             const float* br = s_const + P.off_brgb;
             float4 o;
@@ -388,71 +533,43 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
             reinterpret_cast<float4*>(P.rf)[g] = o;
           }
         } else {
-          const bool relu = L.relu != 0;
-          const bool sig_head = L.head == 1;
+          const float* bias = s_const + L.bias_off;
+          const float* wa = s_const + P.off_walpha;
+          const int kind = L.relu ? (L.head == 1 ? 2 : 1) : 0;
 #pragma unroll
           for (int p = 0; p < H / 128; ++p) {
             mbar_wait(bar(B_dfull(t)), ph_dfull, 5);
             ph_dfull ^= 1;
             tc_fence_after();
+            if (timing && pair == blockIdx.x) tl[256 + ((l * 2 + p) * 2 + t) * 2] = clock64();
             constexpr bool kTwoPass = (H == 256);
-            const bool last_pass = (p == H / 128 - 1);
-            if (kTwoPass && last_pass) {
-              // the old A is dead now: park the first pass's half of the new A
-#pragma unroll
-              for (int j = 0; j < H / 64; ++j) tmem_st16(a_tmem + (uint32_t)(j * 16), &held[j * 16]);
-            }
-            const float* bias = s_const + L.bias_off + p * 128;
-            const float* wa = s_const + P.off_walpha + p * 128;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {     // 8 x 16 columns; unrolled so held[] has static indices
-              float v[16];
-              tmem_ld16(d_tmem + (uint32_t)(c * 16), v);
-              if (P.dbg && l == P.dbg_layer && p == P.dbg_pass && g < P.m_total) {
-                float* dst = P.dbg + g * 128 + c * 16;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) dst[i] = v[i];
-              }
-#pragma unroll
-              for (int i = 0; i < 16; i += 4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(bias + c * 16 + i);
-                v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
-              }
-              if (sig_head) {   // fc_alpha on the rectified, unrounded trunk output
-#pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                  const float4 w4 = *reinterpret_cast<const float4*>(wa + c * 16 + i);
-                  sigma = fmaf(fmaxf(v[i], 0.0f), w4.x, sigma);
-                  sigma = fmaf(fmaxf(v[i + 1], 0.0f), w4.y, sigma);
-                  sigma = fmaf(fmaxf(v[i + 2], 0.0f), w4.z, sigma);
-                  sigma = fmaf(fmaxf(v[i + 3], 0.0f), w4.w, sigma);
-                }
-              }
-              if (kTwoPass && !last_pass) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) held[c * 8 + i] = pack_bf16(v[2 * i], v[2 * i + 1], relu);
-              } else {
-                uint32_t pk[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1], relu);
-                tmem_st8(a_tmem + (uint32_t)(p * 64 + c * 8), pk);
-              }
-            }
-            // accumulator drained
-            tc_fence_before();
-            mbar_arrive(bar(B_dfree(t)));
-            if (last_pass) {
+            const bool hold = kTwoPass && p == 0;
+            float* dbg_dst = (kDbg && P.dbg_layer == l && P.dbg_pass == p && g < P.m_total) ? P.dbg + g * 128 : nullptr;
+            const float* bp = bias + p * 128;
+            const float* wp = wa + p * 128;
+            const uint32_t dfree = bar(B_dfree(t));
+            if (hold) {
+              if (kind == 0) epilogue_pass<H, false, false, true, false, kDbg>(d_tmem, a_tmem, 0, bp, wp, sigma, held, dfree, dbg_dst);
+              else if (kind == 1) epilogue_pass<H, true, false, true, false, kDbg>(d_tmem, a_tmem, 0, bp, wp, sigma, held, dfree, dbg_dst);
+              else epilogue_pass<H, true, true, true, false, kDbg>(d_tmem, a_tmem, 0, bp, wp, sigma, held, dfree, dbg_dst);
+            } else {
+              constexpr bool park = kTwoPass;
+              const uint32_t col0 = (uint32_t)(p * 64);
+              if (kind == 0) epilogue_pass<H, false, false, false, park, kDbg>(d_tmem, a_tmem, col0, bp, wp, sigma, held, dfree, dbg_dst);
+              else if (kind == 1) epilogue_pass<H, true, false, false, park, kDbg>(d_tmem, a_tmem, col0, bp, wp, sigma, held, dfree, dbg_dst);
+              else epilogue_pass<H, true, true, false, park, kDbg>(d_tmem, a_tmem, col0, bp, wp, sigma, held, dfree, dbg_dst);
               tmem_wait_st();
               tc_fence_before();
               mbar_arrive(bar(B_aready(t)));
             }
+            if (timing && pair == blockIdx.x) tl[256 + ((l * 2 + p) * 2 + t) * 2 + 1] = clock64();
           }
         }
       }
     }
   } else {
     // =============================== encoders ===============================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
     const int row = (warp - 12) * 32 + lane;
     uint32_t it = 0;
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++it) {
@@ -693,13 +810,15 @@ extern "C" DEXNERF_API int dexnerf_tc_query(const dexnerf_flexible_spec* spec, c
   const int grid = (int)(n_pairs < kNumSMs ? n_pairs : kNumSMs);
   const size_t smem = Smem::total + 1024;
   cudaStream_t st = (cudaStream_t)stream;
-  if (spec->hidden == 256) {
-    DN_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mlp_tc_kernel<256><<<grid, kThreads, smem, st>>>(P);
-  } else {
-    DN_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mlp_tc_kernel<128><<<grid, kThreads, smem, st>>>(P);
-  }
+  auto launch = [&](auto kernel) -> int {
+    DN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<grid, kThreads, smem, st>>>(P);
+    return 0;
+  };
+  int rc;
+  if (spec->hidden == 256) rc = dbg ? launch(mlp_tc_kernel<256, true>) : launch(mlp_tc_kernel<256, false>);
+  else rc = dbg ? launch(mlp_tc_kernel<128, true>) : launch(mlp_tc_kernel<128, false>);
+  if (rc) return rc;
   DN_CHECK_LAUNCH("mlp_tc");
   return 0;
 }

@@ -1,0 +1,59 @@
+"""Pipeline timeline of the tcgen05 MLP kernel (block 0, first tile pair): SM-clock stamps of each
+MMA pass issue window and each epilogue pass, dumped through the kernel's timing tap
+(dbg_layer = -2).  Run on the GPU box:  python tests/tc_timeline.py [n_rays] [S]"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "dex-nerf_b200"))
+
+import nerf  # noqa: E402
+from nerf import tensorcore  # noqa: E402
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 148 * 16
+    S = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+    torch.manual_seed(1)
+    model = nerf.FlexibleNeRFModel(8, 256, 4, 10, 4).cuda()
+    ex, ed = nerf.get_embedding_function(10, True, True), nerf.get_embedding_function(4, True, True)
+    prog = model.program(ex, ed)
+    g = torch.Generator().manual_seed(0)
+    ro = (torch.randn(n, 3, generator=g) * 0.3).cuda()
+    rd = torch.randn(n, 3, generator=g).cuda()
+    vd = rd / rd.norm(dim=-1, keepdim=True)
+    z = torch.sort(2 + 4 * torch.rand(n, S, generator=g), dim=-1).values.cuda()
+    rf = torch.empty(n, S, 4, device="cuda")
+    for _ in range(2):
+        tensorcore.query(model, prog, ro, rd, vd, z, rf)
+    tl = torch.zeros(1024, dtype=torch.int64, device="cuda")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    tensorcore.query(model, prog, ro, rd, vd, z, rf, dbg=tl.view(torch.float32), dbg_layer=-2)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    tiles = (n * S + 127) // 128
+    print("kernel %.3f ms for %d samples (%d tiles, %.1f pairs/SM): %.2f ns/sample, %.1f TFLOP/s"
+          % (ms, n * S, tiles, tiles / 2 / 148, ms * 1e6 / (n * S), n * S * 1186816 / ms / 1e9))
+    t = tl.cpu().tolist()
+    t0 = min(x for x in t[:512] if x > 0)
+    print("layer pass tile |  mma_start  mma_end (issue) |  epi_start  epi_end | epi_len  gap(epi_start - mma_end)")
+    for l in range(10):
+        for p in range(2):
+            for tile in range(2):
+                i = ((l * 2 + p) * 2 + tile) * 2
+                ms_, me_, es_, ee_ = t[i], t[i + 1], t[256 + i], t[256 + i + 1]
+                if ms_ == 0:
+                    continue
+                print("%5d %4d %4d | %10d %9d | %10d %8d | %7d %6d"
+                      % (l, p, tile, ms_ - t0, me_ - t0, es_ - t0, ee_ - t0, ee_ - es_, es_ - me_))
+    last = max(t[256:512])
+    print("pair span: %d cycles (MMA floor for 2 tiles: 37120)" % (last - t0))
+
+
+if __name__ == "__main__":
+    main()
