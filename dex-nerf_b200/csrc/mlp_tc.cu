@@ -6,7 +6,7 @@
 // tensor pipe always has an MMA pass of one tile to run while the other tile is in its epilogue:
 //
 //   warp 0        weight producer: streams pre-packed bf16 UMMA weight images (<=16 KB chunks,
-//                 128 out-features x 64 in-features) from L2 into a 6-slot shared-memory ring with
+//                 128 out-features x 64 in-features) from L2 into a 9-slot shared-memory ring with
 //                 cp.async.bulk (TMA bulk copy, mbarrier complete_tx); each chunk is consumed by
 //                 both tiles before the slot is recycled.
 //   warp 1        MMA issuer: one thread issues tcgen05.mma (M=128, N=128, K=16).  Hidden
@@ -38,13 +38,14 @@ namespace tc {
 
 constexpr int kTileM = 128;
 constexpr int kSlotBytes = 16384;
-constexpr int kNumSlots = 6;
+constexpr int kNumSlots = 9;
 constexpr int kMaxLayers = 16;
-constexpr int kThreads = 512;
+constexpr int kThreads = 768;   // 4 control warps + 16 epilogue warps + 4 encoder warps
+constexpr int kEpiThreadsPerTile = 256;
 constexpr int kPeXyzBytes = kTileM * 64 * 2;  // 16 KB, K padded to 64
 constexpr int kPeDirBytes = kTileM * 32 * 2;  // 8 KB,  K padded to 32
 constexpr int kMaxConstFloats = 4096;
-constexpr uint32_t kSpinLimit = 1u << 28;
+constexpr uint32_t kSpinLimit = 1u << 22;   // ~ a second of polling, then trap
 
 struct TcLayer {
   int k_main;    // K read from the TMEM-resident activations (0 for layer1)
@@ -65,7 +66,7 @@ struct TcParams {
   float* dbg;              // optional: raw accumulator dump of (dbg_layer, dbg_pass), [tile][128][128]
   int64_t m_total;
   int S;
-  int n_layers, hidden, n_const;
+  int n_layers, hidden, n_const, last_xyz_layer;
   int off_walpha, off_balpha, off_wrgb, off_brgb;
   int Lx, Ld, include_xyz, include_dir, log_xyz, log_dir, dim_xyz, dim_dir;
   int dbg_layer, dbg_pass;
@@ -104,6 +105,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int who
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > kSpinLimit) barrier_timeout(who);
   }
+}
+// Four barrier polls issued back to back (their ~100-cycle latencies overlap); falls back to the
+// bounded sequential wait when any of them is not complete yet.
+__device__ __forceinline__ void mbar_wait4(uint32_t b0, uint32_t p0, uint32_t b1, uint32_t p1, uint32_t b2,
+                                           uint32_t p2, uint32_t b3, uint32_t p3, int who) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred q0, q1, q2, q3;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 q0, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 q1, [%3], %4;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 q2, [%5], %6;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 q3, [%7], %8;\n\t"
+      "and.pred q0, q0, q1;\n\tand.pred q2, q2, q3;\n\tand.pred q0, q0, q2;\n\t"
+      "selp.u32 %0, 1, 0, q0;\n\t}"
+      : "=r"(ok) : "r"(b0), "r"(p0), "r"(b1), "r"(p1), "r"(b2), "r"(p2), "r"(b3), "r"(p3) : "memory");
+  if (!ok) { mbar_wait(b0, p0, who); mbar_wait(b1, p1, who); mbar_wait(b2, p2, who); mbar_wait(b3, p3, who); }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -170,14 +187,33 @@ __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr) : "memory");
+      : "r"(taddr));
+}
+// Same, but also lists the slice that is about to be processed as read-write: every use of `cur`
+// is then ordered AFTER this load has been issued, so its latency overlaps the arithmetic on `cur`
+// (the compiler would otherwise sink the issue below the arithmetic to save registers).
+__device__ __forceinline__ void tmem_ld16_issue_tied(uint32_t taddr, uint32_t (&r)[16], uint32_t (&cur)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "+r"(cur[0]), "+r"(cur[1]), "+r"(cur[2]), "+r"(cur[3]), "+r"(cur[4]), "+r"(cur[5]), "+r"(cur[6]), "+r"(cur[7]),
+        "+r"(cur[8]), "+r"(cur[9]), "+r"(cur[10]), "+r"(cur[11]), "+r"(cur[12]), "+r"(cur[13]), "+r"(cur[14]), "+r"(cur[15])
+      : "r"(taddr));
+}
+// read-only constants (biases, head weights) straight from shared memory; not volatile, so the
+// compiler may hoist these loads above the TMEM waits
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
 }
 __device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.wait::ld.sync.aligned;"
       : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-        "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-      :: "memory");
+        "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
   asm volatile(
@@ -232,10 +268,11 @@ __device__ __forceinline__ bool elect_one() {
 struct Smem {
   // offsets from the 1024-aligned base
   static constexpr int w_slots = 0;
-  static constexpr int pe_xyz = w_slots + kNumSlots * kSlotBytes;        // [tile][buf]
-  static constexpr int pe_dir = pe_xyz + 4 * kPeXyzBytes;                // [tile][buf]
-  static constexpr int consts = pe_dir + 4 * kPeDirBytes;
-  static constexpr int bars = consts + kMaxConstFloats * 4;
+  static constexpr int pe_xyz = w_slots + kNumSlots * kSlotBytes;        // [tile]
+  static constexpr int pe_dir = pe_xyz + 2 * kPeXyzBytes;                // [tile]
+  static constexpr int consts = pe_dir + 2 * kPeDirBytes;
+  static constexpr int xchg = consts + kMaxConstFloats * 4;             // [tile][row] float4 head partials
+  static constexpr int bars = xchg + 2 * kTileM * 16;
   static constexpr int n_bars = 2 * kNumSlots + 4 + 4 + 2 + 2 + 2;
   static constexpr int tmem_ptr = bars + n_bars * 8;
   static constexpr int total = tmem_ptr + 16;
@@ -243,32 +280,36 @@ struct Smem {
 // barrier indices
 __device__ __forceinline__ int B_wfull(int s) { return s; }
 __device__ __forceinline__ int B_wempty(int s) { return kNumSlots + s; }
-__device__ __forceinline__ int B_pefull(int t, int b) { return 2 * kNumSlots + t * 2 + b; }
-__device__ __forceinline__ int B_peempty(int t, int b) { return 2 * kNumSlots + 4 + t * 2 + b; }
+__device__ __forceinline__ int B_xyzfull(int t) { return 2 * kNumSlots + t; }
+__device__ __forceinline__ int B_xyzempty(int t) { return 2 * kNumSlots + 2 + t; }
+__device__ __forceinline__ int B_dirfull(int t) { return 2 * kNumSlots + 4 + t; }
+__device__ __forceinline__ int B_dirempty(int t) { return 2 * kNumSlots + 6 + t; }
 __device__ __forceinline__ int B_aready(int t) { return 2 * kNumSlots + 8 + t; }
 __device__ __forceinline__ int B_dfull(int t) { return 2 * kNumSlots + 10 + t; }
 __device__ __forceinline__ int B_dfree(int t) { return 2 * kNumSlots + 12 + t; }
 
 __device__ __forceinline__ int chunks_in_pass(const TcLayer& L) { return L.k_main / 64 + (L.smem_src ? 1 : 0); }
 
-// One epilogue pass over the 128-column accumulator of a tile (one thread per sample row):
-// + bias, optional sigma head, optional ReLU, pack to bf16, then either keep the packed words in
-// registers (first pass of a 256-wide layer) or store them as the next layer's A operand.
-template <int H, bool kRelu, bool kSig, bool kHold, bool kPark, bool kDbg>
-__device__ __forceinline__ void epilogue_pass(uint32_t d_tmem, uint32_t a_tmem, uint32_t a_col0, const float* bias,
-                                              const float* wa, float& sigma, uint32_t (&held)[H / 4],
-                                              uint32_t dfree_bar, float* dbg_dst) {
-  uint32_t v[2][16];      // double-buffered 16-column slices of the accumulator
+// One epilogue pass of one warp over ITS 64 of the 128 accumulator columns of a tile (one thread per
+// sample row; two warps per 32-row quarter split the columns): + bias, optional sigma head,
+// optional ReLU, pack to bf16, then either keep the packed words in registers (first pass of a
+// 256-wide layer) or store them as the next layer's A operand.
+template <bool kRelu, bool kSig, bool kHold, bool kPark, bool kDbg>
+__device__ __forceinline__ void epilogue_pass(uint32_t d_tmem, uint32_t a_park, uint32_t a_store, uint32_t bias,
+                                              uint32_t wa, float& sigma, uint32_t (&held)[32],
+                                              uint32_t dfree_bar, float* dbg_dst, long long* stamps) {
+  uint32_t v[2][16];      // 16-column slices of the accumulator
+  if (kDbg && stamps) stamps[0] = clock64();
   tmem_ld16_issue(d_tmem, v[0]);
   if (kPark) {
-    // the old A is dead now: park the first pass's half of the new A
-#pragma unroll
-    for (int j = 0; j < H / 64; ++j) tmem_st16(a_tmem + (uint32_t)(j * 16), &held[j * 16]);
+    // the old A is dead now: park the first pass's share of the new A
+    tmem_st16(a_park, &held[0]);
+    tmem_st16(a_park + 16, &held[16]);
   }
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {     // 8 x 16 columns; unrolled so held[] has static indices
+  for (int c = 0; c < 4; ++c) {     // 4 x 16 columns; unrolled so held[] has static indices
     tmem_ld16_wait(v[c & 1]);
-    if (c + 1 < 8) tmem_ld16_issue(d_tmem + (uint32_t)((c + 1) * 16), v[(c + 1) & 1]);
+    if (c + 1 < 4) tmem_ld16_issue(d_tmem + (uint32_t)((c + 1) * 16), v[(c + 1) & 1]);
     if (kDbg && dbg_dst) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) dbg_dst[c * 16 + i] = __uint_as_float(v[c & 1][i]);
@@ -276,13 +317,13 @@ __device__ __forceinline__ void epilogue_pass(uint32_t d_tmem, uint32_t a_tmem, 
     uint32_t pk[8];
 #pragma unroll
     for (int i = 0; i < 16; i += 4) {
-      const float4 b4 = *reinterpret_cast<const float4*>(bias + c * 16 + i);
+      const float4 b4 = lds128(bias + (uint32_t)((c * 16 + i) * 4));
       const float x0 = __uint_as_float(v[c & 1][i]) + b4.x;
       const float x1 = __uint_as_float(v[c & 1][i + 1]) + b4.y;
       const float x2 = __uint_as_float(v[c & 1][i + 2]) + b4.z;
       const float x3 = __uint_as_float(v[c & 1][i + 3]) + b4.w;
       if (kSig) {   // fc_alpha on the rectified, unrounded trunk output
-        const float4 w4 = *reinterpret_cast<const float4*>(wa + c * 16 + i);
+        const float4 w4 = lds128(wa + (uint32_t)((c * 16 + i) * 4));
         sigma = fmaf(fmaxf(x0, 0.0f), w4.x, sigma);
         sigma = fmaf(fmaxf(x1, 0.0f), w4.y, sigma);
         sigma = fmaf(fmaxf(x2, 0.0f), w4.z, sigma);
@@ -296,9 +337,10 @@ __device__ __forceinline__ void epilogue_pass(uint32_t d_tmem, uint32_t a_tmem, 
         pk[i / 2 + 1] = pack_bf16(x2, x3, kRelu);
       }
     }
-    if (!kHold) tmem_st8(a_tmem + a_col0 + (uint32_t)(c * 8), pk);
-    if (c == 7) {
-      // accumulator fully read (the last wait::ld covered it): release it early
+    if (!kHold) tmem_st8(a_store + (uint32_t)(c * 8), pk);
+    if (kDbg && stamps) stamps[1 + c] = clock64();
+    if (c == 3) {
+      // this warp's columns are fully read (the last wait::ld covered them)
       tc_fence_before();
       mbar_arrive(dfree_bar);
     }
@@ -321,10 +363,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
   if (threadIdx.x == 0) {
     for (int s = 0; s < kNumSlots; ++s) { mbar_init(bar(B_wfull(s)), 1); mbar_init(bar(B_wempty(s)), 2); }
     for (int t = 0; t < 2; ++t) {
-      for (int b = 0; b < 2; ++b) { mbar_init(bar(B_pefull(t, b)), 128); mbar_init(bar(B_peempty(t, b)), 1); }
-      mbar_init(bar(B_aready(t)), 128);
+      mbar_init(bar(B_xyzfull(t)), 128); mbar_init(bar(B_xyzempty(t)), 1);
+      mbar_init(bar(B_dirfull(t)), 128); mbar_init(bar(B_dirempty(t)), 1);
+      mbar_init(bar(B_aready(t)), kEpiThreadsPerTile);
       mbar_init(bar(B_dfull(t)), 1);
-      mbar_init(bar(B_dfree(t)), 128);
+      mbar_init(bar(B_dfree(t)), kEpiThreadsPerTile);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -342,10 +385,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + Smem::tmem_ptr);
   const float* s_const = reinterpret_cast<const float*>(smem + Smem::consts);
 
-  // register budget per warpgroup (512 threads x 128 at launch): 104 / 152 / 152 / 104.
-  // Each setmaxnreg sits at the top of its role branch so that ptxas scopes the budget to it.
+  // register budget: 768 threads x 80 registers, no re-balancing (setmaxnreg.inc can only draw
+  // from registers other warpgroups of the CTA released with setmaxnreg.dec).
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
   if (warp == 0) {
     // =============================== weight producer ===============================
     const bool leader = elect_one();
@@ -363,7 +405,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
 #pragma unroll 1
           for (int c = 0; c < nc; ++c, ++cnt) {
             const int kc = (c < L.k_main / 64) ? 64 : L.k_smem;
-            const uint32_t bytes = (uint32_t)(np * kc * 2);
+            uint32_t bytes = (uint32_t)(np * kc * 2);
+            if (kDbg && P.dbg_layer == -3) bytes = 1024;   // experiment: timing without the weight traffic
             const uint32_t slot = cnt % kNumSlots, ph = (cnt / kNumSlots) & 1;
             mbar_wait(bar(B_wempty(slot)), ph ^ 1, 0);
             if (leader) {
@@ -391,8 +434,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     constexpr int kMain = H / 64;               // 64-wide K chunks of a hidden-activation operand
 #pragma unroll 1
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++it) {
-      const int buf = it & 1;
-      const uint32_t pe_ph = (it >> 1) & 1;
+      const uint32_t pe_ph = it & 1;
 #pragma unroll 1
       for (int l = 0; l < P.n_layers; ++l) {
         const TcLayer& L = P.layers[l];
@@ -408,20 +450,35 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
           for (int t = 0; t < 2; ++t) {
             const uint32_t a_tmem = tmem_base + (uint32_t)(t * 256);
             const uint32_t d_tmem = a_tmem + 128;
-            // the accumulator must have been drained by the previous epilogue pass of this tile
-            mbar_wait(bar(B_dfree(t)), ph_dfree[t] ^ 1, 1);
+            // Gate: the accumulator must have been drained by this tile's previous epilogue pass and,
+            // for the first pass of a layer, the new A operand must be in place.  a_ready is
+            // arrived after d_free by every epilogue thread, so one poll covers both.
+            if (p == 0 && l > 0) {
+              mbar_wait(bar(B_aready(t)), ph_aready[t], 3);
+              ph_aready[t] ^= 1;
+            } else {
+              mbar_wait(bar(B_dfree(t)), ph_dfree[t] ^ 1, 1);
+              if (l == 0) mbar_wait(bar(B_xyzfull(t)), pe_ph, 2);
+            }
             ph_dfree[t] ^= 1;
-            if (p == 0) {
-              if (l == 0) mbar_wait(bar(B_pefull(t, buf)), pe_ph, 2);
-              else { mbar_wait(bar(B_aready(t)), ph_aready[t], 3); ph_aready[t] ^= 1; }
+            uint32_t slot = slot_p, phase = phase_p;
+            if (t == 0 && has_main) {
+              // all main chunks of the pass are normally resident already (the ring runs ahead)
+              uint32_t sl[4], ph4[4];
+              uint32_t s2 = slot, p2 = phase;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                sl[c] = bar(B_wfull(s2)); ph4[c] = p2;
+                if (c + 1 < kMain) { if (++s2 == kNumSlots) { s2 = 0; p2 ^= 1; } }
+              }
+              if (kMain == 4) mbar_wait4(sl[0], ph4[0], sl[1], ph4[1], sl[2], ph4[2], sl[3], ph4[3], 4);
+              else mbar_wait4(sl[0], ph4[0], sl[1], ph4[1], sl[1], ph4[1], sl[1], ph4[1], 4);
             }
             tc_fence_after();
             if (timing) reinterpret_cast<long long*>(P.dbg)[((l * 2 + p) * 2 + t) * 2] = clock64();
-            uint32_t slot = slot_p, phase = phase_p;
             if (has_main) {
-#pragma unroll
+#pragma unroll 1
               for (int c = 0; c < kMain; ++c) {
-                if (t == 0) { mbar_wait(bar(B_wfull(slot)), phase, 4); tc_fence_after(); }
                 // descriptor low word: address (16-byte units) | LBO << 16; K-step advance = 2*LBO
                 const uint32_t b_lo = (slot0_lo + slot * (kSlotBytes >> 4)) | (b_lbo16 << 16);
                 if (leader) {
@@ -438,9 +495,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
             if (L.smem_src) {
               if (t == 0) { mbar_wait(bar(B_wfull(slot)), phase, 4); tc_fence_after(); }
               const uint32_t b_lo = (slot0_lo + slot * (kSlotBytes >> 4)) | (b_lbo16 << 16);
+              if (L.smem_src == 2 && p == 0) mbar_wait(bar(B_dirfull(t)), pe_ph, 2);
               const uint32_t a_addr = (L.smem_src == 1)
-                  ? sbase + Smem::pe_xyz + (uint32_t)(t * 2 + buf) * kPeXyzBytes
-                  : sbase + Smem::pe_dir + (uint32_t)(t * 2 + buf) * kPeDirBytes;
+                  ? sbase + Smem::pe_xyz + (uint32_t)t * kPeXyzBytes
+                  : sbase + Smem::pe_dir + (uint32_t)t * kPeDirBytes;
               const uint32_t a_lo = ((a_addr >> 4) & 0x3FFF) | ((uint32_t)kTileM << 16);   // LBO = 128*16 B
               if (leader) {
 #pragma unroll
@@ -457,7 +515,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
             }
             if (leader) {
               tc_commit(bar(B_dfull(t)));
-              if (l == P.n_layers - 1 && p == L.n_pass - 1) tc_commit(bar(B_peempty(t, buf)));
+              if (p == L.n_pass - 1) {
+                if (l == P.last_xyz_layer) tc_commit(bar(B_xyzempty(t)));   // encoders may refill
+                if (L.smem_src == 2) tc_commit(bar(B_dirempty(t)));
+              }
             }
             __syncwarp();
             if (timing) reinterpret_cast<long long*>(P.dbg)[((l * 2 + p) * 2 + t) * 2 + 1] = clock64();
@@ -467,19 +528,23 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
       }
     }
   }
-  } else if (warp < 12) {
+  } else if (warp < 20) {
     // =============================== epilogue ===============================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
-    const int t = (warp - 4) >> 2, q = warp & 3;
+    // 16 warps: tile t = e / 8, column half hs = (e / 4) % 2, lane quarter q = warp % 4 (a warp can
+    // only touch the 32 TMEM lanes of its quarter).  Two warps share each 32-row quarter so that
+    // one computes while the other waits on its tcgen05.ld.
+    const int e = warp - 4;
+    const int t = e >> 3, hs = (e >> 2) & 1, q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const uint32_t a_tmem = tmem_base + (uint32_t)(t * 256) + lane_base;
-    const uint32_t d_tmem = a_tmem + 128;
-    const bool timing = kDbg && P.dbg_layer == -2 && blockIdx.x == 0 && q == 0 && lane == 0;
+    const uint32_t d_tmem = a_tmem + 128 + (uint32_t)(hs * 64);
+    const bool timing = kDbg && P.dbg_layer == -2 && blockIdx.x == 0 && q == 0 && hs == 0 && lane == 0;
     long long* tl = reinterpret_cast<long long*>(P.dbg);
+    float4* xchg = reinterpret_cast<float4*>(smem + Smem::xchg) + t * kTileM + row;
+    const int pair_bar = 1 + t * 4 + q;            // named barrier of the two warps of this quarter
     uint32_t ph_dfull = 0;
-    uint32_t held[H / 4];   // first-pass results of a 2-pass layer (H/2 bf16 = H/4 words)
-    uint32_t v[2][16];
+    uint32_t held[32];   // first-pass results of a 2-pass layer (this warp's 64 outputs as bf16 pairs)
 #pragma unroll 1
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       const int64_t g = (pair * 2 + t) * kTileM + row;
@@ -494,25 +559,29 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
           tc_fence_after();
           if (timing && pair == blockIdx.x) tl[256 + ((l * 2) * 2 + t) * 2] = clock64();
           float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
-          const float* bias = s_const + L.bias_off;
-          const float* wr = s_const + P.off_wrgb;
-          constexpr int hw = H / 2;
-          tmem_ld16_issue(d_tmem, v[0]);
+          constexpr int hw = H / 2;           // outputs of the dir layer
+          constexpr int mine = hw / 2;        // columns this warp reduces
+          const uint32_t col0 = (uint32_t)(hs * mine);
+          const uint32_t bias = sbase + Smem::consts + ((uint32_t)L.bias_off + col0) * 4;
+          const uint32_t wr = sbase + Smem::consts + ((uint32_t)P.off_wrgb + col0) * 4;
+          const uint32_t d_last = a_tmem + 128 + col0;
+          uint32_t v[2][16];
+          tmem_ld16_issue(d_last, v[0]);
 #pragma unroll
-          for (int c = 0; c < hw / 16; ++c) {
+          for (int c = 0; c < mine / 16; ++c) {
             tmem_ld16_wait(v[c & 1]);
-            if (c + 1 < hw / 16) tmem_ld16_issue(d_tmem + (uint32_t)((c + 1) * 16), v[(c + 1) & 1]);
+            if (c + 1 < mine / 16) tmem_ld16_issue(d_last + (uint32_t)((c + 1) * 16), v[(c + 1) & 1]);
             if (kDbg && l == P.dbg_layer && g < P.m_total) {
-              float* dst = P.dbg + g * 128 + c * 16;
+              float* dst = P.dbg + g * 128 + col0 + c * 16;
 #pragma unroll
               for (int i = 0; i < 16; ++i) dst[i] = __uint_as_float(v[c & 1][i]);
             }
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(bias + c * 16 + i);
-              const float4 r4 = *reinterpret_cast<const float4*>(wr + c * 16 + i);
-              const float4 g4 = *reinterpret_cast<const float4*>(wr + hw + c * 16 + i);
-              const float4 u4 = *reinterpret_cast<const float4*>(wr + 2 * hw + c * 16 + i);
+              const float4 b4 = lds128(bias + (uint32_t)((c * 16 + i) * 4));
+              const float4 r4 = lds128(wr + (uint32_t)((c * 16 + i) * 4));
+              const float4 g4 = lds128(wr + (uint32_t)((hw + c * 16 + i) * 4));
+              const float4 u4 = lds128(wr + (uint32_t)((2 * hw + c * 16 + i) * 4));
               const float x0 = fmaxf(__uint_as_float(v[c & 1][i]) + b4.x, 0.0f);
               const float x1 = fmaxf(__uint_as_float(v[c & 1][i + 1]) + b4.y, 0.0f);
               const float x2 = fmaxf(__uint_as_float(v[c & 1][i + 2]) + b4.z, 0.0f);
@@ -525,16 +594,21 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
           tc_fence_before();
           mbar_arrive(bar(B_dfree(t)));
           if (timing && pair == blockIdx.x) tl[256 + ((l * 2) * 2 + t) * 2 + 1] = clock64();
-          if (g < P.m_total) {
+          // combine the two column halves: hs == 1 hands its partial sums to hs == 0
+          if (hs == 1) *xchg = make_float4(rgb0, rgb1, rgb2, sigma);
+          asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+          if (hs == 0 && g < P.m_total) {
+            const float4 o2 = *xchg;
             const float* br = s_const + P.off_brgb;
             float4 o;
-            o.x = rgb0 + br[0]; o.y = rgb1 + br[1]; o.z = rgb2 + br[2];
-            o.w = sigma + s_const[P.off_balpha];
+            o.x = rgb0 + o2.x + br[0]; o.y = rgb1 + o2.y + br[1]; o.z = rgb2 + o2.z + br[2];
+            o.w = sigma + o2.w + s_const[P.off_balpha];
             reinterpret_cast<float4*>(P.rf)[g] = o;
           }
+          asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // xchg may be rewritten
         } else {
-          const float* bias = s_const + L.bias_off;
-          const float* wa = s_const + P.off_walpha;
+          const uint32_t bias = sbase + Smem::consts + ((uint32_t)L.bias_off + hs * 64) * 4;
+          const uint32_t wa = sbase + Smem::consts + ((uint32_t)P.off_walpha + hs * 64) * 4;
           const int kind = L.relu ? (L.head == 1 ? 2 : 1) : 0;
 #pragma unroll
           for (int p = 0; p < H / 128; ++p) {
@@ -544,21 +618,26 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
             if (timing && pair == blockIdx.x) tl[256 + ((l * 2 + p) * 2 + t) * 2] = clock64();
             constexpr bool kTwoPass = (H == 256);
             const bool hold = kTwoPass && p == 0;
-            float* dbg_dst = (kDbg && P.dbg_layer == l && P.dbg_pass == p && g < P.m_total) ? P.dbg + g * 128 : nullptr;
-            const float* bp = bias + p * 128;
-            const float* wp = wa + p * 128;
+            float* dbg_dst = (kDbg && P.dbg_layer == l && P.dbg_pass == p && g < P.m_total)
+                                 ? P.dbg + g * 128 + hs * 64 : nullptr;
+            const uint32_t bp = bias + (uint32_t)(p * 128 * 4);
+            const uint32_t wp = wa + (uint32_t)(p * 128 * 4);
             const uint32_t dfree = bar(B_dfree(t));
+            const uint32_t a_park = a_tmem + (uint32_t)(hs * 32);                 // pass-0 outputs: K [hs*64, +64)
+            const uint32_t a_store = a_tmem + (uint32_t)(p * 64 + hs * 32);       // pass-p outputs
+            long long* stamps = (timing && pair == blockIdx.x && l == 2) ? tl + 600 + (p * 2 + t) * 16 : nullptr;
             if (hold) {
-              if (kind == 0) epilogue_pass<H, false, false, true, false, kDbg>(d_tmem, a_tmem, 0, bp, wp, sigma, held, dfree, dbg_dst);
-              else if (kind == 1) epilogue_pass<H, true, false, true, false, kDbg>(d_tmem, a_tmem, 0, bp, wp, sigma, held, dfree, dbg_dst);
-              else epilogue_pass<H, true, true, true, false, kDbg>(d_tmem, a_tmem, 0, bp, wp, sigma, held, dfree, dbg_dst);
+              if (kind == 0) epilogue_pass<false, false, true, false, kDbg>(d_tmem, a_park, a_store, bp, wp, sigma, held, dfree, dbg_dst, stamps);
+              else if (kind == 1) epilogue_pass<true, false, true, false, kDbg>(d_tmem, a_park, a_store, bp, wp, sigma, held, dfree, dbg_dst, stamps);
+              else epilogue_pass<true, true, true, false, kDbg>(d_tmem, a_park, a_store, bp, wp, sigma, held, dfree, dbg_dst, stamps);
             } else {
               constexpr bool park = kTwoPass;
-              const uint32_t col0 = (uint32_t)(p * 64);
-              if (kind == 0) epilogue_pass<H, false, false, false, park, kDbg>(d_tmem, a_tmem, col0, bp, wp, sigma, held, dfree, dbg_dst);
-              else if (kind == 1) epilogue_pass<H, true, false, false, park, kDbg>(d_tmem, a_tmem, col0, bp, wp, sigma, held, dfree, dbg_dst);
-              else epilogue_pass<H, true, true, false, park, kDbg>(d_tmem, a_tmem, col0, bp, wp, sigma, held, dfree, dbg_dst);
+              if (kind == 0) epilogue_pass<false, false, false, park, kDbg>(d_tmem, a_park, a_store, bp, wp, sigma, held, dfree, dbg_dst, stamps);
+              else if (kind == 1) epilogue_pass<true, false, false, park, kDbg>(d_tmem, a_park, a_store, bp, wp, sigma, held, dfree, dbg_dst, stamps);
+              else epilogue_pass<true, true, false, park, kDbg>(d_tmem, a_park, a_store, bp, wp, sigma, held, dfree, dbg_dst, stamps);
+              if (kDbg && stamps) stamps[9] = clock64();
               tmem_wait_st();
+              if (kDbg && stamps) stamps[10] = clock64();
               tc_fence_before();
               mbar_arrive(bar(B_aready(t)));
             }
@@ -569,27 +648,24 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     }
   } else {
     // =============================== encoders ===============================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
-    const int row = (warp - 12) * 32 + lane;
+    const int row = (warp - 20) * 32 + lane;
     uint32_t it = 0;
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++it) {
-      const int buf = it & 1;
-      const uint32_t ph = (it >> 1) & 1;
+      const uint32_t ph = it & 1;
+      // xyz tiles first (needed by the pair's very first layer), then the dir tiles (only needed
+      // by its last layer, and only free once the previous pair has completely retired)
       for (int t = 0; t < 2; ++t) {
-        mbar_wait(bar(B_peempty(t, buf)), ph ^ 1, 6);
         const int64_t g = (pair * 2 + t) * kTileM + row;
-        float pt[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
+        float pt[3] = {0.f, 0.f, 0.f};
         const bool valid = g < P.m_total;
         if (valid) {
           const int64_t ray = g / P.S;
           const float zz = P.z[g];
 #pragma unroll
-          for (int a = 0; a < 3; ++a) {
-            pt[a] = __fadd_rn(P.ro[ray * 3 + a], __fmul_rn(P.rd[ray * 3 + a], zz));
-            dir[a] = P.vd[ray * 3 + a];
-          }
+          for (int a = 0; a < 3; ++a) pt[a] = __fadd_rn(P.ro[ray * 3 + a], __fmul_rn(P.rd[ray * 3 + a], zz));
         }
-        uint8_t* xyz = smem + Smem::pe_xyz + (t * 2 + buf) * kPeXyzBytes + row * 16;
+        mbar_wait(bar(B_xyzempty(t)), ph ^ 1, 6);
+        uint8_t* xyz = smem + Smem::pe_xyz + t * kPeXyzBytes + row * 16;
         for (int k8 = 0; k8 < 8; ++k8) {   // 8 encoding columns = one 16-byte core-matrix row
           uint32_t w4[4];
 #pragma unroll
@@ -601,7 +677,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
           }
           *reinterpret_cast<uint4*>(xyz + k8 * (kTileM * 16)) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
         }
-        uint8_t* dr = smem + Smem::pe_dir + (t * 2 + buf) * kPeDirBytes + row * 16;
+        fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
+        mbar_arrive(bar(B_xyzfull(t)));
+      }
+      for (int t = 0; t < 2; ++t) {
+        const int64_t g = (pair * 2 + t) * kTileM + row;
+        float dir[3] = {0.f, 0.f, 0.f};
+        const bool valid = g < P.m_total;
+        if (valid) {
+          const int64_t ray = g / P.S;
+#pragma unroll
+          for (int a = 0; a < 3; ++a) dir[a] = P.vd[ray * 3 + a];
+        }
+        mbar_wait(bar(B_dirempty(t)), ph ^ 1, 7);
+        uint8_t* dr = smem + Smem::pe_dir + t * kPeDirBytes + row * 16;
         for (int k8 = 0; k8 < 4; ++k8) {
           uint32_t w4[4];
 #pragma unroll
@@ -613,8 +702,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
           }
           *reinterpret_cast<uint4*>(dr + k8 * (kTileM * 16)) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
         }
-        fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
-        mbar_arrive(bar(B_pefull(t, buf)));
+        fence_proxy_async();
+        mbar_arrive(bar(B_dirfull(t)));
       }
     }
   }
@@ -805,7 +894,10 @@ extern "C" DEXNERF_API int dexnerf_tc_query(const dexnerf_flexible_spec* spec, c
   P.Lx = spec->Lx; P.Ld = spec->Ld; P.include_xyz = spec->include_xyz; P.include_dir = spec->include_dir;
   P.log_xyz = spec->log_xyz; P.log_dir = spec->log_dir; P.dim_xyz = spec->dim_xyz; P.dim_dir = spec->dim_dir;
   P.dbg_layer = dbg_layer; P.dbg_pass = dbg_pass;
-  for (int l = 0; l < plan.n_layers; ++l) P.layers[l] = plan.layers[l].tc;
+  for (int l = 0; l < plan.n_layers; ++l) {
+    P.layers[l] = plan.layers[l].tc;
+    if (plan.layers[l].tc.smem_src == 1) P.last_xyz_layer = l;
+  }
   const int64_t n_tiles = (P.m_total + kTileM - 1) / kTileM, n_pairs = (n_tiles + 1) / 2;
   const int grid = (int)(n_pairs < kNumSMs ? n_pairs : kNumSMs);
   const size_t smem = Smem::total + 1024;

@@ -39,6 +39,12 @@ def main():
     tiles = (n * S + 127) // 128
     print("kernel %.3f ms for %d samples (%d tiles, %.1f pairs/SM): %.2f ns/sample, %.1f TFLOP/s"
           % (ms, n * S, tiles, tiles / 2 / 148, ms * 1e6 / (n * S), n * S * 1186816 / ms / 1e9))
+    for mode, name in ((-3, "weights traffic cut to 1 KB/chunk (results invalid)"), (-4, "debug build, full traffic")):
+        e0.record()
+        tensorcore.query(model, prog, ro, rd, vd, z, rf, dbg=tl.view(torch.float32), dbg_layer=mode)
+        e1.record()
+        torch.cuda.synchronize()
+        print("%s: %.3f ms" % (name, e0.elapsed_time(e1)))
     t = tl.cpu().tolist()
     t0 = min(x for x in t[:512] if x > 0)
     print("layer pass tile |  mma_start  mma_end (issue) |  epi_start  epi_end | epi_len  gap(epi_start - mma_end)")
@@ -51,6 +57,11 @@ def main():
                     continue
                 print("%5d %4d %4d | %10d %9d | %10d %8d | %7d %6d"
                       % (l, p, tile, ms_ - t0, me_ - t0, es_ - t0, ee_ - t0, ee_ - es_, es_ - me_))
+    for p in range(2):
+        for tile in range(2):
+            st = t[600 + (p * 2 + tile) * 16: 600 + (p * 2 + tile) * 16 + 11]
+            if st[0]:
+                print("layer 2 pass %d tile %d chunk stamps (rel):" % (p, tile), [x - st[0] if x else None for x in st])
     last = max(t[256:512])
     print("pair span: %d cycles (MMA floor for 2 tiles: 37120)" % (last - t0))
 

@@ -38,7 +38,14 @@ __device__ __forceinline__ bool try_wait(uint32_t bar, uint32_t parity) {
 }
 
 // variant: 0 SS noswz, 1 TS noswz-B, 2 SS swz128, 3 TS swz128-B
-__global__ void __launch_bounds__(128, 1) bench(int variant, int N, int reps, int ksteps, long long* out) {
+#define LD16(taddr, r)                                                                                          \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                        \
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"               \
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), \
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) \
+               : "r"(taddr) : "memory")
+__device__ volatile int g_stop;
+__global__ void __launch_bounds__(512, 1) bench(int variant, int N, int reps, int ksteps, long long* out, int n_ld, long long* ld_out, unsigned* sink) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar;
@@ -57,6 +64,28 @@ __global__ void __launch_bounds__(128, 1) bench(int variant, int N, int reps, in
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tm = tmem_ptr;
+  __shared__ volatile int s_stop;
+  if (threadIdx.x == 0) s_stop = 0;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5;
+  if (warp >= 4 && warp < 4 + n_ld) {
+    // concurrent accumulator readers (columns 0..127 of this warp's lane quarter)
+    const uint32_t base = tm + (((uint32_t)(warp & 3) * 32) << 16);
+    uint32_t r[16]; unsigned acc = 0; long long n = 0;
+    const long long t0 = clock64();
+    while (!s_stop) {
+      for (int c = 0; c < 8; ++c) {
+        LD16(base + c * 16, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc ^= r[j];
+      }
+      ++n;
+    }
+    const long long t1 = clock64();
+    if ((threadIdx.x & 31) == 0) { ld_out[(warp - 4) * 2] = t1 - t0; ld_out[(warp - 4) * 2 + 1] = n; }
+    sink[threadIdx.x] = acc;
+  }
   if (threadIdx.x < 32) {
     const uint32_t a_smem = smem_u32(smem);                 // A tile: 128 rows x (ksteps*16) K
     const uint32_t b_smem = smem_u32(smem) + 64 * 1024;     // B tile: N rows x (ksteps*16) K
@@ -91,7 +120,7 @@ __global__ void __launch_bounds__(128, 1) bench(int variant, int N, int reps, in
       const long long t1 = clock64();
       if (t1 - t0 < best) best = t1 - t0;
     }
-    if (threadIdx.x == 0) out[blockIdx.x] = best;
+    if (threadIdx.x == 0) { out[blockIdx.x] = best; s_stop = 1; }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -99,24 +128,27 @@ __global__ void __launch_bounds__(128, 1) bench(int variant, int N, int reps, in
 }
 
 int main() {
-  long long* out;
+  long long *out, *ld_out; unsigned* sink;
   cudaMalloc(&out, 148 * sizeof(long long));
+  cudaMalloc(&ld_out, 64 * sizeof(long long));
+  cudaMalloc(&sink, 512 * 4);
   cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const char* names[4] = {"SS  B no-swizzle", "TS  B no-swizzle", "SS  B 128B-swizzle", "TS  B 128B-swizzle"};
-  for (int grid : {1, 148}) {
-    for (int N : {64, 128, 256}) {
-      for (int v = 0; v < 4; ++v) {
-        const int reps = 8, ksteps = 16;
-        bench<<<grid, 128, 200 * 1024>>>(v, N, reps, ksteps, out);
+  for (int n_ld : {0, 4, 8}) {
+    for (int N : {128, 256}) {
+      for (int v = 0; v < 2; ++v) {
+        const int reps = 32, ksteps = 16;
+        cudaMemset(ld_out, 0, 64 * sizeof(long long));
+        bench<<<1, 512, 200 * 1024>>>(v, N, reps, ksteps, out, n_ld, ld_out, sink);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("variant %d N %d: %s\n", v, N, cudaGetErrorString(e)); return 1; }
-        long long h[148];
-        cudaMemcpy(h, out, grid * sizeof(long long), cudaMemcpyDeviceToHost);
-        long long mx = 0;
-        for (int i = 0; i < grid; ++i) mx = h[i] > mx ? h[i] : mx;
-        const double per = (double)mx / (reps * ksteps);
-        printf("grid %3d  N %3d  %-20s: %7lld cycles for %d MMAs = %6.1f cyc/MMA  (floor %d)  %.0f%% of peak\n", grid, N,
-               names[v], mx, reps * ksteps, per, N / 2, 100.0 * (N / 2) / per);
+        long long h[1], l[32];
+        cudaMemcpy(h, out, sizeof(long long), cudaMemcpyDeviceToHost);
+        cudaMemcpy(l, ld_out, 32 * sizeof(long long), cudaMemcpyDeviceToHost);
+        const double per = (double)h[0] / (reps * ksteps);
+        printf("readers %d  N %3d  %-18s: %6.1f cyc/MMA (%.0f%% of peak)", n_ld, N, names[v], per, 100.0 * (N / 2) / per);
+        if (n_ld) printf(" | reader warp 0: %.0f cycles per 128-col pass (%lld passes)", (double)l[0] / (l[1] ? l[1] : 1), l[1]);
+        printf("\n");
       }
     }
   }
