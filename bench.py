@@ -197,10 +197,8 @@ def main():
     n_gpus = world
     dev = torch.device("cuda", local)
 
-    rows = H // n_gpus
-    row0 = rank * rows
-    if rank == n_gpus - 1:
-        rows = H - row0
+    from nerf.sharding import row_block
+    row0, rows = row_block(H, rank, n_gpus)
     mc, mf = state_dicts()
     mc, mf = mc.to(dev), mf.to(dev)
     cfg = make_cfg(nerf)
