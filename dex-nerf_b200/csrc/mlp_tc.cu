@@ -264,6 +264,55 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// sin and cos of an fp32 argument of any magnitude the encodings reach (|arg| < ~1e4): two-term
+// Cody-Waite reduction by 2*pi (exact product in the FMA, one rounding) to [-pi, pi], then the
+// MUFU approximations, whose absolute error there is < 2^-21 - three orders of magnitude below
+// the bf16 rounding the operand gets next.  ~8 instructions instead of the ~100 of sinf + cosf.
+__device__ __forceinline__ void sincos_reduced(float arg, float& s, float& c) {
+  const float n = rintf(arg * 0.15915494309189535f);
+  float r = fmaf(n, -6.2831854820251465f, arg);
+  r = fmaf(n, 1.7484556000744883e-7f, r);
+  s = __sinf(r);
+  c = __cosf(r);
+}
+
+// One sample row of a positional-encoding operand tile in the standard configuration
+// (include_input, log sampling: columns [x(3), sin(2^b x)(3), cos(2^b x)(3), ...]), written as
+// bf16 UMMA core-matrix rows (16 bytes = 8 columns each, kTileM*16 bytes apart).  Fully unrolled:
+// every column's (band, axis, sin|cos) is a compile-time constant and only one band's six values
+// are live at a time.
+template <int kGroups>
+__device__ __forceinline__ void encode_row_std(const float (&x)[3], int dim, bool valid, uint8_t* dst) {
+  float sv[3] = {0.f, 0.f, 0.f}, cv[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k8 = 0; k8 < kGroups; ++k8) {
+    uint32_t w4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float e[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = k8 * 8 + 2 * j + h;
+        float v;
+        if (c < 3) {
+          v = x[c];
+        } else {
+          const int band = (c - 3) / 6, rem = (c - 3) % 6;
+          if (rem == 0 && c < dim) {
+            const float f = (float)(1u << band);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) sincos_reduced(__fmul_rn(x[a], f), sv[a], cv[a]);
+          }
+          v = rem < 3 ? sv[rem] : cv[rem - 3];
+        }
+        e[h] = (valid && c < dim) ? v : 0.f;
+      }
+      w4[j] = pack_bf16(e[0], e[1], false);
+    }
+    *reinterpret_cast<uint4*>(dst + k8 * (kTileM * 16)) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+  }
+}
+
 // ------------------------------------------------------------------ shared-memory map
 struct Smem {
   // offsets from the 1024-aligned base
@@ -649,6 +698,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
   } else {
     // =============================== encoders ===============================
     const int row = (warp - 20) * 32 + lane;
+    const bool std_xyz = P.include_xyz && P.log_xyz, std_dir = P.include_dir && P.log_dir;
     uint32_t it = 0;
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++it) {
       const uint32_t ph = it & 1;
@@ -666,16 +716,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
         }
         mbar_wait(bar(B_xyzempty(t)), ph ^ 1, 6);
         uint8_t* xyz = smem + Smem::pe_xyz + t * kPeXyzBytes + row * 16;
-        for (int k8 = 0; k8 < 8; ++k8) {   // 8 encoding columns = one 16-byte core-matrix row
-          uint32_t w4[4];
+        if (std_xyz) {
+          encode_row_std<8>(pt, P.dim_xyz, valid, xyz);
+        } else {
+          for (int k8 = 0; k8 < 8; ++k8) {   // 8 encoding columns = one 16-byte core-matrix row
+            uint32_t w4[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int c0 = k8 * 8 + 2 * j;
-            const float e0 = (valid && c0 < P.dim_xyz) ? pe_column(pt, c0, P.Lx, P.include_xyz, P.log_xyz) : 0.f;
-            const float e1 = (valid && c0 + 1 < P.dim_xyz) ? pe_column(pt, c0 + 1, P.Lx, P.include_xyz, P.log_xyz) : 0.f;
-            w4[j] = pack_bf16(e0, e1, false);
+            for (int j = 0; j < 4; ++j) {
+              const int c0 = k8 * 8 + 2 * j;
+              const float e0 = (valid && c0 < P.dim_xyz) ? pe_column(pt, c0, P.Lx, P.include_xyz, P.log_xyz) : 0.f;
+              const float e1 = (valid && c0 + 1 < P.dim_xyz) ? pe_column(pt, c0 + 1, P.Lx, P.include_xyz, P.log_xyz) : 0.f;
+              w4[j] = pack_bf16(e0, e1, false);
+            }
+            *reinterpret_cast<uint4*>(xyz + k8 * (kTileM * 16)) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
           }
-          *reinterpret_cast<uint4*>(xyz + k8 * (kTileM * 16)) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
         }
         fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
         mbar_arrive(bar(B_xyzfull(t)));
@@ -691,16 +745,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
         }
         mbar_wait(bar(B_dirempty(t)), ph ^ 1, 7);
         uint8_t* dr = smem + Smem::pe_dir + t * kPeDirBytes + row * 16;
-        for (int k8 = 0; k8 < 4; ++k8) {
-          uint32_t w4[4];
+        if (std_dir) {
+          encode_row_std<4>(dir, P.dim_dir, valid, dr);
+        } else {
+          for (int k8 = 0; k8 < 4; ++k8) {
+            uint32_t w4[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int c0 = k8 * 8 + 2 * j;
-            const float e0 = (valid && c0 < P.dim_dir) ? pe_column(dir, c0, P.Ld, P.include_dir, P.log_dir) : 0.f;
-            const float e1 = (valid && c0 + 1 < P.dim_dir) ? pe_column(dir, c0 + 1, P.Ld, P.include_dir, P.log_dir) : 0.f;
-            w4[j] = pack_bf16(e0, e1, false);
+            for (int j = 0; j < 4; ++j) {
+              const int c0 = k8 * 8 + 2 * j;
+              const float e0 = (valid && c0 < P.dim_dir) ? pe_column(dir, c0, P.Ld, P.include_dir, P.log_dir) : 0.f;
+              const float e1 = (valid && c0 + 1 < P.dim_dir) ? pe_column(dir, c0 + 1, P.Ld, P.include_dir, P.log_dir) : 0.f;
+              w4[j] = pack_bf16(e0, e1, false);
+            }
+            *reinterpret_cast<uint4*>(dr + k8 * (kTileM * 16)) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
           }
-          *reinterpret_cast<uint4*>(dr + k8 * (kTileM * 16)) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
         }
         fence_proxy_async();
         mbar_arrive(bar(B_dirfull(t)));

@@ -399,9 +399,82 @@ def gen_tiny():
     print("tiny.npz")
 
 
+def gen_train_grads():
+    """One TRAINING iteration of the reference (train_dexnerf_rgb.py:246-278): train-mode
+    run_one_iter_of_nerf with the four RNG draws replayed, loss = mse(rgb_coarse, target) +
+    mse(rgb_fine, target), loss.backward().  Stores the loss and every parameter gradient of both
+    nets, plus the Adam-updated parameters after one optimizer.step() (lr 5e-3)."""
+    out = {}
+    g = torch.Generator().manual_seed(17)
+    H, W = 6, 8
+    T = rand_pose(g)
+    T[:3, 3] = torch.tensor([0.1, -0.2, 3.0])
+    K = torch.tensor([[9.0, 0, 4.0], [0, 9.0, 3.0], [0, 0, 1]])
+    ro, rd = ref.get_ray_bundle(H, W, None, T, K)
+    ro, rd = ro.reshape(-1, 3), rd.reshape(-1, 3)
+    n = ro.shape[0]
+    target = torch.rand(n, 3, generator=g)
+    thr = [5.0, 20.0, 60.0, 100.0]
+    enc_x = ref.get_embedding_function(6, True, True)
+    enc_d = ref.get_embedding_function(4, True, True)
+    for tag, (hidden, layers, skip, white) in {"h32": (32, 5, 2, False), "h128": (128, 8, 3, True)}.items():
+        nets = []
+        for seed in (31, 32):
+            torch.manual_seed(seed)
+            m = RepairedFlexible(num_layers=layers, hidden_size=hidden, skip_connect_every=skip,
+                                 num_encoding_fn_xyz=6, num_encoding_fn_dir=4)
+            with torch.no_grad():
+                m.fc_alpha.weight.mul_(20.0)
+                m.fc_alpha.bias.fill_(1.0)
+            nets.append(m)
+        mc, mf = nets
+        for k, v in mc.state_dict().items():
+            out[f"{tag}.coarse." + k] = npy(v).copy()
+        for k, v in mf.state_dict().items():
+            out[f"{tag}.fine." + k] = npy(v).copy()
+        cfg = make_cfg(16, 24, 2.0, 6.0, True, 0.2, white, False)
+        torch.manual_seed(4040)
+        t_rand = torch.rand(n, 16)
+        noise_c = torch.randn(n, 16) * 0.2
+        u = torch.rand(n, 24)
+        noise_f = torch.randn(n, 40) * 0.2
+        opt = torch.optim.Adam(list(mc.parameters()) + list(mf.parameters()), lr=5e-3)
+        torch.manual_seed(4040)
+        res = ref.run_one_iter_of_nerf(H, W, 9.0, mc, mf, ro, rd, cfg, mode="train", encode_position_fn=enc_x,
+                                       encode_direction_fn=enc_d, m_thres_cand=thr)
+        coarse_loss = torch.nn.functional.mse_loss(res[0][..., :3], target[..., :3])
+        fine_loss = torch.nn.functional.mse_loss(res[3][..., :3], target[..., :3])
+        loss = coarse_loss + fine_loss
+        loss.backward()
+        out.update({f"{tag}.t_rand": npy(t_rand), f"{tag}.noise_c": npy(noise_c), f"{tag}.u": npy(u),
+                    f"{tag}.noise_f": npy(noise_f), f"{tag}.loss": npy(loss),
+                    f"{tag}.coarse_loss": npy(coarse_loss), f"{tag}.fine_loss": npy(fine_loss),
+                    f"{tag}.cfg": np.array([hidden, layers, skip, int(white)])})
+        for k, p in mc.named_parameters():
+            out[f"{tag}.grad.coarse." + k] = npy(p.grad).copy()
+        for k, p in mf.named_parameters():
+            out[f"{tag}.grad.fine." + k] = npy(p.grad).copy()
+        opt.step()
+        for k, p in mc.named_parameters():
+            out[f"{tag}.adam.coarse." + k] = npy(p).copy()
+        for k, p in mf.named_parameters():
+            out[f"{tag}.adam.fine." + k] = npy(p).copy()
+        print(tag, "loss", float(loss), "grad norm coarse",
+              float(sum((p.grad ** 2).sum() for p in mc.parameters()) ** 0.5))
+    out.update(T=npy(T), K=npy(K), HW=np.array([H, W]), ro=npy(ro), rd=npy(rd), target=npy(target),
+               thr=np.array(thr, dtype=np.float32))
+    np.savez_compressed(os.path.join(HERE, "train_grads.npz"), **out)
+    print("train_grads.npz")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1:          # regenerate selected fixtures only: make_golden.py train_grads ...
+        for name in sys.argv[1:]:
+            globals()["gen_" + name]()
+        sys.exit(0)
     gen_ops()
     gen_models()
     gen_pipeline()
     gen_lego()
     gen_tiny()
+    gen_train_grads()
