@@ -162,6 +162,108 @@ composite_kernel(const float4* __restrict__ rf, const float* __restrict__ z,
   }
 }
 
+// Backward of the compositing (training, BASELINE config 4): given dL/d(rgb_map), dL/d(depth_map),
+// dL/d(acc_map) per ray, produce dL/d(radiance_field) (n,S,4).  Same warp-per-ray layout as the
+// forward.  With gw_i = dL/dw_i = g_rgb.c_i + g_depth z_i + g_acc (- sum g_rgb if white bg):
+//   dL/dalpha_i = gw_i T_i - (sum_{k>i} gw_k w_k) / x_i        x_i = 1 - alpha_i + 1e-10
+//   dL/dsigma_i = dL/dalpha_i * dist_i * exp(-sigma_i dist_i),  masked by sigma_i > 0 (ReLU)
+//   dL/drgb_raw = w_i g_rgb c_i (1 - c_i)                        c_i = sigmoid(rgb_raw_i)
+// (what autograd derives for volume_rendering_utils.py:17-48 + cumprod_exclusive).  The forward
+// quantities are recomputed: pass 1 collects the transmittance carried into every 32-sample chunk,
+// pass 2 walks the chunks backwards with a warp-level suffix scan of gw_k w_k in fp64.
+constexpr int kMaxChunks = 64;   // S <= 2048
+
+__global__ void __launch_bounds__(kCompositeWarps * 32)
+composite_bwd_kernel(const float4* __restrict__ rf, const float* __restrict__ z, const float* __restrict__ rd,
+                     const float* __restrict__ noise, int64_t n, int S, int white_background,
+                     const float* __restrict__ g_rgb, const float* __restrict__ g_depth,
+                     const float* __restrict__ g_acc, float4* __restrict__ d_rf) {
+  __shared__ double s_carry[kCompositeWarps][kMaxChunks];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * kCompositeWarps;
+  const int n_chunks = (S + 31) / 32;
+  for (int64_t ray = (int64_t)blockIdx.x * kCompositeWarps + warp; ray < n; ray += warps) {
+    const float dx = rd[ray * 3], dy = rd[ray * 3 + 1], dz = rd[ray * 3 + 2];
+    const float norm =
+        (float)sqrt((double)dx * (double)dx + (double)dy * (double)dy + (double)dz * (double)dz);
+    const float gr = g_rgb ? g_rgb[ray * 3] : 0.f, gg = g_rgb ? g_rgb[ray * 3 + 1] : 0.f,
+                gb = g_rgb ? g_rgb[ray * 3 + 2] : 0.f;
+    const float gd = g_depth ? g_depth[ray] : 0.f;
+    float ga = g_acc ? g_acc[ray] : 0.f;
+    if (white_background) ga -= (gr + gg + gb);   // rgb_map += 1 - acc_map
+    const float4* rf_row = rf + ray * S;
+    const float* z_row = z + ray * S;
+    auto sample = [&](int j, float4& v, float& zj, float& dist, float& sigma, float& e) {
+      const bool valid = j < S;
+      v = make_float4(0.f, 0.f, 0.f, 0.f);
+      zj = 0.f;
+      float zn = 0.f, nz = 0.f;
+      if (valid) {
+        v = rf_row[j];
+        zj = z_row[j];
+        if (j + 1 < S) zn = z_row[j + 1];
+        if (noise) nz = noise[ray * S + j];
+      }
+      dist = (j + 1 < S) ? __fsub_rn(zn, zj) : 1e10f;
+      dist = __fmul_rn(dist, norm);
+      sigma = fmaxf(__fadd_rn(v.w, nz), 0.0f);
+      e = expf(-__fmul_rn(sigma, dist));
+      return valid;
+    };
+    // pass 1: transmittance carried into each chunk
+    double carry = 1.0;
+    for (int c = 0; c < n_chunks; ++c) {
+      float4 v; float zj, dist, sigma, e;
+      const bool valid = sample(c * 32 + lane, v, zj, dist, sigma, e);
+      const float alpha = valid ? __fsub_rn(1.0f, e) : 0.0f;
+      const float x = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
+      const double incl = warp_inclusive_product(valid ? (double)x : 1.0, lane);
+      if (lane == 0) s_carry[warp][c] = carry;
+      carry *= __shfl_sync(0xffffffffu, incl, 31);
+    }
+    __syncwarp();
+    // pass 2: chunks in reverse
+    double suffix = 0.0;
+    for (int c = n_chunks - 1; c >= 0; --c) {
+      const int j = c * 32 + lane;
+      float4 v; float zj, dist, sigma, e;
+      const bool valid = sample(j, v, zj, dist, sigma, e);
+      const float alpha = valid ? __fsub_rn(1.0f, e) : 0.0f;
+      const float x = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
+      const double incl = warp_inclusive_product(valid ? (double)x : 1.0, lane);
+      double excl = shfl_up_f64(incl, 1);
+      if (lane == 0) excl = 1.0;
+      const float trans = (float)(s_carry[warp][c] * excl);
+      const float w = __fmul_rn(alpha, trans);
+      const float cr = 1.0f / (1.0f + expf(-v.x)), cg = 1.0f / (1.0f + expf(-v.y)),
+                  cb = 1.0f / (1.0f + expf(-v.z));
+      const float gw = gr * cr + gg * cg + gb * cb + gd * zj + ga;
+      const double p = valid ? (double)gw * (double)w : 0.0;
+      double rev = p;   // inclusive suffix sum over the lanes
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const double o = __shfl_down_sync(0xffffffffu, rev, d);
+        if (lane + d < 32) rev += o;
+      }
+      double after = __shfl_down_sync(0xffffffffu, rev, 1);
+      if (lane == 31) after = 0.0;
+      const double R = after + suffix;
+      suffix += __shfl_sync(0xffffffffu, rev, 0);
+      if (valid) {
+        const float dalpha = (float)((double)gw * (double)trans - R / (double)x);
+        const float dsigma = (sigma > 0.0f) ? dalpha * dist * e : 0.0f;
+        float4 o;
+        o.x = w * gr * cr * (1.0f - cr);
+        o.y = w * gg * cg * (1.0f - cg);
+        o.z = w * gb * cb * (1.0f - cb);
+        o.w = dsigma;
+        d_rf[ray * S + j] = o;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // Stand-alone cumprod_exclusive (nerf/nerf_helpers.py:43-64): one warp per row.
 __global__ void __launch_bounds__(256) cumprod_exclusive_kernel(const float* __restrict__ x,
                                                                 int64_t n, int S,
@@ -218,5 +320,25 @@ extern "C" DEXNERF_API int dexnerf_cumprod_exclusive(const float* x, int64_t n, 
   if (blocks > cap) blocks = cap;
   cumprod_exclusive_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, S, out);
   DN_CHECK_LAUNCH("cumprod_exclusive");
+  return 0;
+}
+
+extern "C" DEXNERF_API int dexnerf_volume_render_backward(const float* rf, const float* z, const float* rd,
+                                                          const float* noise, int64_t n, int S,
+                                                          int white_background, const float* g_rgb,
+                                                          const float* g_depth, const float* g_acc,
+                                                          float* d_rf, void* stream) {
+  DN_REQUIRE(rf && z && rd && d_rf, "volume_render_backward: null pointer");
+  DN_REQUIRE(S >= 1 && S <= 32 * kMaxChunks, "volume_render_backward: S must be in 1..%d", 32 * kMaxChunks);
+  DN_REQUIRE((reinterpret_cast<uintptr_t>(rf) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_rf) & 15) == 0,
+             "volume_render_backward: rf and d_rf must be 16-byte aligned");
+  if (n <= 0) return 0;
+  int64_t blocks = ceil_div64(n, kCompositeWarps);
+  const int64_t cap = (int64_t)kNumSMs * 8 * 4;
+  if (blocks > cap) blocks = cap;
+  composite_bwd_kernel<<<(int)blocks, kCompositeWarps * 32, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(rf), z, rd, noise, n, S, white_background, g_rgb, g_depth, g_acc,
+      reinterpret_cast<float4*>(d_rf));
+  DN_CHECK_LAUNCH("volume_render_backward");
   return 0;
 }

@@ -29,34 +29,18 @@
 // Weight-image layout (no swizzle, K-major "interleaved" canonical layout): an operand tile is a
 // grid of 8-row x 16-byte core matrices, each 128 contiguous bytes; byte offset of element
 // (row r, k) = (k/8)*LBO + (r/8)*SBO + (r%8)*16 + (k%8)*2 with SBO = 128 and LBO = rows*16.
-#include <cuda_bf16.h>
-
-#include "common.cuh"
+#include "tc_plan.cuh"
+#include "tc_ptx.cuh"
 
 namespace dexnerf {
 namespace tc {
 
-constexpr int kTileM = 128;
 constexpr int kSlotBytes = 16384;
 constexpr int kNumSlots = 9;
-constexpr int kMaxLayers = 16;
 constexpr int kThreads = 768;   // 4 control warps + 16 epilogue warps + 4 encoder warps
 constexpr int kEpiThreadsPerTile = 256;
 constexpr int kPeXyzBytes = kTileM * 64 * 2;  // 16 KB, K padded to 64
 constexpr int kPeDirBytes = kTileM * 32 * 2;  // 8 KB,  K padded to 32
-constexpr int kMaxConstFloats = 4096;
-constexpr uint32_t kSpinLimit = 1u << 22;   // ~ a second of polling, then trap
-
-struct TcLayer {
-  int k_main;    // K read from the TMEM-resident activations (0 for layer1)
-  int smem_src;  // 0 none, 1 xyz encoding, 2 dir encoding
-  int k_smem;    // padded K of the shared-memory operand
-  int n_out;     // output features
-  int n_pass;    // passes of 128 (or n_out when smaller)
-  int relu;
-  int head;      // 1: sigma head is evaluated in this layer's epilogue, 2: rgb head + final store
-  int bias_off;  // into the const block (floats)
-};
 
 struct TcParams {
   const uint8_t* weights;  // chunk images, consumption order
@@ -70,199 +54,15 @@ struct TcParams {
   int off_walpha, off_balpha, off_wrgb, off_brgb;
   int Lx, Ld, include_xyz, include_dir, log_xyz, log_dir, dim_xyz, dim_dir;
   int dbg_layer, dbg_pass;
+  // training tape (kTape kernels only): bf16 operand images of every layer input, in the
+  // MN-major half-tile layout the weight-gradient GEMM consumes ([tile][half][fg][64 rows][8]),
+  // plus one ReLU bit per activation ([tile][slot][128 rows] x 64 bits)
+  uint8_t* tape;
+  int64_t tape_xyz, tape_dir;            // byte offsets of the encoding images
+  int64_t tape_act[kMaxLayers];          // ... of each tensor-core layer's OUTPUT image
+  int64_t tape_mask[kMaxLayers];         // ... of its ReLU mask (unused for layers without ReLU)
   TcLayer layers[kMaxLayers];
 };
-
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must end in a trap (launch failure), never in a hung GPU.
-__device__ __noinline__ void barrier_timeout(int who) {
-  printf("dexnerf mlp_tc: barrier timeout (wait site %d, block %d, thread %d)\n", who, blockIdx.x, threadIdx.x);
-  __trap();
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int who) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > kSpinLimit) barrier_timeout(who);
-  }
-}
-// Four barrier polls issued back to back (their ~100-cycle latencies overlap); falls back to the
-// bounded sequential wait when any of them is not complete yet.
-__device__ __forceinline__ void mbar_wait4(uint32_t b0, uint32_t p0, uint32_t b1, uint32_t p1, uint32_t b2,
-                                           uint32_t p2, uint32_t b3, uint32_t p3, int who) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred q0, q1, q2, q3;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 q0, [%1], %2;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 q1, [%3], %4;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 q2, [%5], %6;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 q3, [%7], %8;\n\t"
-      "and.pred q0, q0, q1;\n\tand.pred q2, q2, q3;\n\tand.pred q0, q0, q2;\n\t"
-      "selp.u32 %0, 1, 0, q0;\n\t}"
-      : "=r"(ok) : "r"(b0), "r"(p0), "r"(b1), "r"(p1), "r"(b2), "r"(p2), "r"(b3), "r"(p3) : "memory");
-  if (!ok) { mbar_wait(b0, p0, who); mbar_wait(b1, p1, who); mbar_wait(b2, p2, who); mbar_wait(b3, p3, who); }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
-}
-__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-// split-phase accumulator load: issue now, make the registers valid later with tmem_ld32_wait
-__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr) : "memory");
-}
-// the registers are listed as read-write so that no use of them can be scheduled above the wait
-__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.wait::ld.sync.aligned;"
-      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-        "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
-        "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
-        "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-      :: "memory");
-}
-__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-// Same, but also lists the slice that is about to be processed as read-write: every use of `cur`
-// is then ordered AFTER this load has been issued, so its latency overlaps the arithmetic on `cur`
-// (the compiler would otherwise sink the issue below the arithmetic to save registers).
-__device__ __forceinline__ void tmem_ld16_issue_tied(uint32_t taddr, uint32_t (&r)[16], uint32_t (&cur)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "+r"(cur[0]), "+r"(cur[1]), "+r"(cur[2]), "+r"(cur[3]), "+r"(cur[4]), "+r"(cur[5]), "+r"(cur[6]), "+r"(cur[7]),
-        "+r"(cur[8]), "+r"(cur[9]), "+r"(cur[10]), "+r"(cur[11]), "+r"(cur[12]), "+r"(cur[13]), "+r"(cur[14]), "+r"(cur[15])
-      : "r"(taddr));
-}
-// read-only constants (biases, head weights) straight from shared memory; not volatile, so the
-// compiler may hoist these loads above the TMEM waits
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-  float4 v;
-  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.wait::ld.sync.aligned;"
-      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-        "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-               : "memory");
-}
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// two fp32 -> packed bf16x2 (lo = first K element), optional ReLU
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi, bool relu) {
-  uint32_t d;
-  if (relu) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-  return d;
-}
-// shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor, version 1)
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
-}
-// instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M = 128
-__device__ __forceinline__ uint32_t instr_desc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-}
-
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
 
 // sin and cos of an fp32 argument of any magnitude the encodings reach (|arg| < ~1e4): two-term
 // Cody-Waite reduction by 2*pi (exact product in the FMA, one rounding) to [-pi, pi], then the
@@ -282,7 +82,8 @@ __device__ __forceinline__ void sincos_reduced(float arg, float& s, float& c) {
 // every column's (band, axis, sin|cos) is a compile-time constant and only one band's six values
 // are live at a time.
 template <int kGroups>
-__device__ __forceinline__ void encode_row_std(const float (&x)[3], int dim, bool valid, uint8_t* dst) {
+__device__ __forceinline__ void encode_row_std(const float (&x)[3], int dim, bool valid, uint8_t* dst,
+                                               uint8_t* tape_dst) {
   float sv[3] = {0.f, 0.f, 0.f}, cv[3] = {0.f, 0.f, 0.f};
 #pragma unroll
   for (int k8 = 0; k8 < kGroups; ++k8) {
@@ -310,7 +111,22 @@ __device__ __forceinline__ void encode_row_std(const float (&x)[3], int dim, boo
       w4[j] = pack_bf16(e[0], e[1], false);
     }
     *reinterpret_cast<uint4*>(dst + k8 * (kTileM * 16)) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+    if (tape_dst) *reinterpret_cast<uint4*>(tape_dst + k8 * 1024) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
   }
+}
+
+// ReLU bits of eight packed bf16 pairs (values are >= +0 after cvt.relu): bit 2i / 2i+1 = lo / hi
+__device__ __forceinline__ uint32_t relu_bits16(const uint32_t* w) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    m |= ((w[i] & 0x7FFFu) ? 1u : 0u) << (2 * i);
+    m |= ((w[i] & 0x7FFF0000u) ? 1u : 0u) << (2 * i + 1);
+  }
+  return m;
+}
+__device__ __forceinline__ void stg128(uint8_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d);
 }
 
 // ------------------------------------------------------------------ shared-memory map
@@ -343,10 +159,12 @@ __device__ __forceinline__ int chunks_in_pass(const TcLayer& L) { return L.k_mai
 // sample row; two warps per 32-row quarter split the columns): + bias, optional sigma head,
 // optional ReLU, pack to bf16, then either keep the packed words in registers (first pass of a
 // 256-wide layer) or store them as the next layer's A operand.
-template <bool kRelu, bool kSig, bool kHold, bool kPark, bool kDbg>
+template <bool kRelu, bool kSig, bool kHold, bool kPark, bool kDbg, bool kTape>
 __device__ __forceinline__ void epilogue_pass(uint32_t d_tmem, uint32_t a_park, uint32_t a_store, uint32_t bias,
                                               uint32_t wa, float& sigma, uint32_t (&held)[32],
-                                              uint32_t dfree_bar, float* dbg_dst, long long* stamps) {
+                                              uint32_t dfree_bar, float* dbg_dst, long long* stamps,
+                                              uint8_t* tape_row, uint2* tape_mask) {
+  uint32_t mbits[2] = {0u, 0u};
   uint32_t v[2][16];      // 16-column slices of the accumulator
   if (kDbg && stamps) stamps[0] = clock64();
   tmem_ld16_issue(d_tmem, v[0]);
@@ -387,6 +205,13 @@ __device__ __forceinline__ void epilogue_pass(uint32_t d_tmem, uint32_t a_park, 
       }
     }
     if (!kHold) tmem_st8(a_store + (uint32_t)(c * 8), pk);
+    if (kTape) {
+      // this thread's 16 outputs of the slice = two 16-byte feature groups of its row
+      const uint32_t* wd = kHold ? &held[c * 8] : pk;
+      stg128(tape_row + (2 * c) * 1024, wd[0], wd[1], wd[2], wd[3]);
+      stg128(tape_row + (2 * c + 1) * 1024, wd[4], wd[5], wd[6], wd[7]);
+      if (kRelu) mbits[c >> 1] |= relu_bits16(wd) << ((c & 1) * 16);
+    }
     if (kDbg && stamps) stamps[1 + c] = clock64();
     if (c == 3) {
       // this warp's columns are fully read (the last wait::ld covered them)
@@ -394,10 +219,11 @@ __device__ __forceinline__ void epilogue_pass(uint32_t d_tmem, uint32_t a_park, 
       mbar_arrive(dfree_bar);
     }
   }
+  if (kTape && kRelu) *tape_mask = make_uint2(mbits[0], mbits[1]);
 }
 
 // ------------------------------------------------------------------ the kernel
-template <int H, bool kDbg>
+template <int H, bool kDbg, bool kTape>
 __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -616,8 +442,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
           const uint32_t d_last = a_tmem + 128 + col0;
           uint32_t v[2][16];
           tmem_ld16_issue(d_last, v[0]);
+          uint32_t ymask[2] = {0u, 0u};
+          uint8_t* y_row = nullptr;
+          if (kTape)
+            y_row = P.tape + P.tape_act[l] + (pair * 2 + t) * (int64_t)(hw * 256) + (row >> 6) * (hw * 128) +
+                    (col0 / 8) * 1024 + (row & 63) * 16;
 #pragma unroll
           for (int c = 0; c < mine / 16; ++c) {
+            uint32_t ypk[8];
             tmem_ld16_wait(v[c & 1]);
             if (c + 1 < mine / 16) tmem_ld16_issue(d_last + (uint32_t)((c + 1) * 16), v[(c + 1) & 1]);
             if (kDbg && l == P.dbg_layer && g < P.m_total) {
@@ -635,11 +467,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
               const float x1 = fmaxf(__uint_as_float(v[c & 1][i + 1]) + b4.y, 0.0f);
               const float x2 = fmaxf(__uint_as_float(v[c & 1][i + 2]) + b4.z, 0.0f);
               const float x3 = fmaxf(__uint_as_float(v[c & 1][i + 3]) + b4.w, 0.0f);
+              if (kTape) { ypk[i / 2] = pack_bf16(x0, x1, false); ypk[i / 2 + 1] = pack_bf16(x2, x3, false); }
               rgb0 = fmaf(x0, r4.x, fmaf(x1, r4.y, fmaf(x2, r4.z, fmaf(x3, r4.w, rgb0))));
               rgb1 = fmaf(x0, g4.x, fmaf(x1, g4.y, fmaf(x2, g4.z, fmaf(x3, g4.w, rgb1))));
               rgb2 = fmaf(x0, u4.x, fmaf(x1, u4.y, fmaf(x2, u4.z, fmaf(x3, u4.w, rgb2))));
             }
+            if (kTape) {
+              stg128(y_row + (2 * c) * 1024, ypk[0], ypk[1], ypk[2], ypk[3]);
+              stg128(y_row + (2 * c + 1) * 1024, ypk[4], ypk[5], ypk[6], ypk[7]);
+              ymask[c >> 1] |= relu_bits16(ypk) << ((c & 1) * 16);
+            }
           }
+          if (kTape)
+            reinterpret_cast<uint2*>(P.tape + P.tape_mask[l] + (pair * 2 + t) * (int64_t)2048 + hs * 1024)[row] =
+                make_uint2(ymask[0], ymask[1]);
           tc_fence_before();
           mbar_arrive(bar(B_dfree(t)));
           if (timing && pair == blockIdx.x) tl[256 + ((l * 2) * 2 + t) * 2 + 1] = clock64();
@@ -675,15 +516,24 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
             const uint32_t a_park = a_tmem + (uint32_t)(hs * 32);                 // pass-0 outputs: K [hs*64, +64)
             const uint32_t a_store = a_tmem + (uint32_t)(p * 64 + hs * 32);       // pass-p outputs
             long long* stamps = (timing && pair == blockIdx.x && l == 2) ? tl + 600 + (p * 2 + t) * 16 : nullptr;
+            uint8_t* tape_row = nullptr;
+            uint2* tape_mask = nullptr;
+            if (kTape) {
+              const int64_t tile = pair * 2 + t;
+              tape_row = P.tape + P.tape_act[l] + tile * (int64_t)(H * 256) + (row >> 6) * (H * 128) +
+                         (p * 16 + hs * 8) * 1024 + (row & 63) * 16;
+              tape_mask = reinterpret_cast<uint2*>(P.tape + P.tape_mask[l] + tile * (int64_t)((H / 128) * 2 * 1024) +
+                                                   (p * 2 + hs) * 1024) + row;
+            }
             if (hold) {
-              if (kind == 0) epilogue_pass<false, false, true, false, kDbg>(d_tmem, a_park, a_store, bp, wp, sigma, held, dfree, dbg_dst, stamps);
-              else if (kind == 1) epilogue_pass<true, false, true, false, kDbg>(d_tmem, a_park, a_store, bp, wp, sigma, held, dfree, dbg_dst, stamps);
-              else epilogue_pass<true, true, true, false, kDbg>(d_tmem, a_park, a_store, bp, wp, sigma, held, dfree, dbg_dst, stamps);
+              if (kind == 0) epilogue_pass<false, false, true, false, kDbg, kTape>(d_tmem, a_park, a_store, bp, wp, sigma, held, dfree, dbg_dst, stamps, tape_row, tape_mask);
+              else if (kind == 1) epilogue_pass<true, false, true, false, kDbg, kTape>(d_tmem, a_park, a_store, bp, wp, sigma, held, dfree, dbg_dst, stamps, tape_row, tape_mask);
+              else epilogue_pass<true, true, true, false, kDbg, kTape>(d_tmem, a_park, a_store, bp, wp, sigma, held, dfree, dbg_dst, stamps, tape_row, tape_mask);
             } else {
               constexpr bool park = kTwoPass;
-              if (kind == 0) epilogue_pass<false, false, false, park, kDbg>(d_tmem, a_park, a_store, bp, wp, sigma, held, dfree, dbg_dst, stamps);
-              else if (kind == 1) epilogue_pass<true, false, false, park, kDbg>(d_tmem, a_park, a_store, bp, wp, sigma, held, dfree, dbg_dst, stamps);
-              else epilogue_pass<true, true, false, park, kDbg>(d_tmem, a_park, a_store, bp, wp, sigma, held, dfree, dbg_dst, stamps);
+              if (kind == 0) epilogue_pass<false, false, false, park, kDbg, kTape>(d_tmem, a_park, a_store, bp, wp, sigma, held, dfree, dbg_dst, stamps, tape_row, tape_mask);
+              else if (kind == 1) epilogue_pass<true, false, false, park, kDbg, kTape>(d_tmem, a_park, a_store, bp, wp, sigma, held, dfree, dbg_dst, stamps, tape_row, tape_mask);
+              else epilogue_pass<true, true, false, park, kDbg, kTape>(d_tmem, a_park, a_store, bp, wp, sigma, held, dfree, dbg_dst, stamps, tape_row, tape_mask);
               if (kDbg && stamps) stamps[9] = clock64();
               tmem_wait_st();
               if (kDbg && stamps) stamps[10] = clock64();
@@ -716,8 +566,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
         }
         mbar_wait(bar(B_xyzempty(t)), ph ^ 1, 6);
         uint8_t* xyz = smem + Smem::pe_xyz + t * kPeXyzBytes + row * 16;
+        uint8_t* xyz_tape = nullptr;
+        if (kTape)
+          xyz_tape = P.tape + P.tape_xyz + (pair * 2 + t) * (int64_t)16384 + (row >> 6) * 8192 + (row & 63) * 16;
         if (std_xyz) {
-          encode_row_std<8>(pt, P.dim_xyz, valid, xyz);
+          encode_row_std<8>(pt, P.dim_xyz, valid, xyz, xyz_tape);
         } else {
           for (int k8 = 0; k8 < 8; ++k8) {   // 8 encoding columns = one 16-byte core-matrix row
             uint32_t w4[4];
@@ -729,6 +582,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
               w4[j] = pack_bf16(e0, e1, false);
             }
             *reinterpret_cast<uint4*>(xyz + k8 * (kTileM * 16)) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            if (kTape) stg128(xyz_tape + k8 * 1024, w4[0], w4[1], w4[2], w4[3]);
           }
         }
         fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -745,8 +599,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
         }
         mbar_wait(bar(B_dirempty(t)), ph ^ 1, 7);
         uint8_t* dr = smem + Smem::pe_dir + t * kPeDirBytes + row * 16;
+        uint8_t* dir_tape = nullptr;
+        if (kTape)
+          dir_tape = P.tape + P.tape_dir + (pair * 2 + t) * (int64_t)8192 + (row >> 6) * 4096 + (row & 63) * 16;
         if (std_dir) {
-          encode_row_std<4>(dir, P.dim_dir, valid, dr);
+          encode_row_std<4>(dir, P.dim_dir, valid, dr, dir_tape);
         } else {
           for (int k8 = 0; k8 < 4; ++k8) {
             uint32_t w4[4];
@@ -758,6 +615,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
               w4[j] = pack_bf16(e0, e1, false);
             }
             *reinterpret_cast<uint4*>(dr + k8 * (kTileM * 16)) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            if (kTape) stg128(dir_tape + k8 * 1024, w4[0], w4[1], w4[2], w4[3]);
           }
         }
         fence_proxy_async();
@@ -774,59 +632,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
   }
 }
 
-// ------------------------------------------------------------------ host: layer table + packing
-struct HostLayer { TcLayer tc; int prog_op; };
-
-struct Plan {
-  int n_layers = 0;
-  HostLayer layers[kMaxLayers];
-  int op_alpha = -1, op_rgb = -1;
-  int off_walpha = 0, off_balpha = 0, off_wrgb = 0, off_brgb = 0, n_const = 0;
-  int64_t weight_bytes = 0;
-  int kx = 0, kd = 0;
-};
-
-static int pad16(int v) { return (v + 15) / 16 * 16; }
-
-static int make_plan(const dexnerf_flexible_spec* s, Plan* plan) {
-  DN_REQUIRE(s, "tc: null spec");
-  DN_REQUIRE(s->hidden == 256 || s->hidden == 128, "tc: hidden must be 128 or 256 (got %d)", s->hidden);
-  DN_REQUIRE(s->n_trunk >= 1 && s->n_trunk + 3 <= kMaxLayers, "tc: unsupported trunk depth %d", s->n_trunk);
-  DN_REQUIRE(s->skip_every >= 1, "tc: skip_every < 1");
-  DN_REQUIRE(s->dim_xyz >= 1 && s->dim_xyz <= 64, "tc: dim_xyz must be <= 64 (got %d)", s->dim_xyz);
-  DN_REQUIRE(s->dim_dir >= 1 && s->dim_dir <= 32, "tc: dim_dir must be in 1..32 (got %d)", s->dim_dir);
-  Plan& P = *plan;
-  const int H = s->hidden;
-  P.kx = pad16(s->dim_xyz);
-  P.kd = pad16(s->dim_dir);
-  int bias = 0, op = 0;
-  auto add = [&](int k_main, int src, int k_smem, int n_out, int relu, int head, int prog_op) {
-    HostLayer& L = P.layers[P.n_layers++];
-    L.tc.k_main = k_main; L.tc.smem_src = src; L.tc.k_smem = k_smem; L.tc.n_out = n_out;
-    L.tc.n_pass = (n_out + 127) / 128; L.tc.relu = relu; L.tc.head = head; L.tc.bias_off = bias;
-    L.prog_op = prog_op;
-    bias += (n_out + 127) / 128 * 128;
-    const int np = n_out < 128 ? n_out : 128;
-    P.weight_bytes += (int64_t)L.tc.n_pass * np * (k_main + (src ? k_smem : 0)) * 2;
-  };
-  add(0, 1, P.kx, H, 0, 0, op++);                                    // layer1 (no ReLU)
-  for (int i = 0; i < s->n_trunk; ++i) {
-    const bool skip = (i % s->skip_every == 0) && i > 0;
-    add(H, skip ? 1 : 0, skip ? P.kx : 0, H, 1, i == s->n_trunk - 1 ? 1 : 0, op++);
-  }
-  P.op_alpha = op++;
-  add(H, 0, 0, H, 1, 0, op++);                                        // fc_feat
-  add(H, 2, P.kd, H / 2, 1, 2, op++);                                 // layers_dir[0] (+ fc_rgb head)
-  P.op_rgb = op++;
-  P.off_walpha = bias; bias += H;
-  P.off_balpha = bias; bias += 4;
-  P.off_wrgb = bias; bias += 3 * (H / 2);
-  P.off_brgb = bias; bias += 4;
-  P.n_const = bias;
-  DN_REQUIRE(P.n_const <= kMaxConstFloats, "tc: const block too large");
-  return 0;
-}
-
+// ------------------------------------------------------------------ host: packing
 static int64_t blob_bytes(const Plan& P) { return (int64_t)kMaxConstFloats * 4 + P.weight_bytes; }
 
 struct PackChunk { int64_t dst; int w_off; int n_out; int n0; int np; int k0; int kc; int k_valid; };
@@ -931,16 +737,17 @@ extern "C" DEXNERF_API int dexnerf_tc_pack(const dexnerf_flexible_spec* spec, co
   return 0;
 }
 
-extern "C" DEXNERF_API int dexnerf_tc_query(const dexnerf_flexible_spec* spec, const void* packed, const float* ro,
-                                            const float* rd, const float* viewdirs, const float* z, int64_t n,
-                                            int S, float* rf, float* dbg, int dbg_layer, int dbg_pass,
-                                            void* stream) {
+static int tc_query_impl(const dexnerf_flexible_spec* spec, const void* packed, const float* ro, const float* rd,
+                         const float* viewdirs, const float* z, int64_t n, int S, float* rf, void* tape,
+                         float* dbg, int dbg_layer, int dbg_pass, void* stream) {
   Plan plan;
   if (int rc = make_plan(spec, &plan)) return rc;
   DN_REQUIRE(packed && ro && rd && viewdirs && z && rf, "tc_query: null pointer");
   DN_REQUIRE(S >= 1, "tc_query: S < 1");
   DN_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 15) == 0 && (reinterpret_cast<uintptr_t>(rf) & 15) == 0,
              "tc_query: packed weights and rf must be 16-byte aligned");
+  DN_REQUIRE((reinterpret_cast<uintptr_t>(tape) & 127) == 0, "tc_query: the tape must be 128-byte aligned");
+  DN_REQUIRE(!(tape && dbg), "tc_query: the debug taps are not available in the training variant");
   if (n <= 0) return 0;
   TcParams P{};
   P.consts = reinterpret_cast<const float*>(packed);
@@ -957,6 +764,14 @@ extern "C" DEXNERF_API int dexnerf_tc_query(const dexnerf_flexible_spec* spec, c
     if (plan.layers[l].tc.smem_src == 1) P.last_xyz_layer = l;
   }
   const int64_t n_tiles = (P.m_total + kTileM - 1) / kTileM, n_pairs = (n_tiles + 1) / 2;
+  if (tape) {
+    // the kernel always processes whole tile PAIRS, so the tape is laid out for an even tile count
+    TapeLayout T;
+    make_tape_layout(plan, n_pairs * 2, &T);
+    P.tape = reinterpret_cast<uint8_t*>(tape);
+    P.tape_xyz = T.xyz; P.tape_dir = T.dir;
+    for (int l = 0; l < plan.n_layers; ++l) { P.tape_act[l] = T.act[l]; P.tape_mask[l] = T.mask[l]; }
+  }
   const int grid = (int)(n_pairs < kNumSMs ? n_pairs : kNumSMs);
   const size_t smem = Smem::total + 1024;
   cudaStream_t st = (cudaStream_t)stream;
@@ -966,9 +781,38 @@ extern "C" DEXNERF_API int dexnerf_tc_query(const dexnerf_flexible_spec* spec, c
     return 0;
   };
   int rc;
-  if (spec->hidden == 256) rc = dbg ? launch(mlp_tc_kernel<256, true>) : launch(mlp_tc_kernel<256, false>);
-  else rc = dbg ? launch(mlp_tc_kernel<128, true>) : launch(mlp_tc_kernel<128, false>);
+  if (spec->hidden == 256)
+    rc = tape ? launch(mlp_tc_kernel<256, false, true>)
+              : (dbg ? launch(mlp_tc_kernel<256, true, false>) : launch(mlp_tc_kernel<256, false, false>));
+  else
+    rc = tape ? launch(mlp_tc_kernel<128, false, true>)
+              : (dbg ? launch(mlp_tc_kernel<128, true, false>) : launch(mlp_tc_kernel<128, false, false>));
   if (rc) return rc;
   DN_CHECK_LAUNCH("mlp_tc");
   return 0;
+}
+
+extern "C" DEXNERF_API int dexnerf_tc_query(const dexnerf_flexible_spec* spec, const void* packed, const float* ro,
+                                            const float* rd, const float* viewdirs, const float* z, int64_t n,
+                                            int S, float* rf, float* dbg, int dbg_layer, int dbg_pass,
+                                            void* stream) {
+  return tc_query_impl(spec, packed, ro, rd, viewdirs, z, n, S, rf, nullptr, dbg, dbg_layer, dbg_pass, stream);
+}
+
+extern "C" DEXNERF_API int64_t dexnerf_tc_tape_bytes(const dexnerf_flexible_spec* spec, int64_t n_samples) {
+  Plan plan;
+  if (make_plan(spec, &plan)) return -1;
+  if (n_samples < 0) { set_error("tc_tape_bytes: negative sample count"); return -1; }
+  const int64_t n_pairs = ((n_samples + kTileM - 1) / kTileM + 1) / 2;
+  TapeLayout T;
+  make_tape_layout(plan, n_pairs * 2, &T);
+  return T.total;
+}
+
+extern "C" DEXNERF_API int dexnerf_tc_query_train(const dexnerf_flexible_spec* spec, const void* packed,
+                                                  const float* ro, const float* rd, const float* viewdirs,
+                                                  const float* z, int64_t n, int S, float* rf, void* tape,
+                                                  void* stream) {
+  DN_REQUIRE(tape, "tc_query_train: null tape");
+  return tc_query_impl(spec, packed, ro, rd, viewdirs, z, n, S, rf, tape, nullptr, -1, 0, stream);
 }

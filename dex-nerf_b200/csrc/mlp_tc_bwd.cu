@@ -1,0 +1,707 @@
+// tcgen05 backward of FlexibleNeRFModel (nerf/models.py:185-256, repaired forward) for the
+// training step of BASELINE config 4 (train_dexnerf_rgb.py:264-281: loss.backward()).
+//
+// The forward (mlp_tc.cu, kTape) leaves a TAPE in HBM: the bf16 input image of every layer and
+// one ReLU bit per activation (tc_plan.cuh, TapeLayout).  The backward is two kernels:
+//
+//   mlp_tc_bwd_dx_kernel   the activation-gradient chain.  Same machine as the forward: one
+//       persistent CTA per SM, pairs of 128-sample tiles, gradients G_l = dL/d(pre-activation_l)
+//       resident in TENSOR MEMORY as the bf16 A operand, TRANSPOSED weight images streamed by bulk
+//       TMA into a shared-memory ring, D = G_{l+1} . W_l[:, :H] accumulated in TMEM, epilogue =
+//       (+ d sigma * w_alpha) -> ReLU mask from the tape -> bf16 -> next A operand.  The first
+//       operand (G of layers_dir[0]) comes from d rgb through fc_rgb on the CUDA cores.  Every G is
+//       also written to the tape as an MN-major bf16 image.
+//   mlp_tc_bwd_dw_kernel   the weight gradients dWt_l[in][out] = X_l^T . G_l: a split-K GEMM whose
+//       K dimension is the SAMPLES.  Both operands are the tape images (MN-major UMMA operands,
+//       loaded by 1-D bulk copies, 3-stage mbarrier ring of 64-sample half-tiles), accumulators for
+//       up to 2 x 128 input features x 256 outputs fill the 512 TMEM columns, CTAs split the tiles
+//       of a layer in proportion to its bytes and reduce with red.global.add.f32.  Bias gradients
+//       are column sums of G taken from the shared-memory image by the otherwise idle warps.
+//
+// Arithmetic contract: bf16-rounded G and activations as tensor-core operands, fp32 accumulation;
+// fc_alpha / fc_rgb gradients use the same bf16 images.  oracle.train_step(bf16=True) is the
+// statement of this contract; the fp32 reference gradients are matched to bf16 tolerance.
+#include "tc_plan.cuh"
+#include "tc_ptx.cuh"
+
+namespace dexnerf {
+namespace tc {
+
+// =====================================================================================
+//                                  dX chain kernel
+// =====================================================================================
+constexpr int kBSlotBytes = 16384;   // one transposed chunk: 128 in-features x 64 out-features
+constexpr int kBSlots = 11;
+constexpr int kBThreads = 640;       // 4 control warps + 16 epilogue warps
+constexpr int kBEpiThreads = 256;    // per tile
+
+struct BwdParams {
+  const uint8_t* weights_t;   // transposed chunk images in consumption order
+  const float* consts;        // forward const block (w_alpha, W_rgb live there)
+  const float4* d_rf;         // dL/d(rgb, sigma) per sample
+  uint8_t* tape;
+  int64_t m_total;
+  int nl;                     // tensor-core layers of the forward (layer1, trunk.., fc_feat, dir)
+  int n_const, off_walpha, off_wrgb;
+  int64_t mask_off[kMaxLayers];
+  int64_t grad_off[kMaxLayers];
+  int64_t ghead_off;
+  int relu[kMaxLayers];       // forward ReLU flag of each layer (its G needs the mask)
+};
+
+struct BSmem {
+  static constexpr int w_slots = 0;
+  static constexpr int consts = w_slots + kBSlots * kBSlotBytes;
+  static constexpr int bars = consts + kMaxConstFloats * 4;
+  static constexpr int n_bars = 2 * kBSlots + 6;
+  static constexpr int tmem_ptr = bars + n_bars * 8;
+  static constexpr int total = tmem_ptr + 16;
+};
+__device__ __forceinline__ int BB_wfull(int s) { return s; }
+__device__ __forceinline__ int BB_wempty(int s) { return kBSlots + s; }
+__device__ __forceinline__ int BB_aready(int t) { return 2 * kBSlots + t; }
+__device__ __forceinline__ int BB_dfull(int t) { return 2 * kBSlots + 2 + t; }
+__device__ __forceinline__ int BB_dfree(int t) { return 2 * kBSlots + 4 + t; }
+
+// One backward epilogue pass of one warp over its 64 accumulator columns: optional rank-1 term
+// d_sigma * w_alpha, optional ReLU mask, bf16 pack, A-operand store (held / parked / direct) and
+// the MN-major tape image of G.
+template <bool kAdd, bool kHold, bool kPark, bool kStore>
+__device__ __forceinline__ void bwd_epilogue_pass(uint32_t d_tmem, uint32_t a_park, uint32_t a_store, bool use_mask,
+                                                  uint2 mask, float dsig, uint32_t wa, uint32_t (&held)[32],
+                                                  uint32_t dfree_bar, uint8_t* tape_row) {
+  uint32_t v[2][16];
+  tmem_ld16_issue(d_tmem, v[0]);
+  if (kPark) {
+    tmem_st16(a_park, &held[0]);
+    tmem_st16(a_park + 16, &held[16]);
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    tmem_ld16_wait(v[c & 1]);
+    if (c + 1 < 4) tmem_ld16_issue(d_tmem + (uint32_t)((c + 1) * 16), v[(c + 1) & 1]);
+    const uint32_t bits = ((c < 2 ? mask.x : mask.y) >> ((c & 1) * 16)) & 0xFFFFu;
+    uint32_t pk[8];
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      float x0 = __uint_as_float(v[c & 1][i]), x1 = __uint_as_float(v[c & 1][i + 1]);
+      float x2 = __uint_as_float(v[c & 1][i + 2]), x3 = __uint_as_float(v[c & 1][i + 3]);
+      if (kAdd) {
+        const float4 w4 = lds128(wa + (uint32_t)((c * 16 + i) * 4));
+        x0 = fmaf(dsig, w4.x, x0); x1 = fmaf(dsig, w4.y, x1);
+        x2 = fmaf(dsig, w4.z, x2); x3 = fmaf(dsig, w4.w, x3);
+      }
+      if (use_mask) {
+        x0 = (bits >> i) & 1u ? x0 : 0.0f;       x1 = (bits >> (i + 1)) & 1u ? x1 : 0.0f;
+        x2 = (bits >> (i + 2)) & 1u ? x2 : 0.0f; x3 = (bits >> (i + 3)) & 1u ? x3 : 0.0f;
+      }
+      if (kHold) {
+        held[c * 8 + i / 2] = pack_bf16(x0, x1, false);
+        held[c * 8 + i / 2 + 1] = pack_bf16(x2, x3, false);
+      } else {
+        pk[i / 2] = pack_bf16(x0, x1, false);
+        pk[i / 2 + 1] = pack_bf16(x2, x3, false);
+      }
+    }
+    const uint32_t* wd = kHold ? &held[c * 8] : pk;
+    if (kStore) tmem_st8(a_store + (uint32_t)(c * 8), wd);
+    *reinterpret_cast<uint4*>(tape_row + (2 * c) * 1024) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+    *reinterpret_cast<uint4*>(tape_row + (2 * c + 1) * 1024) = make_uint4(wd[4], wd[5], wd[6], wd[7]);
+    if (c == 3) {
+      tc_fence_before();
+      mbar_arrive(dfree_bar);
+    }
+  }
+}
+
+template <int H>
+__global__ void __launch_bounds__(kBThreads, 1) mlp_tc_bwd_dx_kernel(const __grid_constant__ BwdParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bars = sbase + BSmem::bars;
+  auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_tiles = (P.m_total + kTileM - 1) / kTileM;
+  const int64_t n_pairs = (n_tiles + 1) / 2;
+  constexpr int kPass = H / 128;          // N = 128 passes of a layer
+  const int n_steps = P.nl - 1;           // MMA layers: step j consumes G[nl-1-j], produces G[nl-2-j]
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kBSlots; ++s) { mbar_init(bar(BB_wfull(s)), 1); mbar_init(bar(BB_wempty(s)), 2); }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(bar(BB_aready(t)), kBEpiThreads);
+      mbar_init(bar(BB_dfull(t)), 1);
+      mbar_init(bar(BB_dfree(t)), kBEpiThreads);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + BSmem::tmem_ptr), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  {
+    float* c = reinterpret_cast<float*>(smem + BSmem::consts);
+    for (int i = threadIdx.x; i < P.n_const; i += kBThreads) c[i] = P.consts[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + BSmem::tmem_ptr);
+
+  if (warp == 0) {
+    // =============================== weight producer ===============================
+    const bool leader = elect_one();
+    uint32_t cnt = 0;
+#pragma unroll 1
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      const uint8_t* src = P.weights_t;
+#pragma unroll 1
+      for (int j = 0; j < n_steps; ++j) {
+        const int nc = (j == 0 ? H / 2 : H) / 64;
+#pragma unroll 1
+        for (int pc = 0; pc < kPass * nc; ++pc, ++cnt) {
+          const uint32_t slot = cnt % kBSlots, ph = (cnt / kBSlots) & 1;
+          mbar_wait(bar(BB_wempty(slot)), ph ^ 1, 10);
+          if (leader) {
+            mbar_arrive_expect_tx(bar(BB_wfull(slot)), kBSlotBytes);
+            bulk_g2s(sbase + BSmem::w_slots + slot * kBSlotBytes, src, kBSlotBytes, bar(BB_wfull(slot)));
+          }
+          __syncwarp();
+          src += kBSlotBytes;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    const bool leader = elect_one();
+    uint32_t w_slot = 0, w_phase = 0;
+    uint32_t ph_dfree[2] = {0, 0}, ph_aready[2] = {0, 0};
+    const uint64_t desc_hi = ((uint64_t)(128 >> 4) << 32) | (1ull << 46);   // SBO = 128 B, version 1
+    const uint32_t slot0_lo = ((sbase + BSmem::w_slots) >> 4) & 0x3FFF;
+    const uint32_t idesc = instr_desc(128);
+    constexpr uint32_t b_lbo16 = 128;      // LBO = 128 rows * 16 B, in 16-byte units
+#pragma unroll 1
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+#pragma unroll 1
+      for (int j = 0; j < n_steps; ++j) {
+        const int nc = (j == 0 ? H / 2 : H) / 64;
+#pragma unroll 1
+        for (int p = 0; p < kPass; ++p) {
+          const uint32_t slot_p = w_slot, phase_p = w_phase;
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const uint32_t a_tmem = tmem_base + (uint32_t)(t * 256);
+            const uint32_t d_tmem = a_tmem + 128;
+            if (p == 0) {
+              mbar_wait(bar(BB_aready(t)), ph_aready[t], 11);
+              ph_aready[t] ^= 1;
+            } else {
+              mbar_wait(bar(BB_dfree(t)), ph_dfree[t] ^ 1, 12);
+            }
+            ph_dfree[t] ^= 1;
+            uint32_t slot = slot_p, phase = phase_p;
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < nc; ++c) {
+              if (t == 0) { mbar_wait(bar(BB_wfull(slot)), phase, 13); tc_fence_after(); }
+              const uint32_t b_lo = (slot0_lo + slot * (kBSlotBytes >> 4)) | (b_lbo16 << 16);
+              if (leader) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  mma_ts(d_tmem, a_tmem + (uint32_t)(c * 32 + ks * 8),
+                         desc_hi | (uint64_t)(b_lo + (uint32_t)ks * 2 * b_lbo16), idesc, (c | ks) ? 1u : 0u);
+                tc_commit(bar(BB_wempty(slot)));
+              }
+              __syncwarp();
+              if (++slot == kBSlots) { slot = 0; phase ^= 1; }
+            }
+            if (leader) tc_commit(bar(BB_dfull(t)));
+            __syncwarp();
+            if (t == 1) { w_slot = slot; w_phase = phase; }
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // =============================== epilogue ===============================
+    const int e = warp - 4;
+    const int t = e >> 3, hs = (e >> 2) & 1, q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const uint32_t a_tmem = tmem_base + (uint32_t)(t * 256) + lane_base;
+    const uint32_t d_tmem = a_tmem + 128 + (uint32_t)(hs * 64);
+    const float* s_const = reinterpret_cast<const float*>(smem + BSmem::consts);
+    uint32_t ph_dfull = 0;
+    uint32_t held[32];
+    const int half = row >> 6, r64 = row & 63;
+#pragma unroll 1
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      const int64_t tile = pair * 2 + t;
+      const int64_t g = tile * kTileM + row;
+      const float4 d = (g < P.m_total) ? P.d_rf[g] : make_float4(0.f, 0.f, 0.f, 0.f);
+      // ---- G of layers_dir[0]: (W_rgb^T d_rgb) masked by y > 0, on the CUDA cores
+      {
+        constexpr int hw = H / 2, mine = hw / 2;
+        const int col0 = hs * mine;
+        const int ld = P.nl - 1;
+        const uint2 ym = reinterpret_cast<const uint2*>(P.tape + P.mask_off[ld] + tile * 2048 + hs * 1024)[row];
+        const float* wr = s_const + P.off_wrgb + col0;
+        uint8_t* trow = P.tape + P.grad_off[ld] + tile * (int64_t)(hw * 256) + half * (hw * 128) +
+                        (col0 / 8) * 1024 + r64 * 16;
+#pragma unroll
+        for (int c = 0; c < mine / 16; ++c) {
+          const uint32_t bits = ((c < 2 ? ym.x : ym.y) >> ((c & 1) * 16)) & 0xFFFFu;
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            const int k = c * 16 + i;
+            float x0 = fmaf(d.x, wr[k], fmaf(d.y, wr[hw + k], d.z * wr[2 * hw + k]));
+            float x1 = fmaf(d.x, wr[k + 1], fmaf(d.y, wr[hw + k + 1], d.z * wr[2 * hw + k + 1]));
+            x0 = (bits >> i) & 1u ? x0 : 0.0f;
+            x1 = (bits >> (i + 1)) & 1u ? x1 : 0.0f;
+            pk[i / 2] = pack_bf16(x0, x1, false);
+          }
+          tmem_st8(a_tmem + (uint32_t)(col0 / 2 + c * 8), pk);
+          *reinterpret_cast<uint4*>(trow + (2 * c) * 1024) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(trow + (2 * c + 1) * 1024) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+        if (hs == 0) {   // the head operand [d rgb, d sigma, 0 ...] (16 features) for dW of fc_rgb / fc_alpha
+          uint8_t* hrow = P.tape + P.ghead_off + tile * 4096 + half * 2048 + r64 * 16;
+          *reinterpret_cast<uint4*>(hrow) = make_uint4(pack_bf16(d.x, d.y, false), pack_bf16(d.z, d.w, false), 0u, 0u);
+          *reinterpret_cast<uint4*>(hrow + 1024) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(bar(BB_aready(t)));
+      }
+      // the bf16-rounded d sigma, as the tensor-core operand of dW(fc_alpha) sees it
+      const float dsig = __bfloat162float(__float2bfloat16_rn(d.w));
+#pragma unroll 1
+      for (int j = 0; j < n_steps; ++j) {
+        const int dst = P.nl - 2 - j;
+        const bool last = (j == n_steps - 1);
+        const bool use_mask = P.relu[dst] != 0;
+        const bool add = (j == 1);
+#pragma unroll
+        for (int p = 0; p < kPass; ++p) {
+          uint2 mask = make_uint2(0u, 0u);
+          if (use_mask)
+            mask = reinterpret_cast<const uint2*>(P.tape + P.mask_off[dst] + tile * (int64_t)(kPass * 2 * 1024) +
+                                                  (p * 2 + hs) * 1024)[row];
+          uint8_t* trow = P.tape + P.grad_off[dst] + tile * (int64_t)(H * 256) + half * (H * 128) +
+                          (p * 16 + hs * 8) * 1024 + r64 * 16;
+          const uint32_t wa = sbase + BSmem::consts + (uint32_t)(P.off_walpha + p * 128 + hs * 64) * 4;
+          const uint32_t a_park = a_tmem + (uint32_t)(hs * 32);
+          const uint32_t a_store = a_tmem + (uint32_t)(p * 64 + hs * 32);
+          const uint32_t dfree = bar(BB_dfree(t));
+          mbar_wait(bar(BB_dfull(t)), ph_dfull, 14);
+          ph_dfull ^= 1;
+          tc_fence_after();
+          if (last) {
+            bwd_epilogue_pass<false, false, false, false>(d_tmem, a_park, a_store, use_mask, mask, dsig, wa, held, dfree, trow);
+          } else if (kPass == 2 && p == 0) {
+            if (add) bwd_epilogue_pass<true, true, false, false>(d_tmem, a_park, a_store, use_mask, mask, dsig, wa, held, dfree, trow);
+            else bwd_epilogue_pass<false, true, false, false>(d_tmem, a_park, a_store, use_mask, mask, dsig, wa, held, dfree, trow);
+          } else {
+            constexpr bool park = (kPass == 2);
+            if (add) bwd_epilogue_pass<true, false, park, true>(d_tmem, a_park, a_store, use_mask, mask, dsig, wa, held, dfree, trow);
+            else bwd_epilogue_pass<false, false, park, true>(d_tmem, a_park, a_store, use_mask, mask, dsig, wa, held, dfree, trow);
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(bar(BB_aready(t)));
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ---- transposed weight images for the dX chain (one 16 KB chunk = 128 in-features x 64 out-features)
+struct BwdPackChunk { int w_off, ld, n0, k0; };
+struct BwdPackParams { int n_chunks; BwdPackChunk chunks[200]; };
+
+__global__ void pack_weights_t_kernel(const float* __restrict__ params, const __grid_constant__ BwdPackParams Q,
+                                      uint8_t* __restrict__ blob) {
+  for (int ci = blockIdx.y; ci < Q.n_chunks; ci += gridDim.y) {
+    const BwdPackChunk c = Q.chunks[ci];
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < 128 * 64; e += gridDim.x * blockDim.x) {
+      const int n = e >> 6, k = e & 63;          // k fastest: coalesced reads of Wt[n][k0 + k]
+      const float w = params[c.w_off + (int64_t)(c.n0 + n) * c.ld + c.k0 + k];
+      const int64_t off = (int64_t)ci * kBSlotBytes + (k >> 3) * (128 * 16) + n * 16 + (k & 7) * 2;
+      *reinterpret_cast<__nv_bfloat16*>(blob + off) = __float2bfloat16_rn(w);
+    }
+  }
+}
+
+// =====================================================================================
+//                              weight-gradient GEMM kernel
+// =====================================================================================
+constexpr int kWStageA = 32768;     // up to 2 M-blocks x 16 feature groups x 64 samples x 16 B
+constexpr int kWStageG = 32768;     // up to 32 feature groups (N = 256)
+constexpr int kWStages = 3;
+constexpr int kWThreads = 256;      // producer, MMA issuer, TMEM allocator, (idle), 4 reducer warps
+constexpr int kMaxDwItems = 40;
+
+struct DwItem {
+  int64_t a_off;     // tape offset of the A image array
+  int64_t g_off;     // tape offset of the G image array
+  int64_t w_out;     // float offset into `grads` of dWt[first in-feature of this item][0]
+  int64_t b_out;     // float offset of the bias gradient, -1: none
+  int a_fg;          // feature groups of the whole A image (per-tile stride a_fg * 2048)
+  int a_fg0;         // first feature group covered by this item
+  int a_fgs;         // feature groups copied per half-tile (<= 32)
+  int n_mblk;        // M blocks of 128 in-features (1 or 2)
+  int a_rows;        // valid in-features (rows flushed)
+  int g_fg;          // feature groups of G; N = 8 * g_fg
+  int col0, n_cols;  // output columns flushed: D[:, col0 : col0 + n_cols] -> dWt[:, 0 : n_cols]
+  int ld;            // row stride of dWt (out features of the layer)
+  int cta0, n_cta;   // CTAs [cta0, cta0 + n_cta) split this item's tiles
+};
+
+struct DwParams {
+  const uint8_t* tape;
+  float* grads;
+  int64_t n_tiles;
+  int n_items;
+  int variant;       // bring-up knob: bit 0 swaps the LBO / SBO fields of the MN-major descriptors
+  DwItem items[kMaxDwItems];
+};
+
+struct WSmem {
+  static constexpr int a = 0;
+  static constexpr int g = a + kWStages * kWStageA;
+  static constexpr int bars = g + kWStages * kWStageG;
+  static constexpr int n_bars = 2 * kWStages + 1;
+  static constexpr int tmem_ptr = bars + n_bars * 8;
+  static constexpr int total = tmem_ptr + 16;
+};
+
+__device__ __forceinline__ void red_add_f32(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(kWThreads, 1) mlp_tc_bwd_dw_kernel(const __grid_constant__ DwParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bars = sbase + WSmem::bars;
+  auto full = [&](int s) { return bars + 8u * (uint32_t)s; };
+  auto empty = [&](int s) { return bars + 8u * (uint32_t)(kWStages + s); };
+  const uint32_t acc_bar = bars + 8u * (uint32_t)(2 * kWStages);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // which item / which slice of its tiles
+  int it = 0;
+  while (it + 1 < P.n_items && (int)blockIdx.x >= P.items[it].cta0 + P.items[it].n_cta) ++it;
+  const DwItem& I = P.items[it];
+  const int split = (int)blockIdx.x - I.cta0;
+  const int64_t tile_begin = P.n_tiles * split / I.n_cta, tile_end = P.n_tiles * (split + 1) / I.n_cta;
+  const int64_t n_stage_total = (tile_end - tile_begin) * 2;     // half-tiles
+  const uint32_t a_bytes = (uint32_t)I.a_fgs * 1024u, g_bytes = (uint32_t)I.g_fg * 1024u;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1 + 128); }
+    mbar_init(acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + WSmem::tmem_ptr), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  // the MMA reads 16 feature groups per M block even when the image has fewer: keep the tail finite
+  for (int i = threadIdx.x; i < kWStages * kWStageA / 16; i += kWThreads)
+    reinterpret_cast<uint4*>(smem + WSmem::a)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + WSmem::tmem_ptr);
+
+  if (warp == 0) {
+    // =============================== producer ===============================
+    const bool leader = elect_one();
+#pragma unroll 1
+    for (int64_t s = 0; s < n_stage_total; ++s) {
+      const int st = (int)(s % kWStages);
+      const uint32_t ph = (uint32_t)((s / kWStages) & 1);
+      mbar_wait(empty(st), ph ^ 1, 20);
+      if (leader) {
+        const int64_t tile = tile_begin + (s >> 1);
+        const int half = (int)(s & 1);
+        const uint8_t* a_src = P.tape + I.a_off + tile * (int64_t)(I.a_fg * 2048) + (int64_t)half * (I.a_fg * 1024) +
+                               (int64_t)I.a_fg0 * 1024;
+        const uint8_t* g_src = P.tape + I.g_off + tile * (int64_t)(I.g_fg * 2048) + (int64_t)half * (I.g_fg * 1024);
+        mbar_arrive_expect_tx(full(st), a_bytes + g_bytes);
+        bulk_g2s(sbase + WSmem::a + st * kWStageA, a_src, a_bytes, full(st));
+        bulk_g2s(sbase + WSmem::g + st * kWStageG, g_src, g_bytes, full(st));
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    const bool leader = elect_one();
+    const int N = I.g_fg * 8;
+    // bf16 x bf16 -> fp32, M = 128, both operands MN-major (bits 15 / 16)
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    // canonical MN-major no-swizzle layout: 8 K-rows x 16 B core matrices; K-adjacent core matrices
+    // 128 B apart (leading byte offset), MN-adjacent ones 1024 B apart (stride byte offset)
+    uint32_t lbo = 128 >> 4, sbo = 1024 >> 4;
+    if (P.variant & 1) { const uint32_t x = lbo; lbo = sbo; sbo = x; }
+    const uint64_t desc_hi = ((uint64_t)sbo << 32) | (1ull << 46);
+#pragma unroll 1
+    for (int64_t s = 0; s < n_stage_total; ++s) {
+      const int st = (int)(s % kWStages);
+      const uint32_t ph = (uint32_t)((s / kWStages) & 1);
+      mbar_wait(full(st), ph, 21);
+      tc_fence_after();
+      const uint32_t a_lo = (((sbase + WSmem::a + st * kWStageA) >> 4) & 0x3FFF) | (lbo << 16);
+      const uint32_t g_lo = (((sbase + WSmem::g + st * kWStageG) >> 4) & 0x3FFF) | (lbo << 16);
+      if (leader) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {        // 64 samples = 4 x K16; a K step = 2 core matrices = 256 B
+          for (int mb = 0; mb < I.n_mblk; ++mb)
+            mma_ss(tmem_base + (uint32_t)(mb * 256),
+                   desc_hi | (uint64_t)(a_lo + (uint32_t)(mb * 16384 + ks * 256) / 16),
+                   desc_hi | (uint64_t)(g_lo + (uint32_t)(ks * 256) / 16), idesc, (s | ks) ? 1u : 0u);
+        }
+        tc_commit(empty(st));
+      }
+      __syncwarp();
+    }
+    if (leader) tc_commit(acc_bar);
+    __syncwarp();
+  } else if (warp >= 4) {
+    // =============================== bias column sums + final reduction ===============================
+    const int j = threadIdx.x - 128;            // 0..127: features 2j, 2j+1 of G
+    const bool has_bias = I.b_out >= 0;
+    const bool mine = has_bias && j < I.g_fg * 4;
+    const int fg = j >> 2, w = j & 3;
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll 1
+    for (int64_t s = 0; s < n_stage_total; ++s) {
+      const int st = (int)(s % kWStages);
+      const uint32_t ph = (uint32_t)((s / kWStages) & 1);
+      mbar_wait(full(st), ph, 22);
+      if (mine) {
+        const uint8_t* gs = smem + WSmem::g + st * kWStageG + fg * 1024 + w * 4;
+#pragma unroll 8
+        for (int r = 0; r < 64; ++r) {
+          const uint32_t v = *reinterpret_cast<const uint32_t*>(gs + ((r + fg) & 63) * 16);   // staggered: no bank conflicts
+          s0 += __uint_as_float(v << 16);
+          s1 += __uint_as_float(v & 0xFFFF0000u);
+        }
+      }
+      mbar_arrive(empty(st));
+    }
+    if (mine) {
+      const int c0 = 2 * j - I.col0;
+      if (c0 >= 0 && c0 < I.n_cols) red_add_f32(P.grads + I.b_out + c0, s0);
+      if (c0 + 1 >= 0 && c0 + 1 < I.n_cols) red_add_f32(P.grads + I.b_out + c0 + 1, s1);
+    }
+    // ---- accumulators -> global (one thread per in-feature row, TMEM lane = row within the M block)
+    if (n_stage_total > 0) {
+      mbar_wait(acc_bar, 0, 23);
+      tc_fence_after();
+      const int q = warp & 3;
+      const int row = q * 32 + lane;
+      const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+      for (int mb = 0; mb < I.n_mblk; ++mb) {
+        const int r = mb * 128 + row;
+        float* dst = P.grads + I.w_out + (int64_t)r * I.ld;
+        for (int c = 0; c < I.g_fg * 8; c += 16) {
+          float v[16];
+          tmem_ld16(tmem_base + lane_base + (uint32_t)(mb * 256 + c), v);      // warp-collective
+          if (r < I.a_rows) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int cc = c + i - I.col0;
+              if (cc >= 0 && cc < I.n_cols) red_add_f32(dst + cc, v[i]);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+}  // namespace tc
+}  // namespace dexnerf
+
+using namespace dexnerf;
+using namespace dexnerf::tc;
+
+// chunks of the dX chain in consumption order: step j uses forward layer nl-1-j, N passes of 128
+// in-features, K chunks of 64 out-features
+static int bwd_chunk_count(const Plan& plan, int H) {
+  int n = 0;
+  for (int j = 0; j < plan.n_layers - 1; ++j) n += (H / 128) * ((j == 0 ? H / 2 : H) / 64);
+  return n;
+}
+
+extern "C" DEXNERF_API int64_t dexnerf_tc_packed_bwd_bytes(const dexnerf_flexible_spec* spec) {
+  Plan plan;
+  if (make_plan(spec, &plan)) return -1;
+  return (int64_t)bwd_chunk_count(plan, spec->hidden) * kBSlotBytes;
+}
+
+extern "C" DEXNERF_API int dexnerf_tc_pack_bwd(const dexnerf_flexible_spec* spec, const dexnerf_mlp_program* prog,
+                                               const float* params, void* packed_t, void* stream) {
+  Plan plan;
+  if (int rc = make_plan(spec, &plan)) return rc;
+  DN_REQUIRE(prog && params && packed_t, "tc_pack_bwd: null pointer");
+  DN_REQUIRE(prog->n_ops == plan.n_layers + 2, "tc_pack_bwd: program has %d ops, expected %d", prog->n_ops,
+             plan.n_layers + 2);
+  const int H = spec->hidden;
+  BwdPackParams Q{};
+  for (int j = 0; j < plan.n_layers - 1; ++j) {
+    const int l = plan.n_layers - 1 - j;
+    const dexnerf_op& op = prog->ops[plan.layers[l].prog_op];
+    const int K = (j == 0) ? H / 2 : H;          // out features of forward layer l
+    DN_REQUIRE(op.out_dim == K && op.src0_dim == H, "tc_pack_bwd: op %d is not a hidden layer", plan.layers[l].prog_op);
+    for (int p = 0; p < H / 128; ++p)
+      for (int c = 0; c < K / 64; ++c) {
+        DN_REQUIRE(Q.n_chunks < 200, "tc_pack_bwd: too many chunks");
+        BwdPackChunk& pc = Q.chunks[Q.n_chunks++];
+        pc.w_off = (int)op.w_off; pc.ld = op.out_dim; pc.n0 = p * 128; pc.k0 = c * 64;
+      }
+  }
+  pack_weights_t_kernel<<<dim3(4, Q.n_chunks), 256, 0, (cudaStream_t)stream>>>(params, Q, reinterpret_cast<uint8_t*>(packed_t));
+  DN_CHECK_LAUNCH("pack_weights_t");
+  return 0;
+}
+
+// Tape layout for `n_samples` samples as 64-bit byte offsets (host array, 4 + 3 * 16 + 3 entries):
+// out[0] = tensor-core layer count nl, out[1] = tile count, out[2] = total bytes, out[3] = ghead,
+// out[4] = xyz, out[5] = dir, out[6 + l] = act[l], out[22 + l] = mask[l], out[38 + l] = grad[l].
+extern "C" DEXNERF_API int dexnerf_tc_tape_layout(const dexnerf_flexible_spec* spec, int64_t n_samples, int64_t* out) {
+  Plan plan;
+  if (int rc = make_plan(spec, &plan)) return rc;
+  DN_REQUIRE(out && n_samples >= 0, "tc_tape_layout: bad argument");
+  const int64_t n_pairs = ((n_samples + kTileM - 1) / kTileM + 1) / 2;
+  TapeLayout T;
+  make_tape_layout(plan, n_pairs * 2, &T);
+  out[0] = plan.n_layers; out[1] = T.n_tiles; out[2] = T.total; out[3] = T.ghead; out[4] = T.xyz; out[5] = T.dir;
+  for (int l = 0; l < kMaxLayers; ++l) { out[6 + l] = T.act[l]; out[22 + l] = T.mask[l]; out[38 + l] = T.grad[l]; }
+  return 0;
+}
+
+// what: bit 0 = run the dX chain, bit 1 = run the weight-gradient GEMM (both for a training step)
+extern "C" DEXNERF_API int dexnerf_tc_backward(const dexnerf_flexible_spec* spec, const dexnerf_mlp_program* prog,
+                                               const void* packed, const void* packed_t, void* tape,
+                                               const float* d_rf, int64_t n, int S, float* grads, int what,
+                                               int variant, void* stream) {
+  Plan plan;
+  if (int rc = make_plan(spec, &plan)) return rc;
+  DN_REQUIRE(prog && packed && packed_t && tape && d_rf && grads, "tc_backward: null pointer");
+  DN_REQUIRE(prog->n_ops == plan.n_layers + 2, "tc_backward: program has %d ops, expected %d", prog->n_ops,
+             plan.n_layers + 2);
+  DN_REQUIRE((reinterpret_cast<uintptr_t>(tape) & 127) == 0 && (reinterpret_cast<uintptr_t>(d_rf) & 15) == 0 &&
+             (reinterpret_cast<uintptr_t>(packed_t) & 15) == 0, "tc_backward: misaligned pointer");
+  DN_REQUIRE(S >= 1, "tc_backward: S < 1");
+  if (n <= 0) return 0;
+  const int H = spec->hidden;
+  const int nl = plan.n_layers;
+  const int64_t m_total = n * (int64_t)S;
+  const int64_t n_tiles = (m_total + kTileM - 1) / kTileM, n_pairs = (n_tiles + 1) / 2;
+  TapeLayout T;
+  make_tape_layout(plan, n_pairs * 2, &T);
+  cudaStream_t st = (cudaStream_t)stream;
+
+  if (what & 1) {
+    BwdParams P{};
+    P.weights_t = reinterpret_cast<const uint8_t*>(packed_t);
+    P.consts = reinterpret_cast<const float*>(packed);
+    P.d_rf = reinterpret_cast<const float4*>(d_rf);
+    P.tape = reinterpret_cast<uint8_t*>(tape);
+    P.m_total = m_total;
+    P.nl = nl; P.n_const = plan.n_const; P.off_walpha = plan.off_walpha; P.off_wrgb = plan.off_wrgb;
+    for (int l = 0; l < nl; ++l) {
+      P.mask_off[l] = T.mask[l]; P.grad_off[l] = T.grad[l]; P.relu[l] = plan.layers[l].tc.relu;
+    }
+    P.ghead_off = T.ghead;
+    const int grid = (int)(n_pairs < kNumSMs ? n_pairs : kNumSMs);
+    const size_t smem = BSmem::total + 1024;
+    auto launch = [&](auto kernel) -> int {
+      DN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kernel<<<grid, kBThreads, smem, st>>>(P);
+      return 0;
+    };
+    const int rc = (H == 256) ? launch(mlp_tc_bwd_dx_kernel<256>) : launch(mlp_tc_bwd_dx_kernel<128>);
+    if (rc) return rc;
+    DN_CHECK_LAUNCH("mlp_tc_bwd_dx");
+  }
+
+  if (what & 2) {
+    DwParams W{};
+    W.tape = reinterpret_cast<const uint8_t*>(tape);
+    W.grads = grads;
+    W.n_tiles = n_pairs * 2;
+    W.variant = variant;
+    double cost[kMaxDwItems];
+    auto add = [&](int64_t a_off, int a_fg, int a_fg0, int a_fgs, int a_rows, int64_t g_off, int g_fg, int64_t w_out,
+                   int64_t b_out, int col0, int n_cols, int ld) {
+      DwItem& I = W.items[W.n_items];
+      I.a_off = a_off; I.a_fg = a_fg; I.a_fg0 = a_fg0; I.a_fgs = a_fgs; I.n_mblk = (a_fgs + 15) / 16;
+      I.a_rows = a_rows; I.g_off = g_off; I.g_fg = g_fg; I.w_out = w_out; I.b_out = b_out;
+      I.col0 = col0; I.n_cols = n_cols; I.ld = ld;
+      cost[W.n_items] = (double)(a_fgs + g_fg);
+      ++W.n_items;
+    };
+    const int hfg = H / 8;
+    for (int l = 0; l < nl; ++l) {
+      const TcLayer& L = plan.layers[l].tc;
+      const dexnerf_op& op = prog->ops[plan.layers[l].prog_op];
+      const int gfg = L.n_out / 8;
+      int64_t w_row = op.w_off;
+      bool bias_done = false;
+      if (L.k_main) {      // hidden-input part: rows [0, H) of Wt
+        add(T.act[l - 1], hfg, 0, hfg, H, T.grad[l], gfg, w_row, op.b_off, 0, L.n_out, L.n_out);
+        bias_done = true;
+        w_row += (int64_t)H * L.n_out;
+      }
+      if (L.smem_src == 1)
+        add(T.xyz, 8, 0, 8, spec->dim_xyz, T.grad[l], gfg, w_row, bias_done ? -1 : op.b_off, 0, L.n_out, L.n_out);
+      else if (L.smem_src == 2)
+        add(T.dir, 4, 0, 4, spec->dim_dir, T.grad[l], gfg, w_row, bias_done ? -1 : op.b_off, 0, L.n_out, L.n_out);
+    }
+    {   // heads: fc_alpha reads the last trunk output, fc_rgb the dir-layer output; G = [d rgb, d sigma, 0..]
+      const dexnerf_op& oa = prog->ops[plan.op_alpha];
+      const dexnerf_op& orgb = prog->ops[plan.op_rgb];
+      add(T.act[nl - 3], hfg, 0, hfg, H, T.ghead, 2, oa.w_off, oa.b_off, 3, 1, 1);
+      add(T.act[nl - 1], hfg / 2, 0, hfg / 2, H / 2, T.ghead, 2, orgb.w_off, orgb.b_off, 0, 3, 3);
+    }
+    DN_REQUIRE(W.n_items <= kMaxDwItems, "tc_backward: too many weight-gradient items");
+    // CTAs per item in proportion to its bytes per tile, at least one, about 2 waves in total
+    double total = 0;
+    for (int i = 0; i < W.n_items; ++i) total += cost[i];
+    int64_t budget = 2 * kNumSMs;
+    if (budget > W.n_tiles * W.n_items) budget = W.n_tiles * W.n_items;
+    int cta = 0;
+    for (int i = 0; i < W.n_items; ++i) {
+      int64_t k = (int64_t)(cost[i] / total * (double)budget + 0.5);
+      if (k < 1) k = 1;
+      if (k > W.n_tiles) k = W.n_tiles;
+      W.items[i].cta0 = cta; W.items[i].n_cta = (int)k;
+      cta += (int)k;
+    }
+    const size_t smem = WSmem::total + 1024;
+    DN_CUDA(cudaFuncSetAttribute(mlp_tc_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mlp_tc_bwd_dw_kernel<<<cta, kWThreads, smem, st>>>(W);
+    DN_CHECK_LAUNCH("mlp_tc_bwd_dw");
+  }
+  return 0;
+}

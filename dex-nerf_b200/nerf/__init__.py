@@ -16,4 +16,5 @@ from .nerf_helpers import (cumprod_exclusive, gather_cdf_util, get_embedding_fun
 from .train_utils import (get_precision, predict_and_render_radiance, run_network, run_one_iter_of_nerf,
                           sample_pdf, set_precision)
 from .sharding import allreduce_gradients, gather_rows, row_block
+from .training import learning_rate, train_step
 from .volume_rendering_utils import volume_render_radiance_field

@@ -38,6 +38,25 @@ def _fusable(model, embed_fn, embeddirs_fn):
             and (model.dim_dir == 0 or (embeddirs_fn is not None and embeddirs_fn.out_dim == model.dim_dir)))
 
 
+def _trainable(model, embed_fn, embeddirs_fn):
+    from . import tensorcore
+    return (_fusable(model, embed_fn, embeddirs_fn)
+            and tensorcore.supported(model, model.program(embed_fn, embeddirs_fn if model.dim_dir else None)))
+
+
+_warned_no_grad = False
+
+
+def _warn_no_grad():
+    global _warned_no_grad
+    if not _warned_no_grad:
+        import warnings
+        warnings.warn("dexnerf: gradients are implemented on the tensor-core path only (FlexibleNeRFModel with "
+                      "view directions, hidden 128/256, get_embedding_function encoders, precision 'bf16'); "
+                      "this call returns outputs WITHOUT a grad_fn, so loss.backward() will raise")
+        _warned_no_grad = True
+
+
 kernel_event_log = None   # bench.py sets this to a list to collect (name, start_evt, end_evt, n, S)
 
 
@@ -131,12 +150,29 @@ def predict_and_render_radiance(ray_batch, model_coarse, model_fine, options, mo
         t_rand = L.dev_f32(t_rand, "t_rand")
     z = _coarse_depths(n, near, far, Nc, opt.lindisp, t_rand, dev)
 
-    rf = _field(model_coarse, ro, rd, viewdirs, z, rays, opt.chunksize, encode_position_fn, encode_direction_fn)
+    from . import training
+    # Gradients are recorded in "train" mode only (the reference's scripts render validation frames
+    # under torch.no_grad(), train_dexnerf_rgb.py:317; a full frame's tape would not fit anyway).
+    with_grad = n > 0 and mode == "train" and training.wants_grad(model_coarse, model_fine)
+    if with_grad and not (_precision == "bf16" and _trainable(model_coarse, encode_position_fn, encode_direction_fn)
+                          and _trainable(model_fine, encode_position_fn, encode_direction_fn)):
+        _warn_no_grad()
+        with_grad = False
     noise = rng.get("noise_coarse")
     if noise is None and std > 0.0:
         noise = torch.randn((n, Nc), dtype=torch.float32, device=dev) * std
-    c = render_maps(rf, z, rd, noise, opt.white_background, thr, T)
-    rgb_coarse, acc_coarse, depth_coarse = c["rgb"], c["acc"], c["depth"]
+    noise = L.dev_f32(noise, "noise_coarse", allow_none=True)
+    if with_grad:
+        # training: one autograd node per network pass (fused query + tape, compositing; backward =
+        # compositing backward + tensor-core activation / weight gradient kernels)
+        rgb_coarse, depth_coarse, acc_coarse, w_coarse, _ = training.render_field(
+            model_coarse, encode_position_fn, encode_direction_fn, ro, rd, viewdirs, z, noise,
+            opt.white_background, thr, T)
+        c = dict(weights=w_coarse)
+    else:
+        rf = _field(model_coarse, ro, rd, viewdirs, z, rays, opt.chunksize, encode_position_fn, encode_direction_fn)
+        c = render_maps(rf, z, rd, noise, opt.white_background, thr, T)
+        rgb_coarse, acc_coarse, depth_coarse = c["rgb"], c["acc"], c["depth"]
 
     if Nf <= 0:
         # the reference builds its return from depth_fine_dex, which only exists after the fine pass
@@ -149,11 +185,17 @@ def predict_and_render_radiance(ray_batch, model_coarse, model_fine, options, mo
     if n:
         L.check(L.lib().dexnerf_resample_merge(L.ptr(z), L.ptr(c["weights"]), n, Nc, Nf, L.ptr(u), L.ptr(z_fine),
                                                L.stream_ptr()), "resample_merge")
-    rf_f = _field(model_fine, ro, rd, viewdirs, z_fine, rays, opt.chunksize, encode_position_fn,
-                  encode_direction_fn)
     noise = rng.get("noise_fine")
     if noise is None and std > 0.0:
         noise = torch.randn((n, Nc + Nf), dtype=torch.float32, device=dev) * std
+    noise = L.dev_f32(noise, "noise_fine", allow_none=True)
+    if with_grad:
+        rgb_f, depth_f, acc_f, _, dex_f = training.render_field(
+            model_fine, encode_position_fn, encode_direction_fn, ro, rd, viewdirs, z_fine, noise,
+            opt.white_background, thr, T)
+        return tuple([rgb_coarse, depth_coarse, acc_coarse, rgb_f, depth_f, acc_f] + [dex_f[t] for t in range(T)])
+    rf_f = _field(model_fine, ro, rd, viewdirs, z_fine, rays, opt.chunksize, encode_position_fn,
+                  encode_direction_fn)
     f = render_maps(rf_f, z_fine, rd, noise, opt.white_background, thr, T, want_weights=False)
     dex = [f["dex"][t] for t in range(T)]
     return tuple([rgb_coarse, depth_coarse, acc_coarse, f["rgb"], f["depth"], f["acc"]] + dex)

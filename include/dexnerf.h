@@ -143,6 +143,39 @@ DEXNERF_API int dexnerf_tc_query(const dexnerf_flexible_spec* spec, const void* 
                      const float* rd, const float* viewdirs, const float* z, int64_t n, int S,
                      float* rf, float* dbg, int dbg_layer, int dbg_pass, void* stream);
 
+/* ---- training (BASELINE config 4; train_dexnerf_rgb.py:246-281 = forward, loss.backward()).
+ *
+ * dexnerf_volume_render_backward: backward of volume_render_radiance_field w.r.t. the radiance
+ * field.  g_rgb (n,3), g_depth (n), g_acc (n) are dL/d(rgb_map, depth_map, acc_map) (any may be
+ * NULL = zero); d_rf (n,S,4) receives dL/d(radiance_field).  rf, z, rd, noise, white_background as
+ * in the forward call. */
+DEXNERF_API int dexnerf_volume_render_backward(const float* rf, const float* z, const float* rd,
+                                   const float* noise, int64_t n, int S, int white_background,
+                                   const float* g_rgb, const float* g_depth, const float* g_acc,
+                                   float* d_rf, void* stream);
+
+/* Tensor-core training path of FlexibleNeRFModel.  The forward variant records a TAPE (bf16
+ * operand images of every layer + ReLU bits, dexnerf_tc_tape_bytes() bytes, 128-byte aligned);
+ * the backward consumes it.  See dex-nerf_b200/csrc/mlp_tc_bwd.cu. */
+DEXNERF_API int64_t dexnerf_tc_tape_bytes(const dexnerf_flexible_spec* spec /*host*/, int64_t n_samples);
+/* host-side description of the tape (offsets in bytes; see mlp_tc_bwd.cu); out: 54 int64 */
+DEXNERF_API int dexnerf_tc_tape_layout(const dexnerf_flexible_spec* spec /*host*/, int64_t n_samples,
+                           int64_t* out /*host*/);
+DEXNERF_API int dexnerf_tc_query_train(const dexnerf_flexible_spec* spec, const void* packed, const float* ro,
+                           const float* rd, const float* viewdirs, const float* z, int64_t n, int S,
+                           float* rf, void* tape, void* stream);
+/* transposed bf16 weight images for the activation-gradient chain */
+DEXNERF_API int64_t dexnerf_tc_packed_bwd_bytes(const dexnerf_flexible_spec* spec /*host*/);
+DEXNERF_API int dexnerf_tc_pack_bwd(const dexnerf_flexible_spec* spec, const dexnerf_mlp_program* prog,
+                        const float* params, void* packed_t, void* stream);
+/* d_rf (n,S,4) = dL/d(raw rgb, sigma) per sample -> grads: fp32 buffer in the program layout of
+ * `params` (Wt[in][out] | bias per op), ACCUMULATED into (zero it first).  packed = forward blob,
+ * packed_t = dexnerf_tc_pack_bwd blob.  what: bit 0 activation-gradient chain, bit 1
+ * weight-gradient GEMM (3 = a full backward); variant: 0 (bring-up knob of the GEMM descriptors). */
+DEXNERF_API int dexnerf_tc_backward(const dexnerf_flexible_spec* spec, const dexnerf_mlp_program* prog,
+                        const void* packed, const void* packed_t, void* tape, const float* d_rf,
+                        int64_t n, int S, float* grads, int what, int variant, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -357,6 +357,7 @@ def render_rays(ro: torch.Tensor, rd: torch.Tensor, model_coarse, model_fine, o:
         raise NameError("num_fine == 0 is unsupported by the reference (train_utils.py:201)")
     z_mid = 0.5 * (z[..., 1:] + z[..., :-1])
     z_samples = sample_pdf(z_mid, w_c[..., 1:-1], o.num_fine, det=(not o.perturb), u=u)
+    z_samples = z_samples.detach()                       # train_utils.py:170
     z_all = merge_fine(z, z_samples)
     pts = ro[:, None, :] + rd[:, None, :] * z_all[:, :, None]
     rf_f = run_network(model_fine, pts, viewdirs, o, o.chunksize)
@@ -367,6 +368,54 @@ def render_rays(ro: torch.Tensor, rd: torch.Tensor, model_coarse, model_fine, o:
         return out, dict(z_coarse=z, weights_coarse=w_c, z_samples=z_samples, z_fine=z_all,
                          rf_coarse=rf, rf_fine=rf_f, weights_fine=f[3], disp_fine=f[1])
     return out
+
+
+# --------------------------------------------------------------------------------------
+# a-10  training iteration                                   train_dexnerf_rgb.py:246-289
+# --------------------------------------------------------------------------------------
+def img2mse(img_src: torch.Tensor, img_tgt: torch.Tensor) -> torch.Tensor:
+    """nerf_helpers.py:9-10 (== torch.nn.functional.mse_loss, mean over all elements)."""
+    return ((img_src - img_tgt) ** 2).mean()
+
+
+def train_loss_and_grads(sd_coarse: Dict[str, torch.Tensor], sd_fine: Dict[str, torch.Tensor],
+                         ro: torch.Tensor, rd: torch.Tensor, target: torch.Tensor, o: RenderOptions,
+                         m_thres_cand: Sequence[float], skip_coarse: int = 4, skip_fine: int = 4,
+                         t_rand=None, u=None, noise_coarse=None, noise_fine=None, bf16: bool = False):
+    """One training iteration's loss and parameter gradients (train_dexnerf_rgb.py:246-278):
+    train-mode render with the four RNG draws replayed, loss = mse(rgb_coarse, target) +
+    mse(rgb_fine, target), autograd backward.  Gradients do not flow through the fine depths
+    (train_utils.py:170).  Returns (loss, coarse_loss, fine_loss, grads_coarse, grads_fine)."""
+    pc = {k: v.detach().clone().to(F32).requires_grad_(True) for k, v in sd_coarse.items()}
+    pf = {k: v.detach().clone().to(F32).requires_grad_(True) for k, v in sd_fine.items()}
+    out = render_rays(ro, rd, lambda x: flexible_forward(pc, x, skip_coarse, bf16=bf16),
+                      lambda x: flexible_forward(pf, x, skip_fine, bf16=bf16), o, m_thres_cand,
+                      t_rand=t_rand, u=u, noise_coarse=noise_coarse, noise_fine=noise_fine)
+    coarse_loss = img2mse(out[0][..., :3], target[..., :3])
+    fine_loss = img2mse(out[3][..., :3], target[..., :3])
+    loss = coarse_loss + fine_loss
+    loss.backward()
+    gc = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in pc.items()}
+    gf = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in pf.items()}
+    return loss.detach(), coarse_loss.detach(), fine_loss.detach(), gc, gf
+
+
+def adam_step(params: Dict[str, torch.Tensor], grads: Dict[str, torch.Tensor], lr: float, step: int = 1,
+              m=None, v=None, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8):
+    """torch.optim.Adam's update (train_dexnerf_rgb.py:142-148, defaults) restated; returns new params."""
+    out = {}
+    for k, p in params.items():
+        g = grads[k]
+        mk = (1 - beta1) * g if m is None else beta1 * m[k] + (1 - beta1) * g
+        vk = (1 - beta2) * g * g if v is None else beta2 * v[k] + (1 - beta2) * g * g
+        mhat, vhat = mk / (1 - beta1 ** step), vk / (1 - beta2 ** step)
+        out[k] = p - lr * mhat / (vhat.sqrt() + eps)
+    return out
+
+
+def learning_rate(base_lr: float, iteration: int, lr_decay: float, lr_decay_factor: float) -> float:
+    """train_dexnerf_rgb.py:283-289."""
+    return base_lr * (lr_decay_factor ** (iteration / (lr_decay * 1000)))
 
 
 # --------------------------------------------------------------------------------------

@@ -1,0 +1,376 @@
+"""Training path on the GPU (BASELINE config 4): compositing backward, the training tape of the
+tensor-core forward, the activation-gradient chain, the weight-gradient GEMM and the whole
+training iteration against the reference-generated gradients (tests/golden/train_grads.npz) and
+the CPU oracle.  Tolerances are written at each comparison."""
+import numpy as np
+import pytest
+import torch
+
+import nerf
+from nerf import _lib as L
+from nerf import tensorcore, training
+from oracle import nerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+t = torch.from_numpy
+
+
+def bf(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def rel_err(a, b):
+    return float((a - b).norm() / (b.norm() + 1e-20))
+
+
+# ------------------------------------------------------------------ compositing backward
+@pytest.mark.parametrize("n,S,white,with_noise", [(37, 48, False, False), (33, 64, True, True), (9, 192, False, True),
+                                                  (5, 5, True, False), (300, 384, False, False)])
+def test_volume_render_backward(n, S, white, with_noise):
+    """dL/d(radiance_field) of volume_render_radiance_field against autograd through the oracle
+    (fp32 graph, fp64 scans).  Bar: 2e-5 of the largest gradient entry per tensor."""
+    g = torch.Generator().manual_seed(n * 1000 + S)
+    rf = torch.randn(n, S, 4, generator=g)
+    rf[..., 3] = 3.0 * torch.randn(n, S, generator=g) + 0.5
+    rf[0, :, 3] = -1.0                      # nothing absorbs
+    if n > 2:
+        rf[2, :-1, 3] = -5.0
+        rf[2, -1, 3] = 0.5                  # only the last (1e10) sample absorbs
+    z = torch.sort(2.0 + 4.0 * torch.rand(n, S, generator=g), dim=-1).values
+    rd = torch.randn(n, 3, generator=g)
+    noise = 0.2 * torch.randn(n, S, generator=g) if with_noise else None
+    g_rgb, g_depth, g_acc = torch.randn(n, 3, generator=g), torch.randn(n, generator=g), torch.randn(n, generator=g)
+    rfo = rf.clone().requires_grad_(True)
+    res = O.volume_render_radiance_field(rfo, z, rd, 0.0, white, [], noise=noise)
+    ((res[0] * g_rgb).sum() + (res[4] * g_depth).sum() + (res[2] * g_acc).sum()).backward()
+    got = training.volume_render_backward(rf.cuda(), z.cuda(), rd.cuda(), None if noise is None else noise.cuda(),
+                                          white, g_rgb.cuda(), g_depth.cuda(), g_acc.cuda()).cpu()
+    ref = rfo.grad
+    assert torch.isfinite(got).all()
+    for ch in range(4):
+        scale = float(ref[..., ch].abs().max()) + 1e-12
+        assert float((got[..., ch] - ref[..., ch]).abs().max()) <= 2e-5 * scale, ch
+    # rgb-only upstream gradient (what the training loss produces): NULL depth / acc pointers
+    got2 = training.volume_render_backward(rf.cuda(), z.cuda(), rd.cuda(), None if noise is None else noise.cuda(),
+                                           white, g_rgb.cuda(), None, None).cpu()
+    rfo2 = rf.clone().requires_grad_(True)
+    res = O.volume_render_radiance_field(rfo2, z, rd, 0.0, white, [], noise=noise)
+    (res[0] * g_rgb).sum().backward()
+    assert float((got2 - rfo2.grad).abs().max()) <= 2e-5 * float(rfo2.grad.abs().max())
+
+
+# ------------------------------------------------------------------ helpers for the tensor-core path
+def make_model(hidden, layers, skip, Lx, seed=3, boost=30.0):
+    torch.manual_seed(seed)
+    m = nerf.FlexibleNeRFModel(layers, hidden, skip, Lx, 4)
+    with torch.no_grad():
+        m.fc_alpha.weight.mul_(boost)
+        m.fc_alpha.bias.fill_(1.0)
+    return m.cuda()
+
+
+def make_rays(n, S, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    ro = (torch.randn(n, 3, generator=g) * 0.3).cuda()
+    rd = torch.randn(n, 3, generator=g).cuda()
+    vd = rd / rd.norm(dim=-1, keepdim=True)
+    z = torch.sort(2 + 4 * torch.rand(n, S, generator=g), dim=-1).values.cuda()
+    return ro, rd, vd, z
+
+
+def emulate_forward(model, enc_xyz, enc_dir):
+    """bf16-operand emulation in torch (on the GPU): list of the bf16 OUTPUT of every tensor-core
+    layer, in the kernel's layer order, and the final (rgb, sigma)."""
+    sd = {k: v.detach().float() for k, v in model.state_dict().items()}
+    skip, n_trunk = model.skip_connect_every, len(model.layers_xyz)
+    xyz, dr = bf(enc_xyz), bf(enc_dir)
+    acts = []
+    h = xyz @ bf(sd["layer1.weight"]).t() + sd["layer1.bias"]
+    acts.append(bf(h))
+    for i in range(n_trunk):
+        inp = bf(h)
+        if i % skip == 0 and i > 0:
+            inp = torch.cat((inp, xyz), -1)
+        h = torch.relu(inp @ bf(sd[f"layers_xyz.{i}.weight"]).t() + sd[f"layers_xyz.{i}.bias"])
+        acts.append(bf(h))
+    sigma = h @ sd["fc_alpha.weight"].t() + sd["fc_alpha.bias"]
+    feat = torch.relu(bf(h) @ bf(sd["fc_feat.weight"]).t() + sd["fc_feat.bias"])
+    acts.append(bf(feat))
+    y = torch.relu(torch.cat((bf(feat), dr), -1) @ bf(sd["layers_dir.0.weight"]).t() + sd["layers_dir.0.bias"])
+    acts.append(bf(y))
+    rgb = y @ sd["fc_rgb.weight"].t() + sd["fc_rgb.bias"]
+    return acts, torch.cat((rgb, sigma), -1)
+
+
+def run_forward_with_tape(model, Lx, n, S, seed=0):
+    ex, ed = nerf.get_embedding_function(Lx, True, True), nerf.get_embedding_function(4, True, True)
+    prog = model.program(ex, ed)
+    spec = tensorcore.spec_for(model, prog)
+    ro, rd, vd, z = make_rays(n, S, seed)
+    rf, tape = training.query_train(model, prog, spec, ro, rd, vd, z)
+    torch.cuda.synchronize()
+    lay = training.tape_layout(spec, n * S)
+    pts = (ro[:, None, :] + rd[:, None, :] * z[:, :, None]).reshape(-1, 3)
+    enc_xyz = ex(pts)
+    enc_dir = ed(vd[:, None, :].expand(n, S, 3).reshape(-1, 3).contiguous())
+    return dict(prog=prog, spec=spec, rf=rf, tape=tape, lay=lay, enc_xyz=enc_xyz, enc_dir=enc_dir, n=n, S=S,
+                ro=ro, rd=rd, vd=vd, z=z)
+
+
+CONFIGS = [(256, 8, 4, 10), (128, 8, 3, 6)]
+
+
+@pytest.mark.parametrize("hidden,layers,skip,Lx", CONFIGS)
+def test_forward_tape(hidden, layers, skip, Lx):
+    """The training variant of the forward returns the same field as the inference kernel and its
+    tape holds the bf16 operand image of every layer plus the ReLU bits."""
+    model = make_model(hidden, layers, skip, Lx)
+    n, S = 7, 50                       # 350 samples: 3 tiles -> padded to 2 pairs
+    r = run_forward_with_tape(model, Lx, n, S)
+    M = n * S
+    rf_inf = torch.empty_like(r["rf"])
+    tensorcore.query(model, r["prog"], r["ro"], r["rd"], r["vd"], r["z"], rf_inf)
+    assert torch.equal(rf_inf, r["rf"])
+    acts, out = emulate_forward(model, r["enc_xyz"], r["enc_dir"])
+    lay, tape = r["lay"], r["tape"]
+    nt = lay["n_tiles"]
+    assert nt == 4 and lay["nl"] == layers + 2
+    dx, dd = model.dim_xyz, model.dim_dir
+    img = training.decode_image(tape, lay["xyz"], nt, 64)[:M]
+    assert float((img[:, :dx] - bf(r["enc_xyz"])).abs().max()) <= 2 ** -7      # one bf16 ulp of |x| <= 1.x .. sin/cos
+    assert float(img[:, dx:].abs().max()) == 0.0
+    img = training.decode_image(tape, lay["dir"], nt, 32)[:M]
+    assert float((img[:, :dd] - bf(r["enc_dir"])).abs().max()) <= 2 ** -7
+    for l, a in enumerate(acts):
+        width = a.shape[1]
+        img = training.decode_image(tape, lay["act"][l], nt, width)[:M]
+        scale = float(a.abs().max())
+        # bf16 rounding of slightly different fp32 sums: a few ulps on a few entries, 2e-2 relative worst case
+        assert float((img - a).abs().max()) <= 2e-2 * scale, l
+        assert rel_err(img, a) < 3e-3, l
+        if l > 0:                           # ReLU layers: mask bit == (stored activation > 0)
+            slots = 2 * ((width + 127) // 128)      # two 64-column (or narrower) blocks per 128-wide pass
+            words = tape[lay["mask"][l]: lay["mask"][l] + nt * slots * 1024].view(torch.int64).view(nt, slots, 128)
+            cols = width // slots
+            bits = ((words[..., None] >> torch.arange(cols, device="cuda")) & 1).bool()    # tile, slot, row, col
+            bits = bits.permute(0, 2, 1, 3).reshape(nt * 128, width)[:M]
+            assert torch.equal(bits, img > 0), l
+
+
+def emulate_backward(model, r, d_rf):
+    """bf16-operand emulation of the activation-gradient chain using the TAPE's own activations
+    (so that ReLU masks agree bit for bit): G per tensor-core layer, in layer order."""
+    sd = {k: v.detach().float() for k, v in model.state_dict().items()}
+    lay, tape, M = r["lay"], r["tape"], r["n"] * r["S"]
+    nt, nl, H = lay["n_tiles"], lay["nl"], model.hidden_size
+    n_trunk = len(model.layers_xyz)
+    act = [training.decode_image(tape, lay["act"][l], nt, H if l < nl - 1 else H // 2)[:M] for l in range(nl)]
+    G = [None] * nl
+    drgb, dsig = d_rf[:, :3], bf(d_rf[:, 3:4])
+    G[nl - 1] = bf((drgb @ sd["fc_rgb.weight"]) * (act[nl - 1] > 0))
+    G[nl - 2] = bf((G[nl - 1] @ bf(sd["layers_dir.0.weight"])[:, :H]) * (act[nl - 2] > 0))
+    dh = G[nl - 2] @ bf(sd["fc_feat.weight"]) + dsig * sd["fc_alpha.weight"]
+    G[nl - 3] = bf(dh * (act[nl - 3] > 0))
+    for i in range(n_trunk - 1, -1, -1):          # trunk layer i is tensor-core layer i + 1
+        dh = G[i + 1] @ bf(sd[f"layers_xyz.{i}.weight"])[:, :H]
+        G[i] = bf(dh * (act[i] > 0)) if i > 0 else bf(dh)
+    return act, G
+
+
+@pytest.mark.parametrize("hidden,layers,skip,Lx", CONFIGS)
+def test_activation_gradient_chain(hidden, layers, skip, Lx):
+    model = make_model(hidden, layers, skip, Lx)
+    n, S = 9, 64
+    r = run_forward_with_tape(model, Lx, n, S, seed=1)
+    M = n * S
+    d_rf = torch.randn(M, 4, generator=torch.Generator().manual_seed(5)).cuda() * 0.1
+    training.mlp_backward(model, r["prog"], r["spec"], r["tape"], d_rf.view(n, S, 4).contiguous(), n, S, what=1)
+    torch.cuda.synchronize()
+    act, G = emulate_backward(model, r, d_rf)
+    lay, nt = r["lay"], r["lay"]["n_tiles"]
+    for l in range(lay["nl"] - 1, -1, -1):
+        got = training.decode_image(r["tape"], lay["grad"][l], nt, G[l].shape[1])
+        assert float(got[M:].abs().max()) == 0.0 if got.shape[0] > M else True      # padded rows carry no gradient
+        e = rel_err(got[:M], G[l])
+        print("G layer", l, "rel_err %.5f" % e)
+        assert e < 1e-2, (l, e)                 # bf16 re-rounding of fp32 sums accumulated in another order
+    got = training.decode_image(r["tape"], lay["ghead"], nt, 16)[:M]
+    assert torch.equal(got[:, :4], bf(d_rf)) and float(got[:, 4:].abs().max()) == 0.0
+
+
+def reference_weight_grads(model, prog, act, G, enc_xyz_img, enc_dir_img, ghead):
+    """dWt = X^T G in fp32 from the bf16 images, assembled in the program layout."""
+    flat = torch.zeros_like(model.packed_params())
+    layers = model._layers()
+    H, nl = model.hidden_size, len(act)
+    n_trunk = len(model.layers_xyz)
+    # tensor-core layer l -> program op: layer1 0, trunk 1..n_trunk, fc_alpha n_trunk+1, fc_feat +2, dir +3, rgb +4
+    tc_ops = list(range(0, n_trunk + 1)) + [n_trunk + 2, n_trunk + 3]
+    for l, opi in enumerate(tc_ops):
+        lin = layers[opi][0]
+        op = prog.ops[opi]
+        if l == 0:
+            X = enc_xyz_img[:, :lin.in_features]
+        else:
+            X = act[l - 1]
+            if lin.in_features > X.shape[1]:
+                extra = enc_dir_img if l == nl - 1 else enc_xyz_img
+                X = torch.cat((X, extra[:, :lin.in_features - X.shape[1]]), -1)
+        flat[op.w_off:op.w_off + lin.in_features * lin.out_features] = (X.t() @ G[l]).reshape(-1)
+        flat[op.b_off:op.b_off + lin.out_features] = G[l].sum(0)
+    oa, orgb = prog.ops[n_trunk + 1], prog.ops[n_trunk + 4]
+    flat[oa.w_off:oa.w_off + H] = (act[nl - 3].t() @ ghead[:, 3:4]).reshape(-1)
+    flat[oa.b_off] = ghead[:, 3].sum()
+    flat[orgb.w_off:orgb.w_off + 3 * (H // 2)] = (act[nl - 1].t() @ ghead[:, :3]).reshape(-1)
+    flat[orgb.b_off:orgb.b_off + 3] = ghead[:, :3].sum(0)
+    return flat
+
+
+@pytest.mark.parametrize("hidden,layers,skip,Lx", CONFIGS)
+def test_weight_gradient_gemm(hidden, layers, skip, Lx):
+    """The split-K weight-gradient GEMM in isolation: random bf16 images written into a tape,
+    dWt = X^T G compared with torch matmul on the same values (fp32 accumulate both sides)."""
+    model = make_model(hidden, layers, skip, Lx)
+    ex, ed = nerf.get_embedding_function(Lx, True, True), nerf.get_embedding_function(4, True, True)
+    prog = model.program(ex, ed)
+    spec = tensorcore.spec_for(model, prog)
+    n, S = 20, 64                           # 1280 samples = 10 tiles
+    lay = training.tape_layout(spec, n * S)
+    nt, nl, H = lay["n_tiles"], lay["nl"], hidden
+    tape = torch.zeros(lay["total"], dtype=torch.uint8, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(11)
+    rnd = lambda w: bf(torch.randn(nt * 128, w, generator=g, device="cuda"))
+    act = [rnd(H if l < nl - 1 else H // 2) for l in range(nl)]
+    G = [bf(rnd(H if l < nl - 1 else H // 2) * 0.1) for l in range(nl)]
+    xyz, dr, ghead = rnd(64), rnd(32), rnd(16)
+    ghead[:, 4:] = 0
+    for l in range(nl):
+        training.encode_image(tape, lay["act"][l], nt, act[l])
+        training.encode_image(tape, lay["grad"][l], nt, G[l])
+    training.encode_image(tape, lay["xyz"], nt, xyz)
+    training.encode_image(tape, lay["dir"], nt, dr)
+    training.encode_image(tape, lay["ghead"], nt, ghead)
+    assert torch.equal(training.decode_image(tape, lay["act"][1], nt, H), act[1])
+    want = reference_weight_grads(model, prog, act, G, xyz, dr, ghead)
+    d_rf = torch.zeros(n, S, 4, device="cuda")
+    errs = {}
+    for variant in (0, 1):
+        got = training.mlp_backward(model, prog, spec, tape, d_rf, n, S, what=2, variant=variant)
+        torch.cuda.synchronize()
+        errs[variant] = rel_err(got, want)
+    print("dW rel_err by descriptor variant", errs)
+    got = training.mlp_backward(model, prog, spec, tape, d_rf, n, S, what=2)
+    bad = []
+    for i, (lin, *_r) in enumerate(model._layers()):
+        op = prog.ops[i]
+        for kind, sl in (("weight", slice(op.w_off, op.w_off + lin.in_features * lin.out_features)),
+                         ("bias", slice(op.b_off, op.b_off + lin.out_features))):
+            e = rel_err(got[sl], want[sl])
+            print("op", i, kind, "rel_err %.2e" % e, "max abs diff %.3e" % float((got[sl] - want[sl]).abs().max()))
+            if e >= 1e-4:
+                bad.append((i, kind, e))
+    assert not bad, bad                  # same bf16 inputs, fp32 accumulation: only summation order differs
+    assert errs[0] < 1e-4, errs
+
+
+# ------------------------------------------------------------------ whole training iteration
+def make_cfg(nc, nf, near, far, white, noise_std=0.2, perturb=True):
+    mode = dict(chunksize=1 << 20, perturb=perturb, num_coarse=nc, num_fine=nf, white_background=white,
+                radiance_field_noise_std=noise_std, lindisp=False)
+    return nerf.CfgNode(dict(dataset=dict(no_ndc=True, near=near, far=far),
+                             nerf=dict(use_viewdirs=True, train=dict(mode), validation=dict(mode))))
+
+
+def test_training_iteration_matches_reference(golden):
+    """The reference's own training iteration (fixture made by tests/golden/make_golden.py
+    gen_train_grads from the unmodified reference): 8-layer x 128 FlexibleNeRFModel pair, RNG
+    replayed.  Bars (bf16 tensor-core operands vs the reference's fp32): loss within 2e-3;
+    every parameter gradient within 6 % of its norm, cosine > 0.998; Adam step direction agrees."""
+    g = golden("train_grads")
+    tag = "h128"
+    hidden, layers, skip, white = map(int, g[f"{tag}.cfg"])
+    nets = []
+    for net in ("coarse", "fine"):
+        m = nerf.FlexibleNeRFModel(layers, hidden, skip, 6, 4)
+        m.load_state_dict({k[len(tag) + len(net) + 2:]: t(v) for k, v in g.items() if k.startswith(f"{tag}.{net}.")})
+        nets.append(m.cuda())
+    mc, mf = nets
+    ex, ed = nerf.get_embedding_function(6, True, True), nerf.get_embedding_function(4, True, True)
+    rng = dict(t_rand=t(g[f"{tag}.t_rand"]).cuda(), u=t(g[f"{tag}.u"]).cuda(),
+               noise_coarse=t(g[f"{tag}.noise_c"]).cuda(), noise_fine=t(g[f"{tag}.noise_f"]).cuda())
+    H, W = map(int, g["HW"])
+    out = nerf.run_one_iter_of_nerf(H, W, 9.0, mc, mf, t(g["ro"]).cuda(), t(g["rd"]).cuda(),
+                                    make_cfg(16, 24, 2.0, 6.0, bool(white)), mode="train", encode_position_fn=ex,
+                                    encode_direction_fn=ed, m_thres_cand=g["thr"].tolist(), rng=rng)
+    assert out[0].requires_grad and out[3].requires_grad and len(out) == 6 + len(g["thr"])
+    target = t(g["target"]).cuda()
+    loss = torch.nn.functional.mse_loss(out[0][..., :3], target) + torch.nn.functional.mse_loss(out[3][..., :3], target)
+    loss.backward()
+    assert abs(float(loss) - float(g[f"{tag}.loss"])) < 2e-3
+    worst = []
+    for net, m in (("coarse", mc), ("fine", mf)):
+        num = den = dot = 0.0
+        for k, p in m.named_parameters():
+            ref = t(g[f"{tag}.grad.{net}.{k}"]).cuda()
+            assert p.grad is not None and p.grad.shape == ref.shape, k
+            assert torch.isfinite(p.grad).all(), k
+            print("grad", net, k, "rel_err %.4f" % rel_err(p.grad, ref), "ref norm %.3e" % float(ref.norm()))
+            if float(ref.norm()) > 1e-7:
+                worst.append((rel_err(p.grad, ref), net, k))
+            num += float(((p.grad - ref) ** 2).sum()); den += float((ref ** 2).sum()); dot += float((p.grad * ref).sum())
+        got_norm = sum(float((p.grad ** 2).sum()) for p in m.parameters()) ** 0.5
+        print("net", net, "total rel_err %.4f" % ((num / den) ** 0.5), "cosine %.5f" % (dot / (den ** 0.5 * got_norm)))
+        assert (num / den) ** 0.5 < 3e-2, net
+        assert dot / (den ** 0.5 * got_norm) > 0.998, net
+    assert max(worst)[0] < 0.15, max(worst)
+
+
+def test_training_iteration_8x256_vs_oracle():
+    """BASELINE config 4's networks (8x256 skip 4, L=10/4, 64 + 128 samples) on a small ray batch
+    against the CPU oracle's autograd with the same bf16 operand contract."""
+    torch.manual_seed(42)
+    mc, mf = nerf.FlexibleNeRFModel(8, 256, 4, 10, 4), nerf.FlexibleNeRFModel(8, 256, 4, 10, 4)
+    with torch.no_grad():
+        for m in (mc, mf):
+            m.fc_alpha.weight.mul_(40.0)
+            m.fc_alpha.bias.fill_(0.5)
+    sdc = {k: v.detach().clone() for k, v in mc.state_dict().items()}
+    sdf = {k: v.detach().clone() for k, v in mf.state_dict().items()}
+    mc, mf = mc.cuda(), mf.cuda()
+    n, nc, nf = 48, 64, 128
+    g = torch.Generator().manual_seed(9)
+    T = O.pose_spherical_world2cam(30.0, -30.0, 4.0)
+    K = torch.tensor([[60.0, 0, 4.0], [0, 60.0, 3.0], [0, 0, 1]])
+    ro, rd = O.get_ray_bundle(6, 8, None, T, K)
+    ro, rd = ro.reshape(-1, 3), rd.reshape(-1, 3)
+    target = torch.rand(n, 3, generator=g)
+    rng = dict(t_rand=torch.rand(n, nc, generator=g), u=torch.rand(n, nf, generator=g),
+               noise_coarse=0.2 * torch.randn(n, nc, generator=g), noise_fine=0.2 * torch.randn(n, nc + nf, generator=g))
+    opts = O.RenderOptions(near=2.0, far=6.0, num_coarse=nc, num_fine=nf, Lx=10, Ld=4, perturb=True, noise_std=0.2)
+    loss_o, _, _, gc, gf = O.train_loss_and_grads(sdc, sdf, ro, rd, target, opts, [], 4, 4, t_rand=rng["t_rand"],
+                                                  u=rng["u"], noise_coarse=rng["noise_coarse"],
+                                                  noise_fine=rng["noise_fine"], bf16=True)
+    ex, ed = nerf.get_embedding_function(10, True, True), nerf.get_embedding_function(4, True, True)
+    opt = torch.optim.Adam(list(mc.parameters()) + list(mf.parameters()), lr=5e-3)
+    before = {k: v.detach().clone() for k, v in mc.state_dict().items()}
+    loss, _, _ = nerf.train_step(mc, mf, opt, ro.cuda(), rd.cuda(), target.cuda(), make_cfg(nc, nf, 2.0, 6.0, False),
+                                 ex, ed, m_thres_cand=[], rng={k: v.cuda() for k, v in rng.items()}, height=6, width=8,
+                                 focal=60.0)
+    assert abs(float(loss) - float(loss_o)) < 2e-3
+    # the optimizer stepped: parameters moved by about lr in the direction of -sign(grad)
+    moved = sum(float((mc.state_dict()[k] - before[k]).abs().sum()) for k in before)
+    assert moved > 0
+    # gradients (recomputed, optimizer.zero_grad() cleared them): compare with the oracle
+    for m, sd in ((mc, sdc), (mf, sdf)):
+        m.load_state_dict(sd)
+    out = nerf.run_one_iter_of_nerf(6, 8, 60.0, mc, mf, ro.cuda(), rd.cuda(), make_cfg(nc, nf, 2.0, 6.0, False),
+                                    mode="train", encode_position_fn=ex, encode_direction_fn=ed, m_thres_cand=[],
+                                    rng={k: v.cuda() for k, v in rng.items()})
+    tg = target.cuda()
+    (torch.nn.functional.mse_loss(out[0], tg) + torch.nn.functional.mse_loss(out[3], tg)).backward()
+    for m, grads in ((mc, gc), (mf, gf)):
+        num = den = 0.0
+        for k, p in m.named_parameters():
+            ref = grads[k].cuda()
+            num += float(((p.grad - ref) ** 2).sum()); den += float((ref ** 2).sum())
+        assert (num / den) ** 0.5 < 3e-2

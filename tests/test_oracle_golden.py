@@ -1,6 +1,7 @@
 """The CPU oracle (oracle/nerf_oracle.py) against outputs of the reference itself
 (tests/golden/*.npz, produced by tests/golden/make_golden.py).  CPU only."""
 import numpy as np
+import pytest
 import torch
 
 from oracle import nerf_oracle as O
@@ -207,3 +208,30 @@ def test_tiny(golden):
     rgb = O.run_one_iter_of_tinynerf(int(H), int(W), t(g["T"]), t(g["K"]), 2.0, 6.0, 64, 6,
                                      lambda x: O.very_tiny_forward(sd, x))
     close(rgb, g["rgb"], 1e-4, 1e-5)
+
+
+# ------------------------------------------------------------------ a-10 training iteration
+@pytest.mark.parametrize("tag", ["h32", "h128"])
+def test_train_gradients_match_reference(golden, tag):
+    """Loss, every parameter gradient and one Adam step of the reference's training iteration
+    (train_dexnerf_rgb.py:246-281) with its four RNG draws replayed."""
+    g = golden("train_grads")
+    hidden, layers, skip, white = map(int, g[f"{tag}.cfg"])
+    sdc = {k[len(tag) + 8:]: t(v) for k, v in g.items() if k.startswith(f"{tag}.coarse.")}
+    sdf = {k[len(tag) + 6:]: t(v) for k, v in g.items() if k.startswith(f"{tag}.fine.")}
+    opts = O.RenderOptions(near=2.0, far=6.0, num_coarse=16, num_fine=24, Lx=6, Ld=4, perturb=True,
+                           noise_std=0.2, white_background=bool(white))
+    loss, cl, fl, gc, gf = O.train_loss_and_grads(
+        sdc, sdf, t(g["ro"]), t(g["rd"]), t(g["target"]), opts, g["thr"].tolist(), skip, skip,
+        t_rand=t(g[f"{tag}.t_rand"]), u=t(g[f"{tag}.u"]), noise_coarse=t(g[f"{tag}.noise_c"]),
+        noise_fine=t(g[f"{tag}.noise_f"]))
+    assert abs(float(loss) - float(g[f"{tag}.loss"])) < 2e-6
+    assert abs(float(cl) - float(g[f"{tag}.coarse_loss"])) < 2e-6
+    for net, grads, sd in (("coarse", gc, sdc), ("fine", gf, sdf)):
+        for k, v in grads.items():
+            ref = t(g[f"{tag}.grad.{net}.{k}"])
+            scale = float(ref.abs().max()) + 1e-12
+            assert float((v - ref).abs().max()) <= 2e-4 * scale + 1e-9, (net, k)
+        new = O.adam_step(sd, {k: t(g[f"{tag}.grad.{net}.{k}"]) for k in sd}, lr=5e-3)
+        for k, v in new.items():
+            assert torch.allclose(v, t(g[f"{tag}.adam.{net}.{k}"]), rtol=0, atol=2e-6), (net, k)
