@@ -160,6 +160,132 @@ def run_reference(args):
         "gpu_launches": 0}))
 
 
+TRAIN_RAYS = 4096
+TRAIN_FLOP_PER_RAY = 3 * FLOP_PER_RAY          # forward + dX + dW: 911.5 MFLOP/ray
+
+
+def run_train(args, dist, rank, world, dev, quiet=False):
+    """BASELINE config 4: one training iteration per step on 4096 rays per GPU drawn from the C2
+    bundle (np.random.seed(42)), train mode (perturb, noise 0.2, random u), loss = mse(coarse) +
+    mse(fine), backward through the tensor-core kernels, one flat NCCL all-reduce of both MLPs'
+    gradients (N > 1), Adam(lr 5e-3) with the reference's exponential decay.  Weak scaling."""
+    import numpy as np
+    import nerf
+    from nerf import _lib as L
+    from nerf import training as TR
+    mc, mf = state_dicts()
+    mc, mf = mc.to(dev), mf.to(dev)
+    mode = dict(chunksize=1 << 30, perturb=True, num_coarse=NC, num_fine=NF, white_background=False,
+                radiance_field_noise_std=0.2, lindisp=False)
+    cfg = nerf.CfgNode(dict(dataset=dict(no_ndc=True, near=NEAR, far=FAR),
+                            nerf=dict(use_viewdirs=True, train=dict(mode), validation=dict(mode))))
+    ex, ed = nerf.get_embedding_function(10, True, True), nerf.get_embedding_function(4, True, True)
+    T_cpu, K_cpu = camera()
+    ro, rd = nerf.get_ray_bundle(H, W, None, T_cpu.to(dev), K_cpu.to(dev))
+    ro, rd = ro.reshape(-1, 3), rd.reshape(-1, 3)
+    np.random.seed(42 + rank)
+    g = torch.Generator().manual_seed(1234 + rank)
+    n_batches = 4
+    sel = [torch.from_numpy(np.random.choice(H * W, size=TRAIN_RAYS, replace=False)) for _ in range(n_batches)]
+    tgt_host = [torch.rand(TRAIN_RAYS, 3, generator=g).pin_memory() for _ in range(n_batches)]
+    sel_host = [s.pin_memory() for s in sel]
+    sel_dev = [s.to(dev) for s in sel]
+    tgt_dev = [x.to(dev) for x in tgt_host]
+    opt = torch.optim.Adam(list(mc.parameters()) + list(mf.parameters()), lr=5e-3)
+    it = [0]
+
+    def step(sel_i, tgt_i):
+        for pg in opt.param_groups:
+            pg["lr"] = nerf.learning_rate(5e-3, it[0], 250, 0.1)
+        it[0] += 1
+        return nerf.train_step(mc, mf, opt, ro[sel_i], rd[sel_i], tgt_i, cfg, ex, ed, m_thres_cand=[],
+                               height=H, width=W, focal=FX, world_size=world)[0]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(ms):
+        if dist is None:
+            return ms
+        tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    for i in range(max(args.warmup, 3)):
+        step(sel_dev[i % n_batches], tgt_dev[i % n_batches])
+    sampler = ClockSampler(dev.index or 0)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    TR.event_log = []
+    launches0 = L.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(sel_dev[i % n_batches], tgt_dev[i % n_batches])
+    e1.record()
+    barrier()
+    launches = L.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_dev = reduce_max(e0.elapsed_time(e1) / args.steps)
+    log, TR.event_log = TR.event_log, None
+    parts = {}
+    for name, a, b, n, S in log:
+        parts.setdefault("%s_S%d" % (name, S), []).append(a.elapsed_time(b))
+    parts = {k: sum(v) / len(v) for k, v in parts.items()}
+    # end to end: ray indices + targets come from pinned host memory, the loss goes back to the host
+    loss_pin = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def e2e_step(i):
+        loss = step(sel_host[i % n_batches].to(dev, non_blocking=True), tgt_host[i % n_batches].to(dev, non_blocking=True))
+        loss_pin.copy_(loss, non_blocking=True)
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    ms_e2e = reduce_max(e0.elapsed_time(e1) / args.steps)
+    if rank != 0:
+        return None
+    pk = peaks()
+    rays = TRAIN_RAYS * world
+    dw_ms = parts.get("mlp_tc_bwd_dw_S%d" % (NC + NF))
+    dx_ms = parts.get("mlp_tc_bwd_dx_S%d" % (NC + NF))
+    fw_ms = parts.get("mlp_tc_train_fwd_S%d" % (NC + NF))
+    flop_fine = TRAIN_RAYS * (NC + NF) * FLOP_PER_EVAL
+    mlp_ms = sum(v for k, v in parts.items() if k.startswith("mlp_tc"))
+    line = {
+        "metric": "training rays/sec (4096-ray batches per GPU, 64+128 samples, 8x256 MLP, fwd+bwd+allreduce+Adam)",
+        "value": rays / (ms_dev * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "C4: NeRF training iteration, 4096 rays per GPU drawn from the C2 800x800 bundle, train "
+                               "mode (perturb, sigma noise 0.2), two 8x256 skip-4 FlexibleNeRFModels, mse(coarse)+mse(fine), "
+                               "Adam lr 5e-3 with exponential decay; gradients all-reduced with NCCL when N > 1",
+                   "rays_per_step": rays, "parallelism": "dp%d" % world,
+                   "l2": "the per-step tape (10 KB/sample, 10.7 GB per step) exceeds the 126 MB L2"},
+        "e2e": {"value": rays / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": TRAIN_RAYS * (8 + 12), "d2h_bytes_per_step": 4},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "kernel": "mlp_tc train fwd + bwd_dx + bwd_dw (fine pass, 192 samples/ray)",
+                     "achieved": 3 * flop_fine / ((fw_ms + dx_ms + dw_ms) * 1e-3) / 1e12 if (fw_ms and dx_ms and dw_ms) else None,
+                     "peak": pk["tf_sustained"], "unit": "TFLOP/s", "peak_source": pk["source"] + " bf16 sustained",
+                     "traffic": None, "kernel_ms": {k: round(v, 4) for k, v in sorted(parts.items())},
+                     "mlp_share_of_step": mlp_ms / ms_dev, "flop_per_launch": flop_fine},
+        "clocks": clocks,
+    }
+    if line["roofline"]["achieved"]:
+        line["roofline"]["frac"] = line["roofline"]["achieved"] / pk["tf_sustained"]
+    if not quiet:
+        print(json.dumps(line))
+    return line
+
+
 def workload_config(n_gpus):
     return {"workload": "C2: full-paper NeRF render 800x800, 64 coarse + 128 fine samples, two 8x256 skip-4 "
                         "FlexibleNeRFModels (L=10/4, viewdirs), T=20 Dex thresholds, validation mode, random-init",
@@ -176,6 +302,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=None, choices=[None, "bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="render", choices=["render", "train"],
+                    help="render: BASELINE config 2 (the headline metric); train: BASELINE config 4")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -196,6 +324,12 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_gpus = world
     dev = torch.device("cuda", local)
+    if args.workload == "train":
+        run_train(args, dist, rank, world, dev)
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     from nerf.sharding import row_block
     row0, rows = row_block(H, rank, n_gpus)

@@ -386,6 +386,9 @@ struct WSmem {
 __device__ __forceinline__ void red_add_f32(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
+__device__ __forceinline__ void red_add_f32x4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 __global__ void __launch_bounds__(kWThreads, 1) mlp_tc_bwd_dw_kernel(const __grid_constant__ DwParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -480,31 +483,48 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_tc_bwd_dw_kernel(const __gri
     __syncwarp();
   } else if (warp >= 4) {
     // =============================== bias column sums + final reduction ===============================
-    const int j = threadIdx.x - 128;            // 0..127: features 2j, 2j+1 of G
+    // thread j owns feature group j / 4 of G (8 features) and every 4th sample of the half-tile:
+    // one 16-byte shared-memory load per sample row, rows rotated by the feature group so that the
+    // four wavefronts of a warp load are conflict free; the four sample phases meet in a shuffle at
+    // the very end
+    const int j = threadIdx.x - 128;            // 0..127
     const bool has_bias = I.b_out >= 0;
-    const bool mine = has_bias && j < I.g_fg * 4;
-    const int fg = j >> 2, w = j & 3;
-    float s0 = 0.f, s1 = 0.f;
+    const int fg = j >> 2, sub = j & 3;
+    const bool mine = has_bias && fg < I.g_fg;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
     for (int64_t s = 0; s < n_stage_total; ++s) {
       const int st = (int)(s % kWStages);
       const uint32_t ph = (uint32_t)((s / kWStages) & 1);
       mbar_wait(full(st), ph, 22);
       if (mine) {
-        const uint8_t* gs = smem + WSmem::g + st * kWStageG + fg * 1024 + w * 4;
-#pragma unroll 8
-        for (int r = 0; r < 64; ++r) {
-          const uint32_t v = *reinterpret_cast<const uint32_t*>(gs + ((r + fg) & 63) * 16);   // staggered: no bank conflicts
-          s0 += __uint_as_float(v << 16);
-          s1 += __uint_as_float(v & 0xFFFF0000u);
+        const uint32_t gs = sbase + WSmem::g + st * kWStageG + fg * 1024;
+#pragma unroll 4
+        for (int r = 0; r < 16; ++r) {
+          const uint32_t row = (uint32_t)(4 * r + sub + fg) & 63u;
+          uint32_t v0, v1, v2, v3;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(gs + row * 16));
+          acc[0] += __uint_as_float(v0 << 16); acc[1] += __uint_as_float(v0 & 0xFFFF0000u);
+          acc[2] += __uint_as_float(v1 << 16); acc[3] += __uint_as_float(v1 & 0xFFFF0000u);
+          acc[4] += __uint_as_float(v2 << 16); acc[5] += __uint_as_float(v2 & 0xFFFF0000u);
+          acc[6] += __uint_as_float(v3 << 16); acc[7] += __uint_as_float(v3 & 0xFFFF0000u);
         }
       }
       mbar_arrive(empty(st));
     }
-    if (mine) {
-      const int c0 = 2 * j - I.col0;
-      if (c0 >= 0 && c0 < I.n_cols) red_add_f32(P.grads + I.b_out + c0, s0);
-      if (c0 + 1 >= 0 && c0 + 1 < I.n_cols) red_add_f32(P.grads + I.b_out + c0 + 1, s1);
+    if (has_bias) {                              // warp-uniform: all lanes take part in the shuffles
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 1);
+        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 2);
+      }
+      if (mine && sub == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int cc = fg * 8 + i - I.col0;
+          if (cc >= 0 && cc < I.n_cols) red_add_f32(P.grads + I.b_out + cc, acc[i]);
+        }
+      }
     }
     // ---- accumulators -> global (one thread per in-feature row, TMEM lane = row within the M block)
     if (n_stage_total > 0) {
@@ -520,10 +540,16 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_tc_bwd_dw_kernel(const __gri
           float v[16];
           tmem_ld16(tmem_base + lane_base + (uint32_t)(mb * 256 + c), v);      // warp-collective
           if (r < I.a_rows) {
+            const int cc0 = c - I.col0;
+            if (cc0 >= 0 && cc0 + 16 <= I.n_cols && ((reinterpret_cast<uintptr_t>(dst + cc0) & 15) == 0)) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int cc = c + i - I.col0;
-              if (cc >= 0 && cc < I.n_cols) red_add_f32(dst + cc, v[i]);
+              for (int i = 0; i < 16; i += 4) red_add_f32x4(dst + cc0 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int cc = cc0 + i;
+                if (cc >= 0 && cc < I.n_cols) red_add_f32(dst + cc, v[i]);
+              }
             }
           }
         }
@@ -685,15 +711,23 @@ extern "C" DEXNERF_API int dexnerf_tc_backward(const dexnerf_flexible_spec* spec
       add(T.act[nl - 1], hfg / 2, 0, hfg / 2, H / 2, T.ghead, 2, orgb.w_off, orgb.b_off, 0, 3, 3);
     }
     DN_REQUIRE(W.n_items <= kMaxDwItems, "tc_backward: too many weight-gradient items");
-    // CTAs per item in proportion to its bytes per tile, at least one, about 2 waves in total
-    double total = 0;
-    for (int i = 0; i < W.n_items; ++i) total += cost[i];
-    int64_t budget = 2 * kNumSMs;
-    if (budget > W.n_tiles * W.n_items) budget = W.n_tiles * W.n_items;
+    // ONE wave of CTAs (one per SM).  Every CTA of item i streams cost[i] * n_tiles / share[i] bytes;
+    // the kernel ends with the slowest CTA, so shares are chosen greedily to minimise that maximum:
+    // start with one CTA per item and keep giving a CTA to the currently most loaded item.
+    int64_t budget = kNumSMs;
+    if (budget < W.n_items) budget = W.n_items;
+    int share[kMaxDwItems];
+    for (int i = 0; i < W.n_items; ++i) share[i] = 1;
+    for (int64_t used = W.n_items; used < budget; ++used) {
+      int best = -1;
+      for (int i = 0; i < W.n_items; ++i)
+        if (share[i] < W.n_tiles && (best < 0 || cost[i] / share[i] > cost[best] / share[best])) best = i;
+      if (best < 0) break;
+      ++share[best];
+    }
     int cta = 0;
     for (int i = 0; i < W.n_items; ++i) {
-      int64_t k = (int64_t)(cost[i] / total * (double)budget + 0.5);
-      if (k < 1) k = 1;
+      int64_t k = share[i];
       if (k > W.n_tiles) k = W.n_tiles;
       W.items[i].cta0 = cta; W.items[i].n_cta = (int)k;
       cta += (int)k;

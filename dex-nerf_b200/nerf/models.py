@@ -17,6 +17,11 @@ from . import _lib as L
 _Linear = torch.nn.Linear
 
 
+def _align4(n):
+    """Blocks of the flat parameter buffer start on multiples of 4 floats (vector loads / reductions)."""
+    return (n + 3) & ~3
+
+
 class _ProgramModule(torch.nn.Module):
     """Shared lowering/packing logic.  Subclasses implement `_layers()` -> list of
     (linear_module, src0, src1, dst, relu) with buffer ids from _lib."""
@@ -47,10 +52,10 @@ class _ProgramModule(torch.nn.Module):
                 raise RuntimeError("layer %d: input width %d != in_features %d"
                                    % (i, op.src0_dim + op.src1_dim, lin.in_features))
             op.dst, op.out_dim, op.relu = dst, lin.out_features, int(relu)
-            op.w_off = off
-            off += lin.in_features * lin.out_features
+            op.w_off = off                                   # every block starts 16-byte aligned
+            off = _align4(off + lin.in_features * lin.out_features)
             op.b_off = off
-            off += lin.out_features
+            off = _align4(off + lin.out_features)
             if dst in (L.BUF_A, L.BUF_B):
                 dims[dst] = lin.out_features
                 width = max(width, lin.out_features)
@@ -75,8 +80,12 @@ class _ProgramModule(torch.nn.Module):
                 for lin, *_ in layers:
                     if not lin.weight.is_cuda:
                         raise ValueError("model parameters must live on a CUDA device (call .to('cuda'))")
-                    parts.append(lin.weight.detach().to(torch.float32).t().contiguous().reshape(-1))
-                    parts.append(lin.bias.detach().to(torch.float32).reshape(-1))
+                    for blk in (lin.weight.detach().to(torch.float32).t().contiguous().reshape(-1),
+                                lin.bias.detach().to(torch.float32).reshape(-1)):
+                        parts.append(blk)
+                        pad = _align4(blk.numel()) - blk.numel()
+                        if pad:
+                            parts.append(blk.new_zeros(pad))
                 flat = torch.cat(parts).contiguous()
             cache = (key, flat)
             self.__dict__["_packed_cache"] = cache

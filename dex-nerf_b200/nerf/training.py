@@ -16,6 +16,26 @@ from . import tensorcore
 from .volume_rendering_utils import render_maps
 
 
+event_log = None     # bench.py sets this to a list to collect (name, start_event, end_event, n, S)
+
+
+class _timed:
+    """CUDA-event bracket around one C-ABI call when bench.py asked for a kernel breakdown."""
+
+    def __init__(self, name, n, S):
+        self.name, self.n, self.S = name, n, S
+
+    def __enter__(self):
+        if event_log is not None:
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if event_log is not None:
+            self.e1.record()
+            event_log.append((self.name, self.e0, self.e1, self.n, self.S))
+
+
 def _layer_params(model):
     return [p for lin, *_ in model._layers() for p in (lin.weight, lin.bias)]
 
@@ -70,8 +90,9 @@ def query_train(model, prog, spec, ro, rd, viewdirs, z):
         raise L.DexNerfError("tc_tape_bytes: " + L.lib().dexnerf_last_error().decode())
     tape = torch.empty(nbytes, dtype=torch.uint8, device=z.device)
     rf = torch.empty((n, S, 4), dtype=torch.float32, device=z.device)
-    L.check(L.lib().dexnerf_tc_query_train(spec, L.ptr(blob), L.ptr(ro), L.ptr(rd), L.ptr(viewdirs), L.ptr(z), n, S,
-                                           L.ptr(rf), L.ptr(tape), L.stream_ptr()), "tc_query_train")
+    with _timed("mlp_tc_train_fwd", n, S):
+        L.check(L.lib().dexnerf_tc_query_train(spec, L.ptr(blob), L.ptr(ro), L.ptr(rd), L.ptr(viewdirs), L.ptr(z), n,
+                                               S, L.ptr(rf), L.ptr(tape), L.stream_ptr()), "tc_query_train")
     return rf, tape
 
 
@@ -80,10 +101,12 @@ def mlp_backward(model, prog, spec, tape, d_rf, n, S, what=3, variant=0):
     blob = tensorcore.packed_weights(model, prog, spec)
     blob_t = packed_weights_t(model, prog, spec)
     flat = torch.zeros_like(model.packed_params())
-    L.check(L.lib().dexnerf_tc_backward(spec, prog, L.ptr(blob), L.ptr(blob_t), L.ptr(tape), L.ptr(d_rf), n, S,
-                                        L.ptr(flat), int(what), int(variant), L.stream_ptr()), "tc_backward")
-    if what == 3:
-        L.launch_count += 1      # two kernels behind this one call
+    for bit, name in ((1, "mlp_tc_bwd_dx"), (2, "mlp_tc_bwd_dw")):     # one kernel per call
+        if what & bit:
+            with _timed(name, n, S):
+                L.check(L.lib().dexnerf_tc_backward(spec, prog, L.ptr(blob), L.ptr(blob_t), L.ptr(tape), L.ptr(d_rf),
+                                                    n, S, L.ptr(flat), bit, int(variant), L.stream_ptr()),
+                        "tc_backward")
     return flat
 
 
@@ -103,10 +126,11 @@ def volume_render_backward(rf, z, rd, noise, white_background, g_rgb, g_depth, g
     d_rf = torch.empty_like(rf)
     if n:
         g = [None if t is None else t.contiguous().to(torch.float32) for t in (g_rgb, g_depth, g_acc)]
-        L.check(L.lib().dexnerf_volume_render_backward(L.ptr(rf), L.ptr(z), L.ptr(rd), L.ptr(noise), n, S,
-                                                       int(bool(white_background)), L.ptr(g[0]), L.ptr(g[1]),
-                                                       L.ptr(g[2]), L.ptr(d_rf), L.stream_ptr()),
-                "volume_render_backward")
+        with _timed("composite_bwd", n, S):
+            L.check(L.lib().dexnerf_volume_render_backward(L.ptr(rf), L.ptr(z), L.ptr(rd), L.ptr(noise), n, S,
+                                                           int(bool(white_background)), L.ptr(g[0]), L.ptr(g[1]),
+                                                           L.ptr(g[2]), L.ptr(d_rf), L.stream_ptr()),
+                    "volume_render_backward")
     return d_rf
 
 

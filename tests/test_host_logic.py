@@ -114,8 +114,10 @@ def test_program_lowering_flexible_8x256():
     assert ops[11].dst == L.OUT_RGB
     macs = sum((o.src0_dim + o.src1_dim) * o.out_dim for o in ops)
     assert macs == 593408
-    total = ops[-1].b_off + ops[-1].out_dim
-    assert total == 595844
+    assert sum((o.src0_dim + o.src1_dim + 1) * o.out_dim for o in ops) == 595844   # parameters
+    # the flat buffer keeps every weight / bias block 16-byte aligned (vector loads and reductions)
+    assert all(o.w_off % 4 == 0 and o.b_off % 4 == 0 for o in ops)
+    assert ops[-1].b_off + ops[-1].out_dim == 595844 + 3                            # 3 floats of padding (fc_alpha)
     assert (p.Lx, p.Ld, p.include_xyz, p.log_xyz) == (10, 4, 1, 1)
 
 
