@@ -47,6 +47,26 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
 
 
+def ncu_traffic(key, rays):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu
+    capture (profiles/ncu_traffic.json), scaled to this launch's ray count; None when absent."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p)).get(key)
+    if not d:
+        return None
+    return (d["dram_bytes_read"] + d["dram_bytes_write"]) * rays / d["rays"]
+
+
+def train_traffic():
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p)).get("train_fine_c4")
+    return None if not d else d["mlp_tc_train_fwd"] + d["mlp_tc_bwd_dx"] + d["mlp_tc_bwd_dw"]
+
+
 def camera():
     from oracle.nerf_oracle import pose_spherical_world2cam
     T = pose_spherical_world2cam(30.0, -30.0, 4.0)
@@ -275,7 +295,7 @@ def run_train(args, dist, rank, world, dev, quiet=False):
         "roofline": {"bound": "tensor", "kernel": "mlp_tc train fwd + bwd_dx + bwd_dw (fine pass, 192 samples/ray)",
                      "achieved": 3 * flop_fine / ((fw_ms + dx_ms + dw_ms) * 1e-3) / 1e12 if (fw_ms and dx_ms and dw_ms) else None,
                      "peak": pk["tf_sustained"], "unit": "TFLOP/s", "peak_source": pk["source"] + " bf16 sustained",
-                     "traffic": None, "kernel_ms": {k: round(v, 4) for k, v in sorted(parts.items())},
+                     "traffic": train_traffic(), "kernel_ms": {k: round(v, 4) for k, v in sorted(parts.items())},
                      "mlp_share_of_step": mlp_ms / ms_dev, "flop_per_launch": flop_fine},
         "clocks": clocks,
     }
@@ -302,6 +322,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=None, choices=[None, "bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the short C4 training measurement of the default run")
     ap.add_argument("--workload", default="render", choices=["render", "train"],
                     help="render: BASELINE config 2 (the headline metric); train: BASELINE config 4")
     args = ap.parse_args()
@@ -408,6 +429,14 @@ def main():
     d2h = sum(o.numel() * o.element_size() for o in out_pin)
     h2d = (T_pin.numel() + K_pin.numel()) * 4
 
+    # BASELINE config 4 rides along (a few training iterations; reported under "train_c4")
+    train_line = None
+    if not args.no_train:
+        del flush
+        torch.cuda.empty_cache()
+        targs = argparse.Namespace(steps=5, warmup=3)
+        train_line = run_train(targs, dist, rank, world, dev, quiet=True)
+
     if rank == 0:
         pk = peaks()
         rays = H * W
@@ -426,11 +455,16 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": kern_name + " (fine pass, %d samples/ray)" % (NC + NF),
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "peak_source": pk["source"] + " bf16 sustained", "traffic": None,
+                         "peak_source": pk["source"] + " bf16 sustained",
+                         "traffic": ncu_traffic("mlp_tc_fine_c2", fine[0][1]),
                          "kernel_ms": kern_ms, "mlp_share_of_step": all_mlp_ms / ms_dev,
                          "flop_per_launch": flop_launch},
             "clocks": clocks,
         }
+        if train_line is not None:
+            line["train_c4"] = {k: train_line[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e")}
+            line["train_c4"]["kernel_ms"] = train_line["roofline"]["kernel_ms"]
+            line["train_c4"]["mlp_frac_of_peak"] = train_line["roofline"].get("frac")
         if not args.no_cpu_baseline:
             v, cores = cpu_oracle_rays_per_s()
             line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",

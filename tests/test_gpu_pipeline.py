@@ -184,3 +184,91 @@ def test_c2_shape_8x256_fp32_vs_oracle():
     rdex = torch.stack(ref[6:], 0)
     assert (dex == rdex).float().mean() > 0.95
     assert float(res[5].mean()) > 0.05       # the field does absorb
+
+
+def _boosted_pair(layers, hidden, skip, boost, bias, seed=7):
+    torch.manual_seed(seed)
+    mc = nerf.FlexibleNeRFModel(layers, hidden, skip, 10, 4)
+    mf = nerf.FlexibleNeRFModel(layers, hidden, skip, 10, 4)
+    with torch.no_grad():
+        for m in (mc, mf):
+            m.fc_alpha.weight.mul_(boost)
+            m.fc_alpha.bias.fill_(bias)
+    sds = [{k: v.detach().clone() for k, v in m.state_dict().items()} for m in (mc, mf)]
+    return mc.cuda(), mf.cuda(), sds[0], sds[1]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_c3_dex_depth_row_sharded(precision):
+    """BASELINE config 3: messytable-style camera (270x480, near 0.3 / far 4, 64+64 samples, T=20),
+    8x128 skip-3 nets (config/messytable-obj.yml:45-53) with a boosted sigma head so that the
+    thresholds 5..100 are crossed; the frame is rendered as 1, 2, 4 and 8 row blocks
+    (nerf.row_block) exactly as the ranks of a multi-GPU render would: the blocks must tile the
+    single-pass result bit for bit, and the Dex depths must match the oracle."""
+    nerf.set_precision(precision)
+    mc, mf, sdc, sdf = _boosted_pair(8, 128, 3, 1500.0, 3.0)
+    H, W = 24, 40                                  # a crop-sized frame with the C3 intrinsics scaled down
+    K = torch.tensor([[40.0, 0, 20.0], [0, 40.0, 12.0], [0, 0, 1]])
+    T = torch.eye(4)
+    T[2, 3] = 1.5
+    thr = [float(m) for m in range(5, 105, 5)]
+    cfg = make_cfg(64, 64, 0.3, 4.0)
+    ex, ed = nerf.get_embedding_function(10, True, True), nerf.get_embedding_function(4, True, True)
+    with torch.no_grad():
+        ro, rd = nerf.get_ray_bundle(H, W, None, T.cuda(), K.cuda())
+        full = nerf.run_one_iter_of_nerf(H, W, 40.0, mc, mf, ro, rd, cfg, mode="validation", encode_position_fn=ex,
+                                         encode_direction_fn=ed, m_thres_cand=thr)
+        for world in (2, 4, 8):
+            blocks = []
+            for rank in range(world):
+                r0, rows = nerf.row_block(H, rank, world)
+                ro_b, rd_b = nerf.get_ray_bundle(H, W, None, T.cuda(), K.cuda(), row_start=r0, row_count=rows)
+                assert torch.equal(ro_b, ro[r0:r0 + rows]) and torch.equal(rd_b, rd[r0:r0 + rows])
+                blocks.append(nerf.run_one_iter_of_nerf(H, W, 40.0, mc, mf, ro_b, rd_b, cfg, mode="validation",
+                                                        encode_position_fn=ex, encode_direction_fn=ed,
+                                                        m_thres_cand=thr))
+            for k in range(len(full)):
+                assert torch.equal(torch.cat([b[k] for b in blocks], 0), full[k]), (world, k)
+    dex = torch.stack(full[6:], 0).reshape(20, -1).cpu()
+    crossed = (dex > 0.3 + 1e-4).float().mean(1)
+    assert float(crossed[0]) > 0.2 and float(crossed[-1]) > 0.02       # low and high thresholds are really hit
+    opts = O.RenderOptions(near=0.3, far=4.0, num_coarse=64, num_fine=64, Lx=10, Ld=4)
+    bf16 = precision == "bf16"
+    ref = O.render_rays(ro.cpu(), rd.cpu(), lambda x: O.flexible_forward(sdc, x, 3, bf16=bf16),
+                        lambda x: O.flexible_forward(sdf, x, 3, bf16=bf16), opts, thr)
+    rdex = torch.stack(ref[6:], 0)
+    # fp32: operator-identical up to summation order; bf16: same operand contract, accumulation order differs
+    tol, same = (2e-3, 0.97) if precision == "fp32" else (4e-3, 0.90)
+    for a, b in zip(full[:6], ref[:6]):
+        assert float((a.reshape(b.shape).cpu() - b).abs().max()) < tol * max(1.0, float(b.abs().max()))
+    assert float((dex == rdex).float().mean()) > same
+    # first crossings are ordered in the threshold wherever the higher threshold is crossed at all
+    hit = dex[1:] > 0.3 + 1e-4
+    assert torch.all(dex[1:][hit] >= dex[:-1][hit])
+
+
+def test_c5_ir_variant_128_256():
+    """BASELINE config 5: 128 + 256 samples per ray (S_fine = 384), near 0.3 / far 4, T=20, the IR
+    scripts' luma output 0.299 R + 0.587 G + 0.114 B (train_nerf_ir.py:260-263) applied in Python;
+    a 1280x720 camera cropped to 12x16 rays, fp32 path against the oracle."""
+    mc, mf, sdc, sdf = _boosted_pair(8, 256, 4, 200.0, 2.0, seed=5)
+    K = torch.tensor([[900.0, 0, 640.0], [0, 900.0, 360.0], [0, 0, 1]])
+    T = torch.eye(4)
+    T[2, 3] = 1.2
+    thr = [float(m) for m in range(5, 105, 5)]
+    with torch.no_grad():
+        ro, rd = nerf.get_ray_bundle(720, 1280, None, T.cuda(), K.cuda(), row_start=354, row_count=12)
+        ro, rd = ro[:, 632:648].contiguous(), rd[:, 632:648].contiguous()
+        res = nerf.run_one_iter_of_nerf(720, 1280, 900.0, mc, mf, ro, rd, make_cfg(128, 256, 0.3, 4.0),
+                                        mode="validation", encode_position_fn=nerf.get_embedding_function(10, True, True),
+                                        encode_direction_fn=nerf.get_embedding_function(4, True, True), m_thres_cand=thr)
+    opts = O.RenderOptions(near=0.3, far=4.0, num_coarse=128, num_fine=256, Lx=10, Ld=4)
+    ref = O.render_rays(ro.cpu(), rd.cpu(), lambda x: O.flexible_forward(sdc, x), lambda x: O.flexible_forward(sdf, x),
+                        opts, thr)
+    for a, b in zip(res[:6], ref[:6]):
+        close(a.reshape(b.shape), b, 2e-3, 3e-4)
+    luma = lambda rgb: 0.299 * rgb[..., 0] + 0.587 * rgb[..., 1] + 0.114 * rgb[..., 2]
+    close(luma(res[3]).reshape(-1), luma(ref[3]), 2e-3, 3e-4)
+    dex = torch.stack(res[6:], 0).reshape(20, -1).cpu()
+    assert (dex == torch.stack(ref[6:], 0)).float().mean() > 0.95
+    assert len(res) == 26 and res[3].shape == (12, 16, 3)
