@@ -176,6 +176,14 @@ DEXNERF_API int dexnerf_tc_backward(const dexnerf_flexible_spec* spec, const dex
                         const void* packed, const void* packed_t, void* tape, const float* d_rf,
                         int64_t n, int S, float* grads, int what, int variant, void* stream);
 
+/* ---- validation depth metrics (nerf/train_utils.py:9-30 compute_err_metric, looped over the
+ * threshold candidates at train_dexnerf_rgb.py:391-404).  pred (T,n) threshold depth planes, gt (n),
+ * mask (n) uint8 or NULL (= the reference's (gt > 0) & (gt < 1.25)).  out (T,4) =
+ * [mean abs err in mm, fraction > 2 mm, > 4 mm, > 8 mm]; best (int32, may be NULL) = index of the
+ * first threshold with the smallest abs err (< 1000, else -1).  workspace: (4T + 1) doubles. */
+DEXNERF_API int dexnerf_depth_error_metrics(const float* pred, const float* gt, const uint8_t* mask, int64_t n,
+                                int T, float* out, int32_t* best, void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -419,6 +419,46 @@ def learning_rate(base_lr: float, iteration: int, lr_decay: float, lr_decay_fact
 
 
 # --------------------------------------------------------------------------------------
+# next rows: validation depth metrics, camera path
+# --------------------------------------------------------------------------------------
+def compute_err_metric(depth_gt: torch.Tensor, depth_pred: torch.Tensor, mask: torch.Tensor) -> Dict[str, float]:
+    """train_utils.py:9-30: mean |pred - gt| in mm and the fractions of masked pixels whose error
+    exceeds 2 / 4 / 8 mm."""
+    p, g = depth_pred[mask], depth_gt[mask]
+    abs_err = float((p * 1000 - g * 1000).abs().to(F64).mean())
+    diff = (g - p).abs()
+    n = diff.numel()
+    return {"depth_abs_err": abs_err, "depth_err2": float((diff > 2e-3).sum()) / n,
+            "depth_err4": float((diff > 4e-3).sum()) / n, "depth_err8": float((diff > 8e-3).sum()) / n}
+
+
+def select_dex_threshold(depth_planes: Sequence[torch.Tensor], depth_gt: torch.Tensor, mask=None):
+    """train_dexnerf_rgb.py:392-404: mask = (gt > 0) & (gt < 1.25) unless given; the first candidate
+    with the smallest abs err below 1000 wins.  Returns (index or -1, its error dict or None)."""
+    if mask is None:
+        mask = (depth_gt > 0) & (depth_gt < 1.25)
+    best, best_err, min_abs = -1, None, 1000.0
+    for k, plane in enumerate(depth_planes):
+        err = compute_err_metric(depth_gt, plane, mask)
+        if err["depth_abs_err"] < min_abs:
+            min_abs, best, best_err = err["depth_abs_err"], k, err
+    return best, best_err
+
+
+def pose_spherical(theta: float, phi: float, radius: float) -> torch.Tensor:
+    """load_blender.py:33-38 (cam->world, OpenGL convention), float32."""
+    t = torch.eye(4, dtype=F32); t[2, 3] = radius
+    p = phi / 180.0 * math.pi
+    rp = torch.eye(4, dtype=F32)
+    rp[1, 1] = rp[2, 2] = math.cos(p); rp[1, 2] = -math.sin(p); rp[2, 1] = math.sin(p)
+    th = theta / 180.0 * math.pi
+    rt = torch.eye(4, dtype=F32)
+    rt[0, 0] = rt[2, 2] = math.cos(th); rt[0, 2] = -math.sin(th); rt[2, 0] = math.sin(th)
+    flip = torch.tensor([[-1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=F32)
+    return flip @ (rt @ (rp @ t))
+
+
+# --------------------------------------------------------------------------------------
 # TinyNeRF (BASELINE config 1)                                      tiny_nerf.py:12-159
 # --------------------------------------------------------------------------------------
 def tiny_query_points(ro, rd, near: float, far: float, num_samples: int, rand=None):

@@ -399,6 +399,33 @@ def gen_tiny():
     print("tiny.npz")
 
 
+def gen_next_rows():
+    """compute_err_metric (train_utils.py:9-30) on synthetic depth planes
+    with the reference's mask rule, the threshold selection loop of train_dexnerf_rgb.py:392-404
+    restated around it, and pose_spherical (load_blender.py:33-38)."""
+    from nerf.load_blender import pose_spherical
+    out = {}
+    g = torch.Generator().manual_seed(808)
+    H, W, T = 27, 48, 20
+    gt = 0.3 + 1.2 * torch.rand(H, W, generator=g)
+    gt[torch.rand(H, W, generator=g) < 0.1] = 0.0                     # holes in the depth sensor
+    planes = gt[None] + 0.02 * torch.randn(T, H, W, generator=g) * torch.linspace(2.0, 0.1, T)[:, None, None].abs()
+    planes[5] = gt + 0.0005 * torch.randn(H, W, generator=g)          # the best candidate
+    mask = (gt > 0) & (gt < 1.25)
+    errs = []
+    for k in range(T):
+        e = ref.compute_err_metric(gt, planes[k], mask)
+        errs.append([e["depth_abs_err"], e["depth_err2"], e["depth_err4"], e["depth_err8"]])
+    errs = np.array(errs, dtype=np.float64)
+    out.update(metric_gt=npy(gt), metric_planes=npy(planes), metric_mask=npy(mask), metric_errs=errs,
+               metric_best=np.array(int(np.argmin(errs[:, 0]))))
+    out["poses"] = np.stack([np.asarray(pose_spherical(a, p, r), dtype=np.float64)
+                             for a, p, r in [(30.0, -30.0, 4.0), (-180.0, -30.0, 4.0), (99.0, 10.0, 2.5)]], 0)
+    out["pose_args"] = np.array([(30.0, -30.0, 4.0), (-180.0, -30.0, 4.0), (99.0, 10.0, 2.5)])
+    np.savez_compressed(os.path.join(HERE, "next_rows.npz"), **out)
+    print("next_rows.npz best", int(out["metric_best"]), errs[int(out["metric_best"])])
+
+
 def gen_train_grads():
     """One TRAINING iteration of the reference (train_dexnerf_rgb.py:246-278): train-mode
     run_one_iter_of_nerf with the four RNG draws replayed, loss = mse(rgb_coarse, target) +
@@ -478,3 +505,4 @@ if __name__ == "__main__":
     gen_lego()
     gen_tiny()
     gen_train_grads()
+    gen_next_rows()

@@ -235,3 +235,20 @@ def test_train_gradients_match_reference(golden, tag):
         new = O.adam_step(sd, {k: t(g[f"{tag}.grad.{net}.{k}"]) for k in sd}, lr=5e-3)
         for k, v in new.items():
             assert torch.allclose(v, t(g[f"{tag}.adam.{net}.{k}"]), rtol=0, atol=2e-6), (net, k)
+
+
+# ------------------------------------------------------------------ next rows
+def test_depth_error_metrics_and_threshold_selection(golden):
+    g = golden("next_rows")
+    gt, planes, mask = t(g["metric_gt"]), t(g["metric_planes"]), t(g["metric_mask"])
+    for k in range(planes.shape[0]):
+        e = O.compute_err_metric(gt, planes[k], mask)
+        close([e["depth_abs_err"], e["depth_err2"], e["depth_err4"], e["depth_err8"]], g["metric_errs"][k], 1e-5, 1e-7)
+    best, err = O.select_dex_threshold(list(planes), gt)
+    assert best == int(g["metric_best"]) and abs(err["depth_abs_err"] - g["metric_errs"][best, 0]) < 1e-4
+
+
+def test_pose_spherical(golden):
+    g = golden("next_rows")
+    for args, ref in zip(g["pose_args"], g["poses"]):
+        close(O.pose_spherical(*map(float, args)), ref, 1e-6, 1e-6)
