@@ -391,6 +391,7 @@ def main():
     if rank == 0:
         sampler.start()
     TU.kernel_event_log = []
+    L.event_log = []
     launches0 = L.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -399,6 +400,7 @@ def main():
         flush.zero_()
     e1.record()
     barrier()
+    hbm_log, L.event_log = L.event_log, None
     launches = L.launch_count - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms_dev = reduce_max(e0.elapsed_time(e1) / args.steps)
@@ -461,6 +463,15 @@ def main():
                          "flop_per_launch": flop_launch},
             "clocks": clocks,
         }
+        # the HBM-bound kernels of the step: achieved GB/s of algorithmic bytes against the measured copy peak
+        hbm = {}
+        for name, a, b, n_, S_, nbytes in hbm_log:
+            hbm.setdefault("%s_S%d" % (name, S_), []).append((a.elapsed_time(b), nbytes))
+        line["hbm_kernels"] = {
+            k: {"ms": sum(x[0] for x in v) / len(v), "bytes": v[0][1],
+                "achieved_gbs": v[0][1] / (sum(x[0] for x in v) / len(v) * 1e-3) / 1e9,
+                "frac_of_hbm_peak": v[0][1] / (sum(x[0] for x in v) / len(v) * 1e-3) / 1e9 / pk["hbm"]}
+            for k, v in sorted(hbm.items())}
         if train_line is not None:
             line["train_c4"] = {k: train_line[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e")}
             line["train_c4"]["kernel_ms"] = train_line["roofline"]["kernel_ms"]

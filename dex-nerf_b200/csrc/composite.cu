@@ -47,10 +47,25 @@ composite_kernel(const float4* __restrict__ rf, const float* __restrict__ z,
                  int64_t* __restrict__ dex_index) {
   extern __shared__ float smem[];
   // staging: [6 + 2T][32]: rgb0 rgb1 rgb2 disp acc depth | dex depth (T) | dex index (T, as int)
-  float* s_thr = smem;                          // T (padded to kMaxThresholds)
+  // Thresholds are ranked ascending once per CTA: a sample that exceeds the k-th smallest threshold
+  // exceeds all smaller ones, so "how many thresholds does sigma exceed" (a 6-step binary search)
+  // replaces T compares, and the first crossings of a whole run of thresholds come out of ONE
+  // ballot (see the level loop below).
+  float* s_thr = smem;                          // T ascending (padded to kMaxThresholds)
   float* s_out = smem + kMaxThresholds;         // (6 + 2T) * 32
+  __shared__ int s_orig[kMaxThresholds];        // sorted rank -> caller's threshold index
+  __shared__ int s_found[kCompositeWarps][kMaxThresholds];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int t = threadIdx.x; t < T; t += blockDim.x) s_thr[t] = thresholds[t];
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const float v = thresholds[t];
+    int rank = 0;
+    for (int o = 0; o < T; ++o) {
+      const float w = thresholds[o];
+      rank += (w < v) || (w == v && o < t);
+    }
+    s_thr[rank] = v;
+    s_orig[rank] = t;
+  }
   __syncthreads();
 
   for (int64_t base = (int64_t)blockIdx.x * kRaysPerCta; base < n;
@@ -65,8 +80,7 @@ composite_kernel(const float4* __restrict__ rf, const float* __restrict__ z,
       const float4* rf_row = rf + ray * S;
       const float* z_row = z + ray * S;
       double carry = 1.0, s_acc = 0.0, s_depth = 0.0, s_r = 0.0, s_g = 0.0, s_b = 0.0;
-      int found0 = -1, found1 = -1;  // lane l owns thresholds l and l + 32
-      int n_found = 0;
+      int level = 0;   // thresholds (in ascending rank) whose first crossing is already known
       for (int c0 = 0; c0 < S; c0 += 32) {
         const int j = c0 + lane;
         const bool valid = j < S;
@@ -98,18 +112,23 @@ composite_kernel(const float4* __restrict__ rf, const float* __restrict__ z,
           s_g += wd * (double)(1.0f / (1.0f + expf(-v.y)));
           s_b += wd * (double)(1.0f / (1.0f + expf(-v.z)));
         }
-        if (n_found < T) {
-          for (int t = 0; t < T; ++t) {
-            const unsigned hit = __ballot_sync(0xffffffffu, valid && sigma > s_thr[t]);
-            if (hit) {
-              const int first = c0 + __ffs(hit) - 1;
-              const bool mine = (t & 31) == lane;
-              const int cur = __shfl_sync(0xffffffffu, (t < 32) ? found0 : found1, t & 31);
-              if (cur < 0) {
-                if (mine) { if (t < 32) found0 = first; else found1 = first; }
-                ++n_found;
-              }
+        if (level < T) {                 // warp-uniform
+          // number of thresholds this sample's sigma exceeds (strictly): upper bound in s_thr
+          int cnt = 0;
+          if (valid) {
+            int lo = 0, hi = T;
+            while (lo < hi) {
+              const int mid = (lo + hi) >> 1;
+              if (s_thr[mid] < sigma) lo = mid + 1; else hi = mid;
             }
+            cnt = lo;
+          }
+          unsigned hit;
+          while ((hit = __ballot_sync(0xffffffffu, cnt > level)) != 0u) {
+            const int src = __ffs(hit) - 1;
+            const int reached = __shfl_sync(0xffffffffu, cnt, src);
+            for (int k = level + lane; k < reached; k += 32) s_found[warp][k] = c0 + src;
+            level = reached;
           }
         }
       }
@@ -134,12 +153,14 @@ composite_kernel(const float4* __restrict__ rf, const float* __restrict__ z,
         s_out[4 * 32 + slot] = acc;
         s_out[5 * 32 + slot] = depth;
       }
-      for (int t = lane; t < T; t += 32) {
-        int idx = (t < 32) ? found0 : found1;
-        if (idx < 0) idx = 0;  // argmax of an all-zero row (volume_rendering_utils.py:56)
+      __syncwarp();
+      for (int k = lane; k < T; k += 32) {
+        const int idx = (k < level) ? s_found[warp][k] : 0;   // argmax of an all-zero row is 0 (volume_rendering_utils.py:56)
+        const int t = s_orig[k];
         s_out[(6 + t) * 32 + slot] = z_row[idx];
         reinterpret_cast<int*>(s_out)[(6 + T + t) * 32 + slot] = idx;
       }
+      __syncwarp();
     }
     __syncthreads();
     // coalesced write-back of the 32-ray block

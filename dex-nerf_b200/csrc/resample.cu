@@ -102,10 +102,11 @@ __global__ void __launch_bounds__(256) resample_merge_kernel(const float* __rest
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
   const int B = Nc - 1;
-  float* s_cdf = smem + (size_t)warp * (2 * B + P);
+  const int St = Nc + Nf;
+  float* s_cdf = smem + (size_t)warp * (2 * B + P + St);
   float* s_bins = s_cdf + B;
   float* s_sort = s_bins + B;
-  const int St = Nc + Nf;
+  float* s_merge = s_sort + P;     // destination of the merge
   for (int64_t ray = (int64_t)blockIdx.x * wpc + warp; ray < n; ray += (int64_t)gridDim.x * wpc) {
     const float* z_row = zc + ray * Nc;
     const float* w_row = weights + ray * Nc + 1;  // weights[..., 1:-1]
@@ -120,6 +121,34 @@ __global__ void __launch_bounds__(256) resample_merge_kernel(const float* __rest
       s_sort[Nc + s] = invert_cdf(s_cdf, s_bins, B, uu, &ind);
     }
     __syncwarp();
+    // cat + sort (train_utils.py:173).  The coarse depths are sorted; with sorted u (validation:
+    // u = linspace) the new samples are sorted too, and the sort is a MERGE: every element's final
+    // position is its own index plus its rank in the other list (two binary searches per lane and
+    // element instead of a 36-stage bitonic network).  Ties: a coarse depth goes before equal
+    // samples, so the positions are a permutation.  Unsorted samples (random u) take the network.
+    bool sorted = true;
+    for (int s = lane; s < Nf - 1; s += 32) sorted = sorted && (s_sort[Nc + s] <= s_sort[Nc + s + 1]);
+    for (int j = lane; j < Nc - 1; j += 32) sorted = sorted && (s_sort[j] <= s_sort[j + 1]);
+    if (__all_sync(0xffffffffu, sorted)) {
+      const float* A = s_sort;         // Nc coarse depths
+      const float* Sm = s_sort + Nc;   // Nf samples
+      for (int i = lane; i < Nc; i += 32) {
+        const float v = A[i];
+        int lo = 0, hi = Nf;           // samples strictly below v
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (Sm[mid] < v) lo = mid + 1; else hi = mid; }
+        s_merge[i + lo] = v;
+      }
+      for (int i = lane; i < Nf; i += 32) {
+        const float v = Sm[i];
+        int lo = 0, hi = Nc;           // coarse depths at or below v
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (A[mid] <= v) lo = mid + 1; else hi = mid; }
+        s_merge[i + lo] = v;
+      }
+      __syncwarp();
+      for (int j = lane; j < St; j += 32) z_fine[ray * St + j] = s_merge[j];
+      __syncwarp();
+      continue;
+    }
     // bitonic sort of P (power of two) values by one warp
     for (int k = 2; k <= P; k <<= 1) {
       for (int j = k >> 1; j > 0; j >>= 1) {
@@ -172,7 +201,7 @@ extern "C" DEXNERF_API int dexnerf_resample_merge(const float* z_coarse, const f
   DN_REQUIRE(Nc >= 3 && Nf >= 1, "resample_merge: need Nc >= 3 and Nf >= 1");
   if (n <= 0) return 0;
   const int P = next_pow2(Nc + Nf);
-  const size_t per_warp = sizeof(float) * (2 * (size_t)(Nc - 1) + P);
+  const size_t per_warp = sizeof(float) * (2 * (size_t)(Nc - 1) + P + (size_t)(Nc + Nf));
   int wpc = 8;
   while (wpc > 1 && per_warp * wpc > 96 * 1024) wpc >>= 1;
   DN_REQUIRE(per_warp * wpc <= 200 * 1024, "resample_merge: %d+%d samples do not fit in shared memory", Nc, Nf);

@@ -94,6 +94,27 @@ def check(rc, what):
         raise DexNerfError("%s failed (%d): %s" % (what, rc, lib().dexnerf_last_error().decode()))
 
 
+event_log = None     # bench.py sets this to a list: (kernel name, start event, end event, n, S, algorithmic bytes)
+
+
+class timed:
+    """CUDA-event bracket around one C-ABI call, active only while bench.py collects a breakdown."""
+
+    def __init__(self, name, n, S, nbytes=0):
+        self.rec = (name, n, S, nbytes)
+
+    def __enter__(self):
+        if event_log is not None:
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if event_log is not None:
+            self.e1.record()
+            name, n, S, nbytes = self.rec
+            event_log.append((name, self.e0, self.e1, n, S, nbytes))
+
+
 def stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 

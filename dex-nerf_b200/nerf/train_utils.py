@@ -183,8 +183,9 @@ def predict_and_render_radiance(ray_batch, model_coarse, model_fine, options, mo
     u = L.dev_f32(u, "u", allow_none=True)
     z_fine = torch.empty((n, Nc + Nf), dtype=torch.float32, device=dev)
     if n:
-        L.check(L.lib().dexnerf_resample_merge(L.ptr(z), L.ptr(c["weights"]), n, Nc, Nf, L.ptr(u), L.ptr(z_fine),
-                                               L.stream_ptr()), "resample_merge")
+        with L.timed("resample_merge", n, Nc + Nf, n * (8 * Nc + 4 * (Nc + Nf) + (4 * Nf if u is not None else 0))):
+            L.check(L.lib().dexnerf_resample_merge(L.ptr(z), L.ptr(c["weights"]), n, Nc, Nf, L.ptr(u), L.ptr(z_fine),
+                                                   L.stream_ptr()), "resample_merge")
     noise = rng.get("noise_fine")
     if noise is None and std > 0.0:
         noise = torch.randn((n, Nc + Nf), dtype=torch.float32, device=dev) * std

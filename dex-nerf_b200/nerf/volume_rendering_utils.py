@@ -35,10 +35,14 @@ def render_maps(radiance_field, depth_values, ray_directions, noise, white_backg
              dex=torch.empty((T, n), dtype=torch.float32, device=dev) if T else None,
              dex_index=torch.empty((T, n), dtype=torch.int64, device=dev) if (T and want_indices) else None)
     if n:
-        L.check(L.lib().dexnerf_volume_render(
-            L.ptr(rf), L.ptr(z), L.ptr(rd), L.ptr(noise), n, S, int(bool(white_background)), L.ptr(thr), T,
-            L.ptr(o["rgb"]), L.ptr(o["disp"]), L.ptr(o["acc"]), L.ptr(o["weights"]), L.ptr(o["depth"]),
-            L.ptr(o["dex"]), L.ptr(o["dex_index"]), L.stream_ptr()), "volume_render_radiance_field")
+        # algorithmic HBM bytes of this launch (24*S + 36 + 4*T per ray in the full form)
+        nbytes = n * (S * (16 + 4 + (4 if noise is not None else 0) + (4 if want_weights else 0)) + 12 + 24 + 4 * T
+                      + (8 * T if want_indices else 0))
+        with L.timed("composite", n, S, nbytes):
+            L.check(L.lib().dexnerf_volume_render(
+                L.ptr(rf), L.ptr(z), L.ptr(rd), L.ptr(noise), n, S, int(bool(white_background)), L.ptr(thr), T,
+                L.ptr(o["rgb"]), L.ptr(o["disp"]), L.ptr(o["acc"]), L.ptr(o["weights"]), L.ptr(o["depth"]),
+                L.ptr(o["dex"]), L.ptr(o["dex_index"]), L.stream_ptr()), "volume_render_radiance_field")
     return o
 
 
