@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
         const uint32_t idesc = instr_desc(np);
         const bool has_main = L.k_main != 0;
         const uint32_t b_lbo16 = (uint32_t)np;            // LBO = np*16 bytes -> np in 16-byte units
-        const bool timing = kDbg && P.dbg_layer == -2 && blockIdx.x == 0 && it == 0 && leader;
+        const bool timing = kDbg && P.dbg_layer == -2 && blockIdx.x == 0 && it == (uint32_t)P.dbg_pass && leader;
 #pragma unroll 1
         for (int p = 0; p < L.n_pass; ++p) {
           const uint32_t slot_p = w_slot, phase_p = w_phase;   // first chunk of this pass
@@ -328,6 +328,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
             // Gate: the accumulator must have been drained by this tile's previous epilogue pass and,
             // for the first pass of a layer, the new A operand must be in place.  a_ready is
             // arrived after d_free by every epilogue thread, so one poll covers both.
+            if (timing) reinterpret_cast<long long*>(P.dbg)[900 + ((l * 2 + p) * 2 + t) * 3] = clock64();
             if (p == 0 && l > 0) {
               mbar_wait(bar(B_aready(t)), ph_aready[t], 3);
               ph_aready[t] ^= 1;
@@ -336,6 +337,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
               if (l == 0) mbar_wait(bar(B_xyzfull(t)), pe_ph, 2);
             }
             ph_dfree[t] ^= 1;
+            if (timing) reinterpret_cast<long long*>(P.dbg)[900 + ((l * 2 + p) * 2 + t) * 3 + 1] = clock64();
             uint32_t slot = slot_p, phase = phase_p;
             if (t == 0 && has_main) {
               // all main chunks of the pass are normally resident already (the ring runs ahead)
@@ -415,7 +417,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     const uint32_t a_tmem = tmem_base + (uint32_t)(t * 256) + lane_base;
     const uint32_t d_tmem = a_tmem + 128 + (uint32_t)(hs * 64);
     const bool timing = kDbg && P.dbg_layer == -2 && blockIdx.x == 0 && q == 0 && hs == 0 && lane == 0;
+    const bool timing_all = kDbg && P.dbg_layer == -2 && blockIdx.x == 0 && lane == 0;   // every epilogue warp: latest end
     long long* tl = reinterpret_cast<long long*>(P.dbg);
+    const int64_t tap_pair = (int64_t)blockIdx.x + (int64_t)P.dbg_pass * gridDim.x;   // which pair of this CTA the timing tap records
     float4* xchg = reinterpret_cast<float4*>(smem + Smem::xchg) + t * kTileM + row;
     const int pair_bar = 1 + t * 4 + q;            // named barrier of the two warps of this quarter
     uint32_t ph_dfull = 0;
@@ -432,7 +436,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
           mbar_wait(bar(B_dfull(t)), ph_dfull, 5);
           ph_dfull ^= 1;
           tc_fence_after();
-          if (timing && pair == blockIdx.x) tl[256 + ((l * 2) * 2 + t) * 2] = clock64();
+          if (timing && pair == tap_pair) tl[256 + ((l * 2) * 2 + t) * 2] = clock64();
           float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
           constexpr int hw = H / 2;           // outputs of the dir layer
           constexpr int mine = hw / 2;        // columns this warp reduces
@@ -483,7 +487,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
                 make_uint2(ymask[0], ymask[1]);
           tc_fence_before();
           mbar_arrive(bar(B_dfree(t)));
-          if (timing && pair == blockIdx.x) tl[256 + ((l * 2) * 2 + t) * 2 + 1] = clock64();
+          if (timing && pair == tap_pair) tl[256 + ((l * 2) * 2 + t) * 2 + 1] = clock64();
           // combine the two column halves: hs == 1 hands its partial sums to hs == 0
           if (hs == 1) *xchg = make_float4(rgb0, rgb1, rgb2, sigma);
           asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
@@ -505,7 +509,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
             mbar_wait(bar(B_dfull(t)), ph_dfull, 5);
             ph_dfull ^= 1;
             tc_fence_after();
-            if (timing && pair == blockIdx.x) tl[256 + ((l * 2 + p) * 2 + t) * 2] = clock64();
+            if (timing && pair == tap_pair) tl[256 + ((l * 2 + p) * 2 + t) * 2] = clock64();
             constexpr bool kTwoPass = (H == 256);
             const bool hold = kTwoPass && p == 0;
             float* dbg_dst = (kDbg && P.dbg_layer == l && P.dbg_pass == p && g < P.m_total)
@@ -515,7 +519,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
             const uint32_t dfree = bar(B_dfree(t));
             const uint32_t a_park = a_tmem + (uint32_t)(hs * 32);                 // pass-0 outputs: K [hs*64, +64)
             const uint32_t a_store = a_tmem + (uint32_t)(p * 64 + hs * 32);       // pass-p outputs
-            long long* stamps = (timing && pair == blockIdx.x && l == 2) ? tl + 600 + (p * 2 + t) * 16 : nullptr;
+            long long* stamps = (timing && pair == tap_pair && l == 2) ? tl + 600 + (p * 2 + t) * 16 : nullptr;
             uint8_t* tape_row = nullptr;
             uint2* tape_mask = nullptr;
             if (kTape) {
@@ -540,7 +544,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
               tc_fence_before();
               mbar_arrive(bar(B_aready(t)));
             }
-            if (timing && pair == blockIdx.x) tl[256 + ((l * 2 + p) * 2 + t) * 2 + 1] = clock64();
+            if (timing && pair == tap_pair) tl[256 + ((l * 2 + p) * 2 + t) * 2 + 1] = clock64();
+            if (timing_all && pair == tap_pair)
+              atomicMax(reinterpret_cast<unsigned long long*>(tl) + 800 + (l * 2 + p) * 2 + t, (unsigned long long)clock64());
           }
         }
       }

@@ -17,6 +17,7 @@ from nerf import tensorcore  # noqa: E402
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 148 * 16
     S = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+    tap = int(sys.argv[3]) if len(sys.argv) > 3 else 0        # which tile pair of CTA 0 is recorded (0 = first)
     torch.manual_seed(1)
     model = nerf.FlexibleNeRFModel(8, 256, 4, 10, 4).cuda()
     ex, ed = nerf.get_embedding_function(10, True, True), nerf.get_embedding_function(4, True, True)
@@ -29,10 +30,10 @@ def main():
     rf = torch.empty(n, S, 4, device="cuda")
     for _ in range(2):
         tensorcore.query(model, prog, ro, rd, vd, z, rf)
-    tl = torch.zeros(1024, dtype=torch.int64, device="cuda")
+    tl = torch.zeros(2048, dtype=torch.int64, device="cuda")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    tensorcore.query(model, prog, ro, rd, vd, z, rf, dbg=tl.view(torch.float32), dbg_layer=-2)
+    tensorcore.query(model, prog, ro, rd, vd, z, rf, dbg=tl.view(torch.float32), dbg_layer=-2, dbg_pass=tap)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
@@ -47,7 +48,7 @@ def main():
         print("%s: %.3f ms" % (name, e0.elapsed_time(e1)))
     t = tl.cpu().tolist()
     t0 = min(x for x in t[:512] if x > 0)
-    print("layer pass tile |  mma_start  mma_end (issue) |  epi_start  epi_end | epi_len  gap(epi_start - mma_end)")
+    print("layer pass tile |  mma_start  mma_end (issue) |  epi_start  epi_end | epi_len  gap(epi_start - mma_end) | last warp's epi_end")
     for l in range(10):
         for p in range(2):
             for tile in range(2):
@@ -55,8 +56,23 @@ def main():
                 ms_, me_, es_, ee_ = t[i], t[i + 1], t[256 + i], t[256 + i + 1]
                 if ms_ == 0:
                     continue
-                print("%5d %4d %4d | %10d %9d | %10d %8d | %7d %6d"
-                      % (l, p, tile, ms_ - t0, me_ - t0, es_ - t0, ee_ - t0, ee_ - es_, es_ - me_))
+                last = t[800 + (l * 2 + p) * 2 + tile]
+                print("%5d %4d %4d | %10d %9d | %10d %8d | %7d %6d | %8d"
+                      % (l, p, tile, ms_ - t0, me_ - t0, es_ - t0, ee_ - t0, ee_ - es_, es_ - me_, last - t0 if last else -1))
+    print("issuer: layer pass tile | before gate -> after gate -> first MMA issue (relative to the previous pass's issue end)")
+    prev_end = None
+    for l in range(10):
+        for p in range(2):
+            for tile in range(2):
+                i = ((l * 2 + p) * 2 + tile)
+                g0, g1 = t[900 + i * 3], t[900 + i * 3 + 1]
+                ms_, me_ = t[i * 2], t[i * 2 + 1]
+                if ms_ == 0:
+                    continue
+                if prev_end is not None and l in (2, 3, 4):
+                    print("  %d %d %d | loop overhead %5d | gate wait %5d | weights wait + fence %5d | issue %5d"
+                          % (l, p, tile, g0 - prev_end, g1 - g0, ms_ - g1, me_ - ms_))
+                prev_end = me_
     for p in range(2):
         for tile in range(2):
             st = t[600 + (p * 2 + tile) * 16: 600 + (p * 2 + tile) * 16 + 11]
