@@ -643,10 +643,17 @@ static int64_t blob_bytes(const Plan& P) { return (int64_t)kMaxConstFloats * 4 +
 
 struct PackChunk { int64_t dst; int w_off; int n_out; int n0; int np; int k0; int kc; int k_valid; };
 
-__global__ void pack_weights_kernel(const float* __restrict__ params, const PackChunk* __restrict__ chunks,
-                                    int n_chunks, uint8_t* __restrict__ blob) {
-  for (int ci = blockIdx.y; ci < n_chunks; ci += gridDim.y) {
-    const PackChunk c = chunks[ci];
+constexpr int kMaxPackChunks = 176;
+struct PackTables {     // passed by value (__grid_constant__): no host->device copy, no synchronisation
+  int n_chunks, n_moves;
+  PackChunk chunks[kMaxPackChunks];
+  int4 moves[32];
+};
+
+__global__ void pack_weights_kernel(const float* __restrict__ params, const __grid_constant__ PackTables Q,
+                                    uint8_t* __restrict__ blob) {
+  for (int ci = blockIdx.y; ci < Q.n_chunks; ci += gridDim.y) {
+    const PackChunk c = Q.chunks[ci];
     const int total = c.np * c.kc;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
       const int k = e / c.np, n = e - k * c.np;          // n fastest: coalesced reads of Wt[k][n]
@@ -658,11 +665,11 @@ __global__ void pack_weights_kernel(const float* __restrict__ params, const Pack
   }
 }
 
-__global__ void pack_consts_kernel(const float* __restrict__ params, const int4* __restrict__ moves, int n_moves,
+__global__ void pack_consts_kernel(const float* __restrict__ params, const __grid_constant__ PackTables Q,
                                    float* __restrict__ consts) {
   // moves: (dst, src, count, transpose_cols) ; transpose_cols > 0: src is Wt[count/cols... ] see host
-  for (int m = blockIdx.x; m < n_moves; m += gridDim.x) {
-    const int4 mv = moves[m];
+  for (int m = blockIdx.x; m < Q.n_moves; m += gridDim.x) {
+    const int4 mv = Q.moves[m];
     for (int i = threadIdx.x; i < mv.z; i += blockDim.x) {
       int src = mv.y + i;
       if (mv.w > 0) {               // W_rgb: consts[c*hw + k] = Wt[k*3 + c]
@@ -690,12 +697,14 @@ extern "C" DEXNERF_API int dexnerf_tc_pack(const dexnerf_flexible_spec* spec, co
                                            const float* params, void* packed, void* workspace, void* stream) {
   Plan plan;
   if (int rc = make_plan(spec, &plan)) return rc;
-  DN_REQUIRE(prog && params && packed && workspace, "tc_pack: null pointer");
+  DN_REQUIRE(prog && params && packed, "tc_pack: null pointer");
+  (void)workspace;   // kept in the ABI; the tables travel as kernel parameters now
   DN_REQUIRE(prog->n_ops == plan.n_layers + 2, "tc_pack: program has %d ops, expected %d", prog->n_ops, plan.n_layers + 2);
   cudaStream_t st = (cudaStream_t)stream;
   // chunk table (host) -> workspace (device)
-  static thread_local PackChunk h_chunks[256];
-  static thread_local int4 h_moves[32];
+  static thread_local PackTables tables;
+  PackChunk* h_chunks = tables.chunks;
+  int4* h_moves = tables.moves;
   int nch = 0, nmv = 0;
   int64_t dst = (int64_t)kMaxConstFloats * 4;
   for (int l = 0; l < plan.n_layers; ++l) {
@@ -707,7 +716,7 @@ extern "C" DEXNERF_API int dexnerf_tc_pack(const dexnerf_flexible_spec* spec, co
     const int np = L.n_out < 128 ? L.n_out : 128;
     for (int p = 0; p < L.n_pass; ++p) {
       for (int c = 0; c < L.k_main / 64 + (L.smem_src ? 1 : 0); ++c) {
-        DN_REQUIRE(nch < 256, "tc_pack: too many chunks");
+        DN_REQUIRE(nch < kMaxPackChunks, "tc_pack: too many chunks");
         PackChunk& pc = h_chunks[nch++];
         const bool main = c < L.k_main / 64;
         pc.dst = dst; pc.w_off = (int)op.w_off; pc.n_out = L.n_out; pc.n0 = p * 128; pc.np = np;
@@ -729,16 +738,12 @@ extern "C" DEXNERF_API int dexnerf_tc_pack(const dexnerf_flexible_spec* spec, co
   h_moves[nmv++] = make_int4(plan.off_balpha, (int)oa.b_off, 1, 0);
   h_moves[nmv++] = make_int4(plan.off_wrgb, (int)orgb.w_off, 3 * (H / 2), H / 2);
   h_moves[nmv++] = make_int4(plan.off_brgb, (int)orgb.b_off, 3, 0);
-  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
-  DN_CUDA(cudaMemcpyAsync(ws, h_chunks, sizeof(PackChunk) * nch, cudaMemcpyHostToDevice, st));
-  DN_CUDA(cudaMemcpyAsync(ws + sizeof(PackChunk) * 256, h_moves, sizeof(int4) * nmv, cudaMemcpyHostToDevice, st));
-  DN_CUDA(cudaStreamSynchronize(st));   // h_* are reused by the next call
+  tables.n_chunks = nch;
+  tables.n_moves = nmv;
   DN_CUDA(cudaMemsetAsync(packed, 0, (size_t)kMaxConstFloats * 4, st));
-  pack_weights_kernel<<<dim3(8, nch), 256, 0, st>>>(params, reinterpret_cast<const PackChunk*>(ws), nch,
-                                                    reinterpret_cast<uint8_t*>(packed));
+  pack_weights_kernel<<<dim3(8, nch), 256, 0, st>>>(params, tables, reinterpret_cast<uint8_t*>(packed));
   DN_CHECK_LAUNCH("pack_weights");
-  pack_consts_kernel<<<nmv, 128, 0, st>>>(params, reinterpret_cast<const int4*>(ws + sizeof(PackChunk) * 256), nmv,
-                                          reinterpret_cast<float*>(packed));
+  pack_consts_kernel<<<nmv, 128, 0, st>>>(params, tables, reinterpret_cast<float*>(packed));
   DN_CHECK_LAUNCH("pack_consts");
   return 0;
 }

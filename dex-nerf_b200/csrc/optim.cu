@@ -1,0 +1,85 @@
+// Training-loop glue on the device: the MSE loss with its gradient
+// (nerf/nerf_helpers.py:9-10 img2mse + autograd, train_dexnerf_rgb.py:264-277) and one fused Adam
+// step over the FLAT parameter buffer of both networks (torch.optim.Adam with its defaults,
+// train_dexnerf_rgb.py:142-148, 278-289) - the same buffer the weight-gradient GEMM reduces into
+// and NCCL all-reduces, so a training iteration touches the 2 x 595 844 parameters in exactly three
+// launches (memset, all-reduce, Adam) instead of ~100 per-tensor ones.
+#include "common.cuh"
+
+namespace dexnerf {
+
+// loss += mean((pred - target)^2) over n*3 values;  g = 2 (pred - target) / (3 n)  (d loss / d pred)
+__global__ void __launch_bounds__(256) mse_loss_grad_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                                            int64_t count, float inv_count, float* __restrict__ g,
+                                                            float* __restrict__ loss) {
+  double part = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    const float d = __fsub_rn(pred[i], target[i]);
+    part += (double)__fmul_rn(d, d);
+    g[i] = __fmul_rn(__fmul_rn(2.0f, d), inv_count);
+  }
+  part = warp_sum_f64(part);
+  __shared__ double s[8];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0;
+    for (int w = 0; w < 8; ++w) a += s[w];
+    atomicAdd(loss, (float)(a * (double)inv_count));
+  }
+}
+
+// torch.optim.Adam (amsgrad = False, weight_decay = 0, maximize = False), element for element:
+//   exp_avg = beta1 exp_avg + (1 - beta1) g;  exp_avg_sq = beta2 exp_avg_sq + (1 - beta2) g g
+//   denom = sqrt(exp_avg_sq) / sqrt(1 - beta2^t) + eps;  p -= (lr / (1 - beta1^t)) exp_avg / denom
+// grad_scale folds the 1 / world of the data-parallel mean into the same pass.
+__global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                        float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                                        float beta1, float beta2, float eps, float step_size,
+                                                        float bc2_sqrt, float grad_scale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = __fmul_rn(g[i], grad_scale);
+    // exp_avg.lerp_(grad, 1 - beta1) == exp_avg + (1 - beta1) (grad - exp_avg)
+    const float mi = __fmaf_rn(1.0f - beta1, __fsub_rn(gi, m[i]), m[i]);
+    // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value = 1 - beta2)
+    const float vi = __fmaf_rn(__fmul_rn(1.0f - beta2, gi), gi, __fmul_rn(v[i], beta2));
+    const float denom = __fadd_rn(__fdiv_rn(sqrtf(vi), bc2_sqrt), eps);
+    p[i] = __fsub_rn(p[i], __fmul_rn(step_size, __fdiv_rn(mi, denom)));
+    m[i] = mi;
+    v[i] = vi;
+  }
+}
+
+}  // namespace dexnerf
+
+using namespace dexnerf;
+
+extern "C" DEXNERF_API int dexnerf_mse_loss_grad(const float* pred, const float* target, int64_t count, float* grad,
+                                                 float* loss_accum, void* stream) {
+  DN_REQUIRE(pred && target && grad && loss_accum, "mse_loss_grad: null pointer");
+  if (count <= 0) return 0;
+  int64_t blocks = ceil_div64(count, 256 * 4);
+  if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+  mse_loss_grad_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(pred, target, count, 1.0f / (float)count, grad,
+                                                                      loss_accum);
+  DN_CHECK_LAUNCH("mse_loss_grad");
+  return 0;
+}
+
+extern "C" DEXNERF_API int dexnerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                                             int64_t n, float lr, float beta1, float beta2, float eps, int64_t step,
+                                             float grad_scale, void* stream) {
+  DN_REQUIRE(params && grads && exp_avg && exp_avg_sq, "adam_step: null pointer");
+  DN_REQUIRE(step >= 1, "adam_step: step counts from 1");
+  if (n <= 0) return 0;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr / bc1);
+  const float bc2_sqrt = (float)sqrt(bc2);
+  int64_t blocks = ceil_div64(n, 256 * 4);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  adam_step_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, beta1, beta2,
+                                                                  eps, step_size, bc2_sqrt, grad_scale);
+  DN_CHECK_LAUNCH("adam_step");
+  return 0;
+}

@@ -16,7 +16,7 @@ from .nerf_helpers import (cumprod_exclusive, gather_cdf_util, get_embedding_fun
 from .train_utils import (get_precision, predict_and_render_radiance, run_network, run_one_iter_of_nerf,
                           sample_pdf, set_precision)
 from .sharding import allreduce_gradients, gather_rows, row_block
-from .training import learning_rate, train_step
+from .training import Trainer, learning_rate, train_step
 from .eval_utils import (cast_to_image, compute_err_metric, dex_depth_error_metrics, pose_spherical, render_path,
                          render_poses_spherical, select_dex_threshold, world2cam_from_blender_pose)
 from .volume_rendering_utils import volume_render_radiance_field

@@ -202,3 +202,167 @@ def train_step(model_coarse, model_fine, optimizer, ro, rd, target, cfg, encode_
     optimizer.step()
     optimizer.zero_grad()
     return loss.detach(), coarse_loss.detach(), fine_loss.detach()
+
+
+# ---------------------------------------------------------------------------------------------------
+# Trainer: the training iteration without per-tensor glue
+# ---------------------------------------------------------------------------------------------------
+class Trainer:
+    """The reference's training iteration (train_dexnerf_rgb.py:246-289) on FLAT buffers.
+
+    Parameters of both networks live in one fp32 buffer in the kernels' program layout
+    (`[coarse | fine]`, each `Wt[in][out] | bias` per layer); gradients, Adam's two moment buffers
+    and the NCCL all-reduce use the same layout, so one iteration is ~35 launches: depths, two
+    forward queries with tape, two compositings, resampling, loss, two compositing backwards, two
+    activation-gradient chains, two weight-gradient GEMMs (reducing straight into the flat gradient
+    buffer), one all-reduce, ONE fused Adam step, and the re-packing of the bf16 weight images.
+    The arithmetic is identical to the autograd path (`run_one_iter_of_nerf(mode="train")` +
+    `torch.optim.Adam`); `sync_to_modules()` writes the parameters back into the nn.Modules (for
+    checkpoints with the reference's state-dict keys, or for rendering through the drop-in API)."""
+
+    def __init__(self, model_coarse, model_fine, options, encode_position_fn, encode_direction_fn, lr=5e-3,
+                 betas=(0.9, 0.999), eps=1e-8, lr_decay=250, lr_decay_factor=0.1, world_size=1, group=None):
+        self.models = (model_coarse, model_fine)
+        self.cfg = options
+        self.ex, self.ed = encode_position_fn, encode_direction_fn
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.lr_decay, self.lr_decay_factor = lr_decay, lr_decay_factor
+        self.world, self.group = int(world_size), group
+        self.iteration = 0
+        self.progs, self.specs, self.sizes = [], [], []
+        for m in self.models:
+            prog = m.program(self.ex, self.ed)
+            spec = tensorcore.spec_for(m, prog)
+            if spec is None:
+                raise L.DexNerfError("Trainer needs tensor-core-capable FlexibleNeRFModels (view directions, "
+                                     "hidden 128/256)")
+            self.progs.append(prog)
+            self.specs.append(spec)
+            self.sizes.append(m.packed_params().numel())
+        dev = self.models[0].packed_params().device
+        total = sum(self.sizes)
+        self.params = torch.empty(total, dtype=torch.float32, device=dev)
+        off = 0
+        self.views = []
+        for m, n in zip(self.models, self.sizes):
+            self.params[off:off + n].copy_(m.packed_params())
+            self.views.append((off, n))
+            off += n
+        self.grads = torch.zeros_like(self.params)
+        self.exp_avg = torch.zeros_like(self.params)
+        self.exp_avg_sq = torch.zeros_like(self.params)
+        self.loss = torch.zeros(3, dtype=torch.float32, device=dev)     # total, coarse, fine
+        self.blobs, self.blobs_t = [], []
+        for spec in self.specs:
+            self.blobs.append(torch.empty(L.lib().dexnerf_tc_packed_bytes(spec), dtype=torch.uint8, device=dev))
+            self.blobs_t.append(torch.empty(L.lib().dexnerf_tc_packed_bwd_bytes(spec), dtype=torch.uint8, device=dev))
+        self._repack()
+
+    # -- parameter plumbing -------------------------------------------------------------------
+    def _flat(self, buf, i):
+        off, n = self.views[i]
+        return buf[off:off + n]
+
+    def _repack(self):
+        """fp32 master parameters -> the bf16 operand images both directions stream (3 launches per net)."""
+        for i, (spec, prog) in enumerate(zip(self.specs, self.progs)):
+            p = self._flat(self.params, i)
+            L.check(L.lib().dexnerf_tc_pack(spec, prog, L.ptr(p), L.ptr(self.blobs[i]), None, L.stream_ptr()), "tc_pack")
+            L.launch_count += 1
+            L.check(L.lib().dexnerf_tc_pack_bwd(spec, prog, L.ptr(p), L.ptr(self.blobs_t[i]), L.stream_ptr()),
+                    "tc_pack_bwd")
+
+    def sync_to_modules(self):
+        """Flat master parameters -> nn.Module parameters (reference state-dict layout)."""
+        with torch.no_grad():
+            for i, m in enumerate(self.models):
+                flat, prog = self._flat(self.params, i), self.progs[i]
+                for k, (lin, *_r) in enumerate(m._layers()):
+                    op = prog.ops[k]
+                    fin, fout = lin.in_features, lin.out_features
+                    lin.weight.copy_(flat[op.w_off:op.w_off + fin * fout].view(fin, fout).t())
+                    lin.bias.copy_(flat[op.b_off:op.b_off + fout])
+
+    def learning_rate(self):
+        return learning_rate(self.lr, self.iteration, self.lr_decay, self.lr_decay_factor)
+
+    # -- one iteration ------------------------------------------------------------------------
+    def _forward(self, i, ro, rd, vd, z, noise, white):
+        n, S = z.shape
+        spec = self.specs[i]
+        nbytes = L.lib().dexnerf_tc_tape_bytes(spec, n * S)
+        tape = torch.empty(nbytes, dtype=torch.uint8, device=z.device)
+        rf = torch.empty((n, S, 4), dtype=torch.float32, device=z.device)
+        with _timed("mlp_tc_train_fwd", n, S):
+            L.check(L.lib().dexnerf_tc_query_train(spec, L.ptr(self.blobs[i]), L.ptr(ro), L.ptr(rd), L.ptr(vd), L.ptr(z),
+                                                   n, S, L.ptr(rf), L.ptr(tape), L.stream_ptr()), "tc_query_train")
+        o = render_maps(rf, z, rd, noise, white, None, 0, want_weights=(i == 0))
+        return rf, tape, o
+
+    def _backward(self, i, rf, tape, z, rd, noise, white, g_rgb):
+        n, S = z.shape
+        d_rf = volume_render_backward(rf, z, rd, noise, white, g_rgb, None, None)
+        g = self._flat(self.grads, i)
+        for bit, name in ((1, "mlp_tc_bwd_dx"), (2, "mlp_tc_bwd_dw")):
+            with _timed(name, n, S):
+                L.check(L.lib().dexnerf_tc_backward(self.specs[i], self.progs[i], L.ptr(self.blobs[i]),
+                                                    L.ptr(self.blobs_t[i]), L.ptr(tape), L.ptr(d_rf), n, S, L.ptr(g),
+                                                    bit, 0, L.stream_ptr()), "tc_backward")
+
+    def step(self, ray_origins, ray_directions, target, rng=None):
+        """One iteration on pre-selected rays (n,3) / targets (n,3).  Returns the loss tensor
+        [total, coarse, fine] (device, overwritten by the next step).  `rng` replays the four draws."""
+        rng = rng or {}
+        opt = self.cfg.nerf.train
+        ro = L.dev_f32(ray_origins.reshape(-1, 3), "ray_origins")
+        rd = L.dev_f32(ray_directions.reshape(-1, 3), "ray_directions")
+        tgt = L.dev_f32(target[..., :3].reshape(-1, 3), "target")
+        n, dev = ro.shape[0], ro.device
+        Nc, Nf = int(opt.num_coarse), int(opt.num_fine)
+        std, white = float(opt.radiance_field_noise_std), bool(opt.white_background)
+        vd = rd / rd.norm(p=2, dim=-1, keepdim=True)
+        near = torch.full((n,), float(self.cfg.dataset.near), dtype=torch.float32, device=dev)
+        far = torch.full((n,), float(self.cfg.dataset.far), dtype=torch.float32, device=dev)
+        t_rand = None
+        if opt.perturb:
+            t_rand = rng.get("t_rand")
+            if t_rand is None:
+                t_rand = torch.rand((n, Nc), dtype=torch.float32, device=dev)
+        z = torch.empty((n, Nc), dtype=torch.float32, device=dev)
+        L.check(L.lib().dexnerf_stratified_z(n, Nc, 0.0, 0.0, L.ptr(near), L.ptr(far), int(bool(opt.lindisp)),
+                                             L.ptr(t_rand), L.ptr(z), L.stream_ptr()), "stratified_z")
+        noise_c = rng.get("noise_coarse")
+        if noise_c is None and std > 0.0:
+            noise_c = torch.randn((n, Nc), dtype=torch.float32, device=dev) * std
+        rf_c, tape_c, oc = self._forward(0, ro, rd, vd, z, noise_c, white)
+        u = rng.get("u")
+        if u is None and opt.perturb != 0.0:
+            u = torch.rand((n, Nf), dtype=torch.float32, device=dev)
+        z_fine = torch.empty((n, Nc + Nf), dtype=torch.float32, device=dev)
+        L.check(L.lib().dexnerf_resample_merge(L.ptr(z), L.ptr(oc["weights"]), n, Nc, Nf, L.ptr(u), L.ptr(z_fine),
+                                               L.stream_ptr()), "resample_merge")
+        noise_f = rng.get("noise_fine")
+        if noise_f is None and std > 0.0:
+            noise_f = torch.randn((n, Nc + Nf), dtype=torch.float32, device=dev) * std
+        rf_f, tape_f, of = self._forward(1, ro, rd, vd, z_fine, noise_f, white)
+        # loss = mse(rgb_coarse, target) + mse(rgb_fine, target)  (train_dexnerf_rgb.py:264-277)
+        self.loss.zero_()
+        g_c, g_f = torch.empty_like(oc["rgb"]), torch.empty_like(of["rgb"])
+        for pred, g, slot in ((oc["rgb"], g_c, 1), (of["rgb"], g_f, 2)):
+            L.check(L.lib().dexnerf_mse_loss_grad(L.ptr(pred), L.ptr(tgt), pred.numel(), L.ptr(g),
+                                                  L.ptr(self.loss[slot:slot + 1]), L.stream_ptr()), "mse_loss_grad")
+        self.grads.zero_()
+        self._backward(1, rf_f, tape_f, z_fine, rd, noise_f, white, g_f)
+        self._backward(0, rf_c, tape_c, z, rd, noise_c, white, g_c)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=self.group)
+        # Adam with the script's schedule: iteration i steps with the rate set after iteration i-1 (:283-289)
+        lr = learning_rate(self.lr, self.iteration - 1, self.lr_decay, self.lr_decay_factor) if self.iteration else self.lr
+        self.iteration += 1
+        L.check(L.lib().dexnerf_adam_step(L.ptr(self.params), L.ptr(self.grads), L.ptr(self.exp_avg),
+                                          L.ptr(self.exp_avg_sq), self.params.numel(), lr, self.betas[0], self.betas[1],
+                                          self.eps, self.iteration, 1.0 / self.world, L.stream_ptr()), "adam_step")
+        self._repack()
+        self.loss[0:1] = self.loss[1:2] + self.loss[2:3]
+        return self.loss

@@ -132,8 +132,8 @@ DEXNERF_API int64_t dexnerf_tc_packed_bytes(const dexnerf_flexible_spec* spec /*
 #define DEXNERF_TC_PACK_WORKSPACE_BYTES 16384
 /* params: the fp32 program-layout buffer of the same model (as for dexnerf_mlp_query);
  * prog: the program it was built from.  packed: device blob of dexnerf_tc_packed_bytes();
- * workspace: device scratch of DEXNERF_TC_PACK_WORKSPACE_BYTES.  Packing is the one entry point
- * that synchronises the stream (once, to hand a small host table to the device). */
+ * workspace: unused since ABI revision 1.1 (may be NULL); packing is stream-ordered like every other
+ * entry point (the layout tables travel as kernel parameters). */
 DEXNERF_API int dexnerf_tc_pack(const dexnerf_flexible_spec* spec, const dexnerf_mlp_program* prog,
                     const float* params, void* packed, void* workspace, void* stream);
 /* run_network on tensor cores: ro, rd, viewdirs (n,3), z (n,S) -> rf (n,S,4).
@@ -183,6 +183,17 @@ DEXNERF_API int dexnerf_tc_backward(const dexnerf_flexible_spec* spec, const dex
  * first threshold with the smallest abs err (< 1000, else -1).  workspace: (4T + 1) doubles. */
 DEXNERF_API int dexnerf_depth_error_metrics(const float* pred, const float* gt, const uint8_t* mask, int64_t n,
                                 int T, float* out, int32_t* best, void* workspace, void* stream);
+
+/* ---- training-loop glue on the flat parameter buffer (train_dexnerf_rgb.py:264-289).
+ * dexnerf_mse_loss_grad: *loss_accum += mean((pred - target)^2) over `count` floats (img2mse,
+ * nerf_helpers.py:9-10) and grad = d(mean)/d(pred) = 2 (pred - target) / count.
+ * dexnerf_adam_step: torch.optim.Adam's update (defaults: no weight decay, no amsgrad) on n floats;
+ * `step` counts from 1; grads are multiplied by grad_scale first (1 / world for data parallel). */
+DEXNERF_API int dexnerf_mse_loss_grad(const float* pred, const float* target, int64_t count, float* grad,
+                          float* loss_accum, void* stream);
+DEXNERF_API int dexnerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                      float lr, float beta1, float beta2, float eps, int64_t step, float grad_scale,
+                      void* stream);
 
 #ifdef __cplusplus
 }

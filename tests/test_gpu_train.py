@@ -374,3 +374,93 @@ def test_training_iteration_8x256_vs_oracle():
             ref = grads[k].cuda()
             num += float(((p.grad - ref) ** 2).sum()); den += float((ref ** 2).sum())
         assert (num / den) ** 0.5 < 3e-2
+
+
+# ------------------------------------------------------------------ flat-buffer Trainer
+def test_adam_and_mse_kernels_vs_torch():
+    g = torch.Generator(device="cuda").manual_seed(2)
+    n = 100_003
+    p = torch.randn(n, device="cuda", generator=g)
+    ref = torch.nn.Parameter(p.clone())
+    opt = torch.optim.Adam([ref], lr=5e-3)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 4):
+        grad = torch.randn(n, device="cuda", generator=g) * (10.0 ** -step)
+        ref.grad = grad.clone()
+        opt.step()
+        L.check(L.lib().dexnerf_adam_step(L.ptr(p), L.ptr(grad), L.ptr(m), L.ptr(v), n, 5e-3, 0.9, 0.999, 1e-8, step, 1.0,
+                                          L.stream_ptr()), "adam")
+        assert float((p - ref.detach()).abs().max()) < 2e-6, step      # fp32 rounding of one update
+    pred, tgt = torch.rand(4096, 3, device="cuda", generator=g), torch.rand(4096, 3, device="cuda", generator=g)
+    gout, loss = torch.empty_like(pred), torch.zeros(1, device="cuda")
+    L.check(L.lib().dexnerf_mse_loss_grad(L.ptr(pred), L.ptr(tgt), pred.numel(), L.ptr(gout), L.ptr(loss), L.stream_ptr()),
+            "mse")
+    pr = pred.clone().requires_grad_(True)
+    lr_ = torch.nn.functional.mse_loss(pr, tgt)
+    lr_.backward()
+    assert abs(float(loss) - float(lr_)) < 1e-6 and float((gout - pr.grad).abs().max()) < 1e-9
+
+
+def test_trainer_matches_autograd_path():
+    """nerf.Trainer (flat buffers, fused Adam) against run_one_iter_of_nerf(mode='train') +
+    torch.optim.Adam on the same networks, rays and random draws: same loss, same parameter update."""
+    import copy
+    torch.manual_seed(11)
+    mc = nerf.FlexibleNeRFModel(8, 256, 4, 10, 4)
+    mf = nerf.FlexibleNeRFModel(8, 256, 4, 10, 4)
+    with torch.no_grad():
+        for m in (mc, mf):
+            m.fc_alpha.weight.mul_(40.0)
+            m.fc_alpha.bias.fill_(0.5)
+    mc, mf = mc.cuda(), mf.cuda()
+    mc2, mf2 = copy.deepcopy(mc), copy.deepcopy(mf)
+    n, nc, nf = 96, 64, 128
+    g = torch.Generator().manual_seed(4)
+    T = O.pose_spherical_world2cam(30.0, -30.0, 4.0)
+    K = torch.tensor([[60.0, 0, 6.0], [0, 60.0, 4.0], [0, 0, 1]])
+    ro, rd = O.get_ray_bundle(8, 12, None, T, K)
+    ro, rd = ro.reshape(-1, 3).cuda(), rd.reshape(-1, 3).cuda()
+    target = torch.rand(n, 3, generator=g).cuda()
+    cfg = make_cfg(nc, nf, 2.0, 6.0, False)
+    ex, ed = nerf.get_embedding_function(10, True, True), nerf.get_embedding_function(4, True, True)
+    trainer = nerf.Trainer(mc2, mf2, cfg, ex, ed, lr=5e-3)
+    opt = torch.optim.Adam(list(mc.parameters()) + list(mf.parameters()), lr=5e-3)
+    before = [p.detach().clone() for m in (mc, mf) for p in m.parameters()]
+    for it in range(2):
+        rng = dict(t_rand=torch.rand(n, nc, generator=g).cuda(), u=torch.rand(n, nf, generator=g).cuda(),
+                   noise_coarse=(0.2 * torch.randn(n, nc, generator=g)).cuda(),
+                   noise_fine=(0.2 * torch.randn(n, nc + nf, generator=g)).cuda())
+        for pg in opt.param_groups:          # the script's schedule: the rate set after the previous iteration
+            pg["lr"] = nerf.learning_rate(5e-3, it - 1, 250, 0.1) if it else 5e-3
+        loss_a, _, _ = nerf.train_step(mc, mf, opt, ro, rd, target, cfg, ex, ed, m_thres_cand=[], rng=rng,
+                                       height=8, width=12, focal=60.0)
+        loss_t = trainer.step(ro, rd, target, rng=rng)
+        assert abs(float(loss_t[0]) - float(loss_a)) < 1e-5, it
+    trainer.sync_to_modules()
+    after_a = [p.detach() for m in (mc, mf) for p in m.parameters()]
+    after_t = [p.detach() for m in (mc2, mf2) for p in m.parameters()]
+    num = sum(float(((a - t_) ** 2).sum()) for a, t_ in zip(after_a, after_t))
+    den = sum(float(((a - b) ** 2).sum()) for a, b in zip(after_a, before))
+    assert den > 0 and (num / den) ** 0.5 < 2e-2         # entries with |grad| ~ eps move differently; the rest agree
+    # the synced modules render like the trainer's own weights
+    with torch.no_grad():
+        a = nerf.run_one_iter_of_nerf(8, 12, 60.0, mc2, mf2, ro, rd, make_cfg(nc, nf, 2.0, 6.0, False, 0.0, False),
+                                      mode="validation", encode_position_fn=ex, encode_direction_fn=ed, m_thres_cand=[])
+    assert torch.isfinite(a[3]).all()
+
+
+def test_trainer_reduces_the_loss():
+    torch.manual_seed(5)
+    mc, mf = nerf.FlexibleNeRFModel(8, 128, 3, 10, 4).cuda(), nerf.FlexibleNeRFModel(8, 128, 3, 10, 4).cuda()
+    cfg = make_cfg(32, 32, 2.0, 6.0, False)
+    ex, ed = nerf.get_embedding_function(10, True, True), nerf.get_embedding_function(4, True, True)
+    trainer = nerf.Trainer(mc, mf, cfg, ex, ed, lr=5e-3)
+    g = torch.Generator().manual_seed(1)
+    T = O.pose_spherical_world2cam(10.0, -20.0, 4.0)
+    K = torch.tensor([[40.0, 0, 16.0], [0, 40.0, 16.0], [0, 0, 1]])
+    ro, rd = O.get_ray_bundle(32, 32, None, T, K)
+    ro, rd = ro.reshape(-1, 3).cuda(), rd.reshape(-1, 3).cuda()
+    target = (0.5 + 0.4 * torch.sin(torch.arange(1024)[:, None] * torch.tensor([0.01, 0.02, 0.03]))).cuda()
+    losses = [float(trainer.step(ro, rd, target)[0]) for _ in range(60)]
+    assert losses[-1] < 0.5 * losses[0], (losses[0], losses[-1])
+    assert trainer.iteration == 60 and trainer.learning_rate() < 5e-3
