@@ -37,6 +37,7 @@ __device__ __forceinline__ double warp_inclusive_product(double v, int lane) {
   return v;
 }
 
+template <int kSpl>
 __global__ void __launch_bounds__(kCompositeWarps * 32)
 composite_kernel(const float4* __restrict__ rf, const float* __restrict__ z,
                  const float* __restrict__ rd, const float* __restrict__ noise, int64_t n, int S,
@@ -81,54 +82,92 @@ composite_kernel(const float4* __restrict__ rf, const float* __restrict__ z,
       const float* z_row = z + ray * S;
       double carry = 1.0, s_acc = 0.0, s_depth = 0.0, s_r = 0.0, s_g = 0.0, s_b = 0.0;
       int level = 0;   // thresholds (in ascending rank) whose first crossing is already known
-      for (int c0 = 0; c0 < S; c0 += 32) {
-        const int j = c0 + lane;
-        const bool valid = j < S;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        float zj = 0.f, zn = 0.f, nz = 0.f;
-        if (valid) {
-          v = rf_row[j];
-          zj = z_row[j];
-          if (j + 1 < S) zn = z_row[j + 1];
-          if (noise) nz = noise[ray * S + j];
+      // A lane owns kSpl CONSECUTIVE samples of every 32*kSpl-sample chunk: its loads are 16*kSpl
+      // contiguous bytes, the transmittance needs one warp scan per chunk (of the lanes' local
+      // products) instead of one per 32 samples, and sample order = (lane, k) order.
+      for (int c0 = 0; c0 < S; c0 += 32 * kSpl) {
+        const int j0 = c0 + lane * kSpl;
+        float4 v[kSpl];
+        float zj[kSpl], sigma[kSpl], alpha[kSpl], xk[kSpl];
+        bool valid[kSpl];
+        float z_next = 0.f;            // depth of the sample after this lane's last one
+#pragma unroll
+        for (int k = 0; k < kSpl; ++k) {
+          valid[k] = j0 + k < S;
+          v[k] = valid[k] ? rf_row[j0 + k] : make_float4(0.f, 0.f, 0.f, 0.f);
+          zj[k] = valid[k] ? z_row[j0 + k] : 0.f;
         }
-        float dist = (j + 1 < S) ? __fsub_rn(zn, zj) : 1e10f;
-        dist = __fmul_rn(dist, norm);
-        const float sigma = fmaxf(__fadd_rn(v.w, nz), 0.0f);
-        const float alpha = valid ? __fsub_rn(1.0f, expf(-__fmul_rn(sigma, dist))) : 0.0f;
-        const float x = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
-        const double incl = warp_inclusive_product(valid ? (double)x : 1.0, lane);
+        z_next = __shfl_down_sync(0xffffffffu, zj[0], 1);
+        if (lane == 31 && j0 + kSpl < S) z_next = z_row[j0 + kSpl];
+        double local = 1.0;            // product of this lane's x, in sample order
+        double before[kSpl];           // ... of the samples before sample k within the lane
+#pragma unroll
+        for (int k = 0; k < kSpl; ++k) {
+          const int j = j0 + k;
+          const float zn = (k + 1 < kSpl) ? zj[k + 1] : z_next;
+          float nz = 0.f;
+          if (valid[k] && noise) nz = noise[ray * S + j];
+          float dist = (j + 1 < S) ? __fsub_rn(zn, zj[k]) : 1e10f;
+          dist = __fmul_rn(dist, norm);
+          sigma[k] = fmaxf(__fadd_rn(v[k].w, nz), 0.0f);
+          alpha[k] = valid[k] ? __fsub_rn(1.0f, expf(-__fmul_rn(sigma[k], dist))) : 0.0f;
+          xk[k] = __fadd_rn(__fsub_rn(1.0f, alpha[k]), 1e-10f);
+          before[k] = local;
+          if (valid[k]) local *= (double)xk[k];
+        }
+        const double incl = warp_inclusive_product(local, lane);
         double excl = shfl_up_f64(incl, 1);
         if (lane == 0) excl = 1.0;
-        const float trans = (float)(carry * excl);
+        const double lane_base = carry * excl;
         carry *= __shfl_sync(0xffffffffu, incl, 31);
-        const float w = __fmul_rn(alpha, trans);
-        if (valid) {
-          if (weights_out) weights_out[ray * S + j] = w;
-          const double wd = (double)w;
-          s_acc += wd;
-          s_depth += wd * (double)zj;
-          s_r += wd * (double)(1.0f / (1.0f + expf(-v.x)));
-          s_g += wd * (double)(1.0f / (1.0f + expf(-v.y)));
-          s_b += wd * (double)(1.0f / (1.0f + expf(-v.z)));
-        }
-        if (level < T) {                 // warp-uniform
-          // number of thresholds this sample's sigma exceeds (strictly): upper bound in s_thr
-          int cnt = 0;
-          if (valid) {
-            int lo = 0, hi = T;
-            while (lo < hi) {
-              const int mid = (lo + hi) >> 1;
-              if (s_thr[mid] < sigma) lo = mid + 1; else hi = mid;
-            }
-            cnt = lo;
+#pragma unroll
+        for (int k = 0; k < kSpl; ++k) {
+          const float trans = (float)(lane_base * before[k]);
+          const float w = __fmul_rn(alpha[k], trans);
+          if (valid[k]) {
+            if (weights_out) weights_out[ray * S + j0 + k] = w;
+            const double wd = (double)w;
+            s_acc += wd;
+            s_depth += wd * (double)zj[k];
+            // sigmoid: 1 / (1 + e^-x); __frcp_rn is the correctly rounded reciprocal, i.e. the same bits
+            // as the division at a third of the instructions
+            s_r += wd * (double)__frcp_rn(__fadd_rn(1.0f, expf(-v[k].x)));
+            s_g += wd * (double)__frcp_rn(__fadd_rn(1.0f, expf(-v[k].y)));
+            s_b += wd * (double)__frcp_rn(__fadd_rn(1.0f, expf(-v[k].z)));
           }
-          unsigned hit;
-          while ((hit = __ballot_sync(0xffffffffu, cnt > level)) != 0u) {
-            const int src = __ffs(hit) - 1;
-            const int reached = __shfl_sync(0xffffffffu, cnt, src);
-            for (int k = level + lane; k < reached; k += 32) s_found[warp][k] = c0 + src;
-            level = reached;
+        }
+        // ---- Dex-NeRF first crossings.  A chunk can only add crossings if some sigma exceeds the
+        // smallest threshold still open; then each sample counts the thresholds it exceeds (upper
+        // bound in the ascending table) and the open thresholds are closed in (lane, k) order.
+        if (level < T) {
+          float smax = 0.0f;
+#pragma unroll
+          for (int k = 0; k < kSpl; ++k) smax = fmaxf(smax, valid[k] ? sigma[k] : 0.0f);
+          if (__any_sync(0xffffffffu, smax > s_thr[level])) {   // warp-uniform
+            int cnt[kSpl];
+#pragma unroll
+            for (int k = 0; k < kSpl; ++k) {
+              int lo = 0, hi = T;
+              const float sg = valid[k] ? sigma[k] : 0.0f;
+              while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (s_thr[mid] < sg) lo = mid + 1; else hi = mid;
+              }
+              cnt[k] = lo;
+            }
+            while (true) {
+              int first = kSpl, reach = 0;      // this lane's first sample that closes an open threshold
+#pragma unroll
+              for (int k = kSpl - 1; k >= 0; --k)
+                if (cnt[k] > level) { first = k; reach = cnt[k]; }
+              const unsigned hit = __ballot_sync(0xffffffffu, first < kSpl);
+              if (hit == 0u) break;
+              const int src = __ffs(hit) - 1;
+              const int kk = __shfl_sync(0xffffffffu, first, src);
+              const int reached = __shfl_sync(0xffffffffu, reach, src);
+              for (int q = level + lane; q < reached; q += 32) s_found[warp][q] = c0 + src * kSpl + kk;
+              level = reached;
+            }
           }
         }
       }
@@ -325,9 +364,15 @@ extern "C" DEXNERF_API int dexnerf_volume_render(const float* rf, const float* z
   int64_t blocks = ceil_div64(n, kRaysPerCta);
   const int64_t cap = (int64_t)kNumSMs * 8 * 4;
   if (blocks > cap) blocks = cap;
-  composite_kernel<<<(int)blocks, kCompositeWarps * 32, smem, (cudaStream_t)stream>>>(
-      reinterpret_cast<const float4*>(rf), z, rd, noise, n, S, white_background, thresholds, T, rgb,
-      disp, acc, weights, depth, dex_depth, dex_index);
+  // samples per lane: 1 up to 32 samples, 2 up to 256 (C2: 64 and 192 fill every lane), 4 beyond (C5: 384)
+  auto launch = [&](auto kernel) {
+    kernel<<<(int)blocks, kCompositeWarps * 32, smem, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(rf), z, rd, noise, n, S, white_background, thresholds, T, rgb,
+        disp, acc, weights, depth, dex_depth, dex_index);
+  };
+  if (S <= 32) launch(composite_kernel<1>);
+  else if (S <= 256) launch(composite_kernel<2>);
+  else launch(composite_kernel<4>);
   DN_CHECK_LAUNCH("volume_render");
   return 0;
 }
