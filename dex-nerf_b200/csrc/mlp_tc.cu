@@ -138,7 +138,7 @@ struct Smem {
   static constexpr int consts = pe_dir + 2 * kPeDirBytes;
   static constexpr int xchg = consts + kMaxConstFloats * 4;             // [tile][row] float4 head partials
   static constexpr int bars = xchg + 2 * kTileM * 16;
-  static constexpr int n_bars = 2 * kNumSlots + 4 + 4 + 2 + 2 + 2;
+  static constexpr int n_bars = 2 * kNumSlots + 4 + 4 + 2 + 2 + 2 + 2;
   static constexpr int tmem_ptr = bars + n_bars * 8;
   static constexpr int total = tmem_ptr + 16;
 };
@@ -152,6 +152,7 @@ __device__ __forceinline__ int B_dirempty(int t) { return 2 * kNumSlots + 6 + t;
 __device__ __forceinline__ int B_aready(int t) { return 2 * kNumSlots + 8 + t; }
 __device__ __forceinline__ int B_dfull(int t) { return 2 * kNumSlots + 10 + t; }
 __device__ __forceinline__ int B_dfree(int t) { return 2 * kNumSlots + 12 + t; }
+__device__ __forceinline__ int B_ready(int t) { return 2 * kNumSlots + 14 + t; }
 
 __device__ __forceinline__ int chunks_in_pass(const TcLayer& L) { return L.k_main / 64 + (L.smem_src ? 1 : 0); }
 
@@ -243,6 +244,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
       mbar_init(bar(B_aready(t)), kEpiThreadsPerTile);
       mbar_init(bar(B_dfull(t)), 1);
       mbar_init(bar(B_dfree(t)), kEpiThreadsPerTile);
+      mbar_init(bar(B_ready(t)), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -302,7 +304,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     // committed), so only tile 0 polls the weight barriers.
     const bool leader = elect_one();
     uint32_t w_slot = 0, w_phase = 0;           // ring cursor of tile 0 (tile 1 trails by one pass)
-    uint32_t ph_dfree[2] = {0, 0}, ph_aready[2] = {0, 0};
+    uint32_t ph_ready[2] = {0, 0};
     uint32_t it = 0;
     const uint64_t desc_hi = ((uint64_t)(128 >> 4) << 32) | (1ull << 46);   // SBO = 128 B, version 1
     const uint32_t slot0_lo = ((sbase + Smem::w_slots) >> 4) & 0x3FFF;      // 16-byte units
@@ -325,32 +327,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
           for (int t = 0; t < 2; ++t) {
             const uint32_t a_tmem = tmem_base + (uint32_t)(t * 256);
             const uint32_t d_tmem = a_tmem + 128;
-            // Gate: the accumulator must have been drained by this tile's previous epilogue pass and,
-            // for the first pass of a layer, the new A operand must be in place.  a_ready is
-            // arrived after d_free by every epilogue thread, so one poll covers both.
+            // Everything this pass waits for (its tile's epilogue, the weight chunks, the encoders) is
+            // awaited by the SCOUT warp (warp 3, below), which then arrives on ready[t]: the issuer's
+            // own critical path between two passes is one barrier poll.
             if (timing) reinterpret_cast<long long*>(P.dbg)[900 + ((l * 2 + p) * 2 + t) * 3] = clock64();
-            if (p == 0 && l > 0) {
-              mbar_wait(bar(B_aready(t)), ph_aready[t], 3);
-              ph_aready[t] ^= 1;
-            } else {
-              mbar_wait(bar(B_dfree(t)), ph_dfree[t] ^ 1, 1);
-              if (l == 0) mbar_wait(bar(B_xyzfull(t)), pe_ph, 2);
-            }
-            ph_dfree[t] ^= 1;
+            mbar_wait(bar(B_ready(t)), ph_ready[t], 1);
+            ph_ready[t] ^= 1;
             if (timing) reinterpret_cast<long long*>(P.dbg)[900 + ((l * 2 + p) * 2 + t) * 3 + 1] = clock64();
             uint32_t slot = slot_p, phase = phase_p;
-            if (t == 0 && has_main) {
-              // all main chunks of the pass are normally resident already (the ring runs ahead)
-              uint32_t sl[4], ph4[4];
-              uint32_t s2 = slot, p2 = phase;
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                sl[c] = bar(B_wfull(s2)); ph4[c] = p2;
-                if (c + 1 < kMain) { if (++s2 == kNumSlots) { s2 = 0; p2 ^= 1; } }
-              }
-              if (kMain == 4) mbar_wait4(sl[0], ph4[0], sl[1], ph4[1], sl[2], ph4[2], sl[3], ph4[3], 4);
-              else mbar_wait4(sl[0], ph4[0], sl[1], ph4[1], sl[1], ph4[1], sl[1], ph4[1], 4);
-            }
             tc_fence_after();
             if (timing) reinterpret_cast<long long*>(P.dbg)[((l * 2 + p) * 2 + t) * 2] = clock64();
             if (has_main) {
@@ -370,9 +354,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
               }
             }
             if (L.smem_src) {
-              if (t == 0) { mbar_wait(bar(B_wfull(slot)), phase, 4); tc_fence_after(); }
               const uint32_t b_lo = (slot0_lo + slot * (kSlotBytes >> 4)) | (b_lbo16 << 16);
-              if (L.smem_src == 2 && p == 0) mbar_wait(bar(B_dirfull(t)), pe_ph, 2);
               const uint32_t a_addr = (L.smem_src == 1)
                   ? sbase + Smem::pe_xyz + (uint32_t)t * kPeXyzBytes
                   : sbase + Smem::pe_dir + (uint32_t)t * kPeDirBytes;
@@ -399,6 +381,52 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
             }
             __syncwarp();
             if (timing) reinterpret_cast<long long*>(P.dbg)[((l * 2 + p) * 2 + t) * 2 + 1] = clock64();
+            if (t == 1) { w_slot = slot; w_phase = phase; }
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // =============================== scout ===============================
+    // Walks the same pass sequence as the issuer, one step ahead of it: waits for the gate of the
+    // next pass (that tile's previous epilogue: d_free, or a_ready for the first pass of a layer),
+    // for its weight chunks (tile 0 only; tile 1 finds them resident) and for the encodings, then
+    // hands the pass to the issuer with ONE arrival.  It cannot run more than one pass of a tile
+    // ahead: the next gate of that tile needs the epilogue of the pass it has just released.
+    const bool leader = elect_one();
+    uint32_t w_slot = 0, w_phase = 0;
+    uint32_t ph_dfree[2] = {0, 0}, ph_aready[2] = {0, 0};
+    uint32_t it = 0;
+#pragma unroll 1
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++it) {
+      const uint32_t pe_ph = it & 1;
+#pragma unroll 1
+      for (int l = 0; l < P.n_layers; ++l) {
+        const TcLayer& L = P.layers[l];
+        const int n_chunks = chunks_in_pass(L);
+#pragma unroll 1
+        for (int p = 0; p < L.n_pass; ++p) {
+          const uint32_t slot_p = w_slot, phase_p = w_phase;
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            if (p == 0 && l > 0) {
+              mbar_wait(bar(B_aready(t)), ph_aready[t], 3);
+              ph_aready[t] ^= 1;
+            } else {
+              mbar_wait(bar(B_dfree(t)), ph_dfree[t] ^ 1, 1);
+              if (l == 0) mbar_wait(bar(B_xyzfull(t)), pe_ph, 2);
+            }
+            ph_dfree[t] ^= 1;
+            uint32_t slot = slot_p, phase = phase_p;
+            for (int c = 0; c < n_chunks; ++c) {
+              if (t == 0) mbar_wait(bar(B_wfull(slot)), phase, 4);
+              if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
+            }
+            if (L.smem_src == 2 && p == 0) mbar_wait(bar(B_dirfull(t)), pe_ph, 2);
+            tc_fence_after();
+            tc_fence_before();
+            if (leader) mbar_arrive(bar(B_ready(t)));
+            __syncwarp();
             if (t == 1) { w_slot = slot; w_phase = phase; }
           }
         }
