@@ -309,12 +309,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     const uint64_t desc_hi = ((uint64_t)(128 >> 4) << 32) | (1ull << 46);   // SBO = 128 B, version 1
     const uint32_t slot0_lo = ((sbase + Smem::w_slots) >> 4) & 0x3FFF;      // 16-byte units
     constexpr int kMain = H / 64;               // 64-wide K chunks of a hidden-activation operand
+    // The layer record of the NEXT layer is fetched (indexed constant loads, a few hundred cycles of
+    // dependent latency) while the last pass of the current layer is being issued, not between layers.
+    TcLayer L = P.layers[0];
 #pragma unroll 1
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++it) {
       const uint32_t pe_ph = it & 1;
 #pragma unroll 1
       for (int l = 0; l < P.n_layers; ++l) {
-        const TcLayer& L = P.layers[l];
+        TcLayer Lnext = L;
         const int np = L.n_out < 128 ? L.n_out : 128;
         const uint32_t idesc = instr_desc(np);
         const bool has_main = L.k_main != 0;
@@ -322,6 +325,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
         const bool timing = kDbg && P.dbg_layer == -2 && blockIdx.x == 0 && it == (uint32_t)P.dbg_pass && leader;
 #pragma unroll 1
         for (int p = 0; p < L.n_pass; ++p) {
+          if (p == L.n_pass - 1) Lnext = P.layers[l + 1 < P.n_layers ? l + 1 : 0];
           const uint32_t slot_p = w_slot, phase_p = w_phase;   // first chunk of this pass
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
@@ -384,6 +388,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
             if (t == 1) { w_slot = slot; w_phase = phase; }
           }
         }
+        L = Lnext;
       }
     }
   } else if (warp == 3) {
