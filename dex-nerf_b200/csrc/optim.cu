@@ -54,13 +54,14 @@ __global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, c
 
 using namespace dexnerf;
 
-extern "C" DEXNERF_API int dexnerf_mse_loss_grad(const float* pred, const float* target, int64_t count, float* grad,
-                                                 float* loss_accum, void* stream) {
+extern "C" DEXNERF_API int dexnerf_mse_loss_grad(const float* pred, const float* target, int64_t count,
+                                                 int64_t total_count, float* grad, float* loss_accum, void* stream) {
   DN_REQUIRE(pred && target && grad && loss_accum, "mse_loss_grad: null pointer");
+  DN_REQUIRE(total_count >= count, "mse_loss_grad: total_count < count");
   if (count <= 0) return 0;
   int64_t blocks = ceil_div64(count, 256 * 4);
   if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
-  mse_loss_grad_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(pred, target, count, 1.0f / (float)count, grad,
+  mse_loss_grad_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(pred, target, count, 1.0f / (float)total_count, grad,
                                                                       loss_accum);
   DN_CHECK_LAUNCH("mse_loss_grad");
   return 0;

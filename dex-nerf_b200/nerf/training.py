@@ -311,49 +311,22 @@ class Trainer:
 
     def step(self, ray_origins, ray_directions, target, rng=None):
         """One iteration on pre-selected rays (n,3) / targets (n,3).  Returns the loss tensor
-        [total, coarse, fine] (device, overwritten by the next step).  `rng` replays the four draws."""
+        [total, coarse, fine] (device, overwritten by the next step).  `rng` replays the four draws.
+        Batches larger than `cfg.nerf.train.chunksize` rays are processed in chunks (the tape of a chunk
+        is 10 KB per sample) whose gradients accumulate in the flat buffer before the single Adam step."""
         rng = rng or {}
         opt = self.cfg.nerf.train
         ro = L.dev_f32(ray_origins.reshape(-1, 3), "ray_origins")
         rd = L.dev_f32(ray_directions.reshape(-1, 3), "ray_directions")
         tgt = L.dev_f32(target[..., :3].reshape(-1, 3), "target")
-        n, dev = ro.shape[0], ro.device
-        Nc, Nf = int(opt.num_coarse), int(opt.num_fine)
-        std, white = float(opt.radiance_field_noise_std), bool(opt.white_background)
-        vd = rd / rd.norm(p=2, dim=-1, keepdim=True)
-        near = torch.full((n,), float(self.cfg.dataset.near), dtype=torch.float32, device=dev)
-        far = torch.full((n,), float(self.cfg.dataset.far), dtype=torch.float32, device=dev)
-        t_rand = None
-        if opt.perturb:
-            t_rand = rng.get("t_rand")
-            if t_rand is None:
-                t_rand = torch.rand((n, Nc), dtype=torch.float32, device=dev)
-        z = torch.empty((n, Nc), dtype=torch.float32, device=dev)
-        L.check(L.lib().dexnerf_stratified_z(n, Nc, 0.0, 0.0, L.ptr(near), L.ptr(far), int(bool(opt.lindisp)),
-                                             L.ptr(t_rand), L.ptr(z), L.stream_ptr()), "stratified_z")
-        noise_c = rng.get("noise_coarse")
-        if noise_c is None and std > 0.0:
-            noise_c = torch.randn((n, Nc), dtype=torch.float32, device=dev) * std
-        rf_c, tape_c, oc = self._forward(0, ro, rd, vd, z, noise_c, white)
-        u = rng.get("u")
-        if u is None and opt.perturb != 0.0:
-            u = torch.rand((n, Nf), dtype=torch.float32, device=dev)
-        z_fine = torch.empty((n, Nc + Nf), dtype=torch.float32, device=dev)
-        L.check(L.lib().dexnerf_resample_merge(L.ptr(z), L.ptr(oc["weights"]), n, Nc, Nf, L.ptr(u), L.ptr(z_fine),
-                                               L.stream_ptr()), "resample_merge")
-        noise_f = rng.get("noise_fine")
-        if noise_f is None and std > 0.0:
-            noise_f = torch.randn((n, Nc + Nf), dtype=torch.float32, device=dev) * std
-        rf_f, tape_f, of = self._forward(1, ro, rd, vd, z_fine, noise_f, white)
-        # loss = mse(rgb_coarse, target) + mse(rgb_fine, target)  (train_dexnerf_rgb.py:264-277)
+        n_total = ro.shape[0]
+        chunk = int(getattr(opt, "chunksize", n_total) or n_total)
         self.loss.zero_()
-        g_c, g_f = torch.empty_like(oc["rgb"]), torch.empty_like(of["rgb"])
-        for pred, g, slot in ((oc["rgb"], g_c, 1), (of["rgb"], g_f, 2)):
-            L.check(L.lib().dexnerf_mse_loss_grad(L.ptr(pred), L.ptr(tgt), pred.numel(), L.ptr(g),
-                                                  L.ptr(self.loss[slot:slot + 1]), L.stream_ptr()), "mse_loss_grad")
         self.grads.zero_()
-        self._backward(1, rf_f, tape_f, z_fine, rd, noise_f, white, g_f)
-        self._backward(0, rf_c, tape_c, z, rd, noise_c, white, g_c)
+        for start in range(0, n_total, chunk):
+            sl = slice(start, min(start + chunk, n_total))
+            sub = {k: v[sl] for k, v in rng.items() if v is not None}
+            self._accumulate(ro[sl], rd[sl], tgt[sl], sub, n_total)
         if self.world > 1:
             import torch.distributed as dist
             dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=self.group)
@@ -366,3 +339,47 @@ class Trainer:
         self._repack()
         self.loss[0:1] = self.loss[1:2] + self.loss[2:3]
         return self.loss
+
+    def _accumulate(self, ro, rd, tgt, rng, n_total):
+        """Forward + backward of one ray chunk; loss terms and gradients accumulate."""
+        opt = self.cfg.nerf.train
+        ro, rd, tgt = ro.contiguous(), rd.contiguous(), tgt.contiguous()
+        n, dev = ro.shape[0], ro.device
+        Nc, Nf = int(opt.num_coarse), int(opt.num_fine)
+        std, white = float(opt.radiance_field_noise_std), bool(opt.white_background)
+        vd = rd / rd.norm(p=2, dim=-1, keepdim=True)
+        near = torch.full((n,), float(self.cfg.dataset.near), dtype=torch.float32, device=dev)
+        far = torch.full((n,), float(self.cfg.dataset.far), dtype=torch.float32, device=dev)
+        t_rand = None
+        if opt.perturb:
+            t_rand = rng.get("t_rand")
+            if t_rand is None:
+                t_rand = torch.rand((n, Nc), dtype=torch.float32, device=dev)
+            t_rand = L.dev_f32(t_rand, "t_rand")
+        z = torch.empty((n, Nc), dtype=torch.float32, device=dev)
+        L.check(L.lib().dexnerf_stratified_z(n, Nc, 0.0, 0.0, L.ptr(near), L.ptr(far), int(bool(opt.lindisp)),
+                                             L.ptr(t_rand), L.ptr(z), L.stream_ptr()), "stratified_z")
+        noise_c = rng.get("noise_coarse")
+        if noise_c is None and std > 0.0:
+            noise_c = torch.randn((n, Nc), dtype=torch.float32, device=dev) * std
+        noise_c = L.dev_f32(noise_c, "noise_coarse", allow_none=True)
+        rf_c, tape_c, oc = self._forward(0, ro, rd, vd, z, noise_c, white)
+        u = rng.get("u")
+        if u is None and opt.perturb != 0.0:
+            u = torch.rand((n, Nf), dtype=torch.float32, device=dev)
+        u = L.dev_f32(u, "u", allow_none=True)
+        z_fine = torch.empty((n, Nc + Nf), dtype=torch.float32, device=dev)
+        L.check(L.lib().dexnerf_resample_merge(L.ptr(z), L.ptr(oc["weights"]), n, Nc, Nf, L.ptr(u), L.ptr(z_fine),
+                                               L.stream_ptr()), "resample_merge")
+        noise_f = rng.get("noise_fine")
+        if noise_f is None and std > 0.0:
+            noise_f = torch.randn((n, Nc + Nf), dtype=torch.float32, device=dev) * std
+        noise_f = L.dev_f32(noise_f, "noise_fine", allow_none=True)
+        rf_f, tape_f, of = self._forward(1, ro, rd, vd, z_fine, noise_f, white)
+        # loss = mse(rgb_coarse, target) + mse(rgb_fine, target)  (train_dexnerf_rgb.py:264-277)
+        g_c, g_f = torch.empty_like(oc["rgb"]), torch.empty_like(of["rgb"])
+        for pred, g, slot in ((oc["rgb"], g_c, 1), (of["rgb"], g_f, 2)):
+            L.check(L.lib().dexnerf_mse_loss_grad(L.ptr(pred), L.ptr(tgt), pred.numel(), 3 * n_total, L.ptr(g),
+                                                  L.ptr(self.loss[slot:slot + 1]), L.stream_ptr()), "mse_loss_grad")
+        self._backward(1, rf_f, tape_f, z_fine, rd, noise_f, white, g_f)
+        self._backward(0, rf_c, tape_c, z, rd, noise_c, white, g_c)

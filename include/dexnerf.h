@@ -185,12 +185,13 @@ DEXNERF_API int dexnerf_depth_error_metrics(const float* pred, const float* gt, 
                                 int T, float* out, int32_t* best, void* workspace, void* stream);
 
 /* ---- training-loop glue on the flat parameter buffer (train_dexnerf_rgb.py:264-289).
- * dexnerf_mse_loss_grad: *loss_accum += mean((pred - target)^2) over `count` floats (img2mse,
- * nerf_helpers.py:9-10) and grad = d(mean)/d(pred) = 2 (pred - target) / count.
+ * dexnerf_mse_loss_grad: *loss_accum += sum((pred - target)^2) / total_count over `count` floats
+ * (img2mse, nerf_helpers.py:9-10; total_count = count unless the batch is processed in chunks) and
+ * grad = 2 (pred - target) / total_count.
  * dexnerf_adam_step: torch.optim.Adam's update (defaults: no weight decay, no amsgrad) on n floats;
  * `step` counts from 1; grads are multiplied by grad_scale first (1 / world for data parallel). */
-DEXNERF_API int dexnerf_mse_loss_grad(const float* pred, const float* target, int64_t count, float* grad,
-                          float* loss_accum, void* stream);
+DEXNERF_API int dexnerf_mse_loss_grad(const float* pred, const float* target, int64_t count, int64_t total_count,
+                          float* grad, float* loss_accum, void* stream);
 DEXNERF_API int dexnerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                       float lr, float beta1, float beta2, float eps, int64_t step, float grad_scale,
                       void* stream);

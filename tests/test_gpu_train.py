@@ -393,7 +393,8 @@ def test_adam_and_mse_kernels_vs_torch():
         assert float((p - ref.detach()).abs().max()) < 2e-6, step      # fp32 rounding of one update
     pred, tgt = torch.rand(4096, 3, device="cuda", generator=g), torch.rand(4096, 3, device="cuda", generator=g)
     gout, loss = torch.empty_like(pred), torch.zeros(1, device="cuda")
-    L.check(L.lib().dexnerf_mse_loss_grad(L.ptr(pred), L.ptr(tgt), pred.numel(), L.ptr(gout), L.ptr(loss), L.stream_ptr()),
+    L.check(L.lib().dexnerf_mse_loss_grad(L.ptr(pred), L.ptr(tgt), pred.numel(), pred.numel(), L.ptr(gout), L.ptr(loss),
+                                          L.stream_ptr()),
             "mse")
     pr = pred.clone().requires_grad_(True)
     lr_ = torch.nn.functional.mse_loss(pr, tgt)
@@ -464,3 +465,29 @@ def test_trainer_reduces_the_loss():
     losses = [float(trainer.step(ro, rd, target)[0]) for _ in range(60)]
     assert losses[-1] < 0.5 * losses[0], (losses[0], losses[-1])
     assert trainer.iteration == 60 and trainer.learning_rate() < 5e-3
+
+
+def test_trainer_chunked_batch_equals_single_pass():
+    """chunksize < batch: the chunks' gradients accumulate in the flat buffer before the one Adam step."""
+    import copy
+    torch.manual_seed(3)
+    mc, mf = nerf.FlexibleNeRFModel(8, 128, 3, 6, 4).cuda(), nerf.FlexibleNeRFModel(8, 128, 3, 6, 4).cuda()
+    mc2, mf2 = copy.deepcopy(mc), copy.deepcopy(mf)
+    ex, ed = nerf.get_embedding_function(6, True, True), nerf.get_embedding_function(4, True, True)
+    n, nc, nf = 96, 16, 24
+    g = torch.Generator().manual_seed(8)
+    ro = (torch.randn(n, 3, generator=g) * 0.2).cuda()
+    rd = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1).cuda()
+    target = torch.rand(n, 3, generator=g).cuda()
+    rng = dict(t_rand=torch.rand(n, nc, generator=g).cuda(), u=torch.rand(n, nf, generator=g).cuda(),
+               noise_coarse=(0.2 * torch.randn(n, nc, generator=g)).cuda(),
+               noise_fine=(0.2 * torch.randn(n, nc + nf, generator=g)).cuda())
+    cfg_a, cfg_b = make_cfg(nc, nf, 2.0, 6.0, True), make_cfg(nc, nf, 2.0, 6.0, True)
+    cfg_b.nerf.train.chunksize = 40                     # 96 rays -> chunks of 40, 40, 16
+    ta, tb = nerf.Trainer(mc, mf, cfg_a, ex, ed), nerf.Trainer(mc2, mf2, cfg_b, ex, ed)
+    la, lb = ta.step(ro, rd, target, rng=rng).clone(), tb.step(ro, rd, target, rng=rng).clone()
+    assert float((la - lb).abs().max()) < 1e-6
+    assert rel_err(tb.grads, ta.grads) < 1e-5
+    upd_a, upd_b = ta.params.clone(), tb.params.clone()
+    assert float((upd_a - upd_b).abs().max()) < 5e-3 + 1e-9      # at most one Adam step (lr) where |grad| ~ eps
+    assert float(((upd_a - upd_b).abs() > 1e-5).float().mean()) < 0.02
