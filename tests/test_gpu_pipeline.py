@@ -274,3 +274,52 @@ def test_c5_ir_variant_128_256():
     dex = torch.stack(res[6:], 0).reshape(20, -1).cpu()
     assert (dex == torch.stack(ref[6:], 0)).float().mean() > 0.95
     assert len(res) == 26 and res[3].shape == (12, 16, 3)
+
+
+def test_c1_tiny_nerf(golden):
+    """BASELINE config 1 (tiny_nerf.py:111-159): get_ray_bundle -> global linspace depths ->
+    positional_encoding(L=6) -> 39-128-128-4 VeryTinyNeRFModel -> render_volume_density, through the
+    drop-in functions tiny_nerf.py imports (`from nerf import cumprod_exclusive, get_minibatches,
+    get_ray_bundle, positional_encoding`).  Golden: the reference itself at 20x20; then the full
+    100x100 frame of config 1 against the oracle."""
+    g = golden("tiny")
+    model = nerf.VeryTinyNeRFModel(filter_size=128, num_encoding_functions=6, use_viewdirs=False)
+    model.load_state_dict({k[len("model."):]: t(g[k]) for k in g.files if k.startswith("model.")})
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.cuda()
+
+    def tiny_iter(H, W, T, K):
+        ro, rd = nerf.get_ray_bundle(H, W, None, T.cuda(), K.cuda())
+        z = torch.linspace(2.0, 6.0, 64, device="cuda")                        # compute_query_points_from_rays
+        pts = ro[..., None, :] + rd[..., None, :] * z[:, None]
+        enc = nerf.positional_encoding(pts.reshape(-1, 3), 6)
+        rf = torch.cat([model(b) for b in nerf.get_minibatches(enc, chunksize=16384)], 0).reshape(H, W, 64, 4)
+        # render_volume_density (tiny_nerf.py:68-107), written with the drop-in cumprod_exclusive as the script does
+        sigma = torch.relu(rf[..., 3])
+        rgb = torch.sigmoid(rf[..., :3])
+        dists = torch.cat((z[1:] - z[:-1], torch.tensor([1e10], device="cuda")), -1)
+        alpha = 1.0 - torch.exp(-sigma * dists)
+        w = alpha * nerf.cumprod_exclusive(1.0 - alpha + 1e-10)
+        # ... and fused: the compositing kernel with unit-norm directions (no ||rd|| scaling in tiny_nerf.py)
+        unit = torch.zeros(H * W, 3, device="cuda")
+        unit[:, 2] = 1.0
+        fused = nerf.volume_render_radiance_field(rf.reshape(H * W, 64, 4), z.expand(H * W, 64).contiguous(), unit,
+                                                  m_thres_cand=[])
+        return (w[..., None] * rgb).sum(-2), (w * z).sum(-1), w.sum(-1), fused
+
+    with torch.no_grad():
+        H, W = map(int, g["HW"])
+        rgb, depth, acc, fused = tiny_iter(H, W, t(g["T"]), t(g["K"]))
+        close(rgb, g["rgb"], 2e-4, 2e-5)
+        close(depth, g["depth"], 2e-4, 2e-5)
+        close(acc, g["acc"], 2e-4, 2e-5)
+        close(fused[0].reshape(H, W, 3), g["rgb"], 2e-4, 2e-5)
+        close(fused[4].reshape(H, W), g["depth"], 2e-4, 2e-5)
+        # config 1 proper: 100x100, focal 138, camera at z = 4
+        K = torch.tensor([[138.0, 0, 50.0], [0, 138.0, 50.0], [0, 0, 1]])
+        T = torch.eye(4)
+        T[2, 3] = 4.0
+        rgb, depth, acc, fused = tiny_iter(100, 100, T, K)
+    ref = O.run_one_iter_of_tinynerf(100, 100, T, K, 2.0, 6.0, 64, 6, lambda x: O.very_tiny_forward(sd, x))
+    close(rgb, ref, 2e-4, 2e-5)
+    close(fused[0].reshape(100, 100, 3), ref, 2e-4, 2e-5)
