@@ -299,9 +299,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
     // The whole warp runs the (warp-uniform) control flow so that descriptors stay cheap to form;
-    // only the asynchronous instructions themselves are issued by one elected lane.  Tile 1 reuses
-    // the weight chunks tile 0 has just waited for (they stay resident until both tiles have
-    // committed), so only tile 0 polls the weight barriers.
+    // only the asynchronous instructions themselves are issued by one elected lane.  The passes of the
+    // two tiles alternate strictly (a tile's epilogue hides behind the other tile's pass); all waiting
+    // is done by the scout warp below, which releases a pass with one arrival on ready[tile].
     const bool leader = elect_one();
     uint32_t w_slot = 0, w_phase = 0;           // ring cursor of tile 0 (tile 1 trails by one pass)
     uint32_t ph_ready[2] = {0, 0};
@@ -314,7 +314,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     TcLayer L = P.layers[0];
 #pragma unroll 1
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++it) {
-      const uint32_t pe_ph = it & 1;
 #pragma unroll 1
       for (int l = 0; l < P.n_layers; ++l) {
         TcLayer Lnext = L;
