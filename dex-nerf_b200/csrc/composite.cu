@@ -354,12 +354,12 @@ extern "C" DEXNERF_API int dexnerf_volume_render(const float* rf, const float* z
                                      const float* thresholds, int T, float* rgb, float* disp,
                                      float* acc, float* weights, float* depth, float* dex_depth,
                                      int64_t* dex_index, void* stream) {
+  if (n <= 0) return 0;   // an empty batch (null data pointers) is a no-op
   DN_REQUIRE(rf && z && rd, "volume_render: null input");
   DN_REQUIRE(S >= 1, "volume_render: S < 1");
   DN_REQUIRE(T >= 0 && T <= kMaxThresholds, "volume_render: at most %d thresholds", kMaxThresholds);
   DN_REQUIRE(T == 0 || thresholds, "volume_render: thresholds is null");
   DN_REQUIRE((reinterpret_cast<uintptr_t>(rf) & 15) == 0, "volume_render: rf must be 16-byte aligned");
-  if (n <= 0) return 0;
   const size_t smem = sizeof(float) * (kMaxThresholds + (6 + 2 * (size_t)T) * 32);
   int64_t blocks = ceil_div64(n, kRaysPerCta);
   const int64_t cap = (int64_t)kNumSMs * 8 * 4;
@@ -378,9 +378,9 @@ extern "C" DEXNERF_API int dexnerf_volume_render(const float* rf, const float* z
 }
 
 extern "C" DEXNERF_API int dexnerf_cumprod_exclusive(const float* x, int64_t n, int S, float* out, void* stream) {
+  if (n <= 0) return 0;   // an empty batch (null data pointers) is a no-op
   DN_REQUIRE(x && out, "cumprod_exclusive: null pointer");
   DN_REQUIRE(S >= 1, "cumprod_exclusive: S < 1");
-  if (n <= 0) return 0;
   int64_t blocks = ceil_div64(n, 8);
   const int64_t cap = (int64_t)kNumSMs * 8 * 4;
   if (blocks > cap) blocks = cap;
@@ -394,11 +394,11 @@ extern "C" DEXNERF_API int dexnerf_volume_render_backward(const float* rf, const
                                                           int white_background, const float* g_rgb,
                                                           const float* g_depth, const float* g_acc,
                                                           float* d_rf, void* stream) {
+  if (n <= 0) return 0;   // an empty batch (null data pointers) is a no-op
   DN_REQUIRE(rf && z && rd && d_rf, "volume_render_backward: null pointer");
   DN_REQUIRE(S >= 1 && S <= 32 * kMaxChunks, "volume_render_backward: S must be in 1..%d", 32 * kMaxChunks);
   DN_REQUIRE((reinterpret_cast<uintptr_t>(rf) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_rf) & 15) == 0,
              "volume_render_backward: rf and d_rf must be 16-byte aligned");
-  if (n <= 0) return 0;
   int64_t blocks = ceil_div64(n, kCompositeWarps);
   const int64_t cap = (int64_t)kNumSMs * 8 * 4;
   if (blocks > cap) blocks = cap;

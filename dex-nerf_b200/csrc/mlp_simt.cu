@@ -227,9 +227,9 @@ using namespace dexnerf;
 
 extern "C" DEXNERF_API int dexnerf_mlp_forward(const dexnerf_mlp_program* prog, const float* params,
                                    const float* x, int64_t M, float* out, void* stream) {
+  if (M <= 0) return 0;   // an empty batch (null data pointers) is a no-op
   if (int rc = validate_program(prog, false)) return rc;
   DN_REQUIRE(params && x && out, "mlp_forward: null pointer");
-  if (M <= 0) return 0;
   SimtArgs a{};
   a.params = params; a.x = x; a.M = M; a.out = out; a.S = 1;
   return launch<0>(prog, a, (cudaStream_t)stream);
@@ -238,11 +238,11 @@ extern "C" DEXNERF_API int dexnerf_mlp_forward(const dexnerf_mlp_program* prog, 
 extern "C" DEXNERF_API int dexnerf_mlp_query(const dexnerf_mlp_program* prog, const float* params,
                                  const float* ro, const float* rd, const float* viewdirs,
                                  const float* z, int64_t n, int S, float* rf, void* stream) {
+  if (n <= 0) return 0;   // an empty batch (null data pointers) is a no-op
   if (int rc = validate_program(prog, true)) return rc;
   DN_REQUIRE(params && ro && rd && z && rf, "mlp_query: null pointer");
   DN_REQUIRE(prog->dim_dir == 0 || viewdirs, "mlp_query: the model takes view directions but viewdirs is null");
   DN_REQUIRE(S >= 1, "mlp_query: S < 1");
-  if (n <= 0) return 0;
   SimtArgs a{};
   a.params = params; a.ro = ro; a.rd = rd; a.viewdirs = viewdirs; a.z = z; a.S = S;
   a.M = n * (int64_t)S; a.out = rf;

@@ -56,9 +56,9 @@ using namespace dexnerf;
 
 extern "C" DEXNERF_API int dexnerf_mse_loss_grad(const float* pred, const float* target, int64_t count,
                                                  int64_t total_count, float* grad, float* loss_accum, void* stream) {
+  if (count <= 0) return 0;   // an empty batch (null data pointers) is a no-op
   DN_REQUIRE(pred && target && grad && loss_accum, "mse_loss_grad: null pointer");
   DN_REQUIRE(total_count >= count, "mse_loss_grad: total_count < count");
-  if (count <= 0) return 0;
   int64_t blocks = ceil_div64(count, 256 * 4);
   if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
   mse_loss_grad_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(pred, target, count, 1.0f / (float)total_count, grad,
@@ -70,9 +70,9 @@ extern "C" DEXNERF_API int dexnerf_mse_loss_grad(const float* pred, const float*
 extern "C" DEXNERF_API int dexnerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                                              int64_t n, float lr, float beta1, float beta2, float eps, int64_t step,
                                              float grad_scale, void* stream) {
+  if (n <= 0) return 0;   // an empty batch (null data pointers) is a no-op
   DN_REQUIRE(params && grads && exp_avg && exp_avg_sq, "adam_step: null pointer");
   DN_REQUIRE(step >= 1, "adam_step: step counts from 1");
-  if (n <= 0) return 0;
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   const float step_size = (float)((double)lr / bc1);

@@ -189,11 +189,11 @@ extern "C" DEXNERF_API int dexnerf_ndc_rays(const float* ro, const float* rd, in
 
 extern "C" DEXNERF_API int dexnerf_positional_encoding(const float* x, int64_t M, int L, int include_input,
                                            int log_sampling, float* out, void* stream) {
+  if (M <= 0) return 0;   // an empty batch (null data pointers) is a no-op
   DN_REQUIRE(x && out, "positional_encoding: null pointer");
   DN_REQUIRE(L >= 0 && L <= 31, "positional_encoding: L out of range");
   const int D = (include_input ? 3 : 0) + 6 * L;
   DN_REQUIRE(D > 0, "positional_encoding: empty encoding");
-  if (M <= 0) return 0;
   posenc_kernel<<<elementwise_grid(M * D), 256, 0, (cudaStream_t)stream>>>(x, M, L, include_input,
                                                                          log_sampling, D, out);
   DN_CHECK_LAUNCH("positional_encoding");
@@ -203,9 +203,9 @@ extern "C" DEXNERF_API int dexnerf_positional_encoding(const float* x, int64_t M
 extern "C" DEXNERF_API int dexnerf_stratified_z(int64_t n, int Nc, float near, float far, const float* near_arr,
                                     const float* far_arr, int lindisp, const float* t_rand, float* z,
                                     void* stream) {
+  if (n <= 0) return 0;   // an empty batch (null data pointers) is a no-op
   DN_REQUIRE(z, "stratified_z: null output");
   DN_REQUIRE(Nc >= 1, "stratified_z: Nc < 1");
-  if (n <= 0) return 0;
   stratified_kernel<<<elementwise_grid(n * Nc), 256, 0, (cudaStream_t)stream>>>(
       n, Nc, near, far, near_arr, far_arr, lindisp, t_rand, z);
   DN_CHECK_LAUNCH("stratified_z");

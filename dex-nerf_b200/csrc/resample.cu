@@ -176,9 +176,9 @@ using namespace dexnerf;
 
 extern "C" DEXNERF_API int dexnerf_sample_pdf(const float* bins, const float* weights, int64_t n, int B, int Nf,
                                   const float* u, float* samples, int64_t* inds, void* stream) {
+  if (n <= 0) return 0;   // an empty batch (null data pointers) is a no-op
   DN_REQUIRE(bins && weights && samples, "sample_pdf: null pointer");
   DN_REQUIRE(B >= 2 && Nf >= 1, "sample_pdf: need at least 2 bins and 1 sample");
-  if (n <= 0) return 0;
   const size_t per_warp = sizeof(float) * 2 * (size_t)B;
   int wpc = 8;
   while (wpc > 1 && per_warp * wpc > 96 * 1024) wpc >>= 1;
@@ -197,9 +197,9 @@ extern "C" DEXNERF_API int dexnerf_sample_pdf(const float* bins, const float* we
 
 extern "C" DEXNERF_API int dexnerf_resample_merge(const float* z_coarse, const float* weights, int64_t n, int Nc,
                                       int Nf, const float* u, float* z_fine, void* stream) {
+  if (n <= 0) return 0;   // an empty batch (null data pointers) is a no-op
   DN_REQUIRE(z_coarse && weights && z_fine, "resample_merge: null pointer");
   DN_REQUIRE(Nc >= 3 && Nf >= 1, "resample_merge: need Nc >= 3 and Nf >= 1");
-  if (n <= 0) return 0;
   const int P = next_pow2(Nc + Nf);
   const size_t per_warp = sizeof(float) * (2 * (size_t)(Nc - 1) + P + (size_t)(Nc + Nf));
   int wpc = 8;
