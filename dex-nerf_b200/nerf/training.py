@@ -286,6 +286,79 @@ class Trainer:
     def learning_rate(self):
         return learning_rate(self.lr, self.iteration, self.lr_decay, self.lr_decay_factor)
 
+    # -- checkpoints in the reference's format (train_dexnerf_rgb.py:442-457 / :167-174) --------
+    def _param_slices(self):
+        """(flat offset of W, flat offset of b, nn.Linear) for every parameter pair, in the order of
+        list(model_coarse.parameters()) + list(model_fine.parameters()) - the optimizer's order
+        (train_dexnerf_rgb.py:142-148)."""
+        out = []
+        for i, m in enumerate(self.models):
+            base = self.views[i][0]
+            by_lin = {id(lin): self.progs[i].ops[k] for k, (lin, *_r) in enumerate(m._layers())}
+            for lin in (mod for mod in m.modules() if isinstance(mod, torch.nn.Linear)):
+                op = by_lin.get(id(lin))
+                out.append((None, None, lin) if op is None else (base + op.w_off, base + op.b_off, lin))
+        return out
+
+    def checkpoint_dict(self, loss=None, psnr=None):
+        """{iter, model_coarse_state_dict, model_fine_state_dict, optimizer_state_dict, loss, psnr} as the
+        reference writes it: the state dicts have the reference's keys, and the optimizer entry is a
+        torch.optim.Adam state_dict over coarse + fine parameters, so the reference's script (or
+        torch.optim.Adam.load_state_dict) resumes from it."""
+        self.sync_to_modules()
+        state, idx = {}, 0
+        for w_off, b_off, lin in self._param_slices():
+            fin, fout = lin.in_features, lin.out_features
+            for off, shape, is_w in ((w_off, (fin, fout), True), (b_off, (fout,), False)):
+                if off is None:          # a layer the forward never uses (none for FlexibleNeRFModel)
+                    idx += 1
+                    continue
+                n = fin * fout if is_w else fout
+                ea, es = self.exp_avg[off:off + n].view(shape), self.exp_avg_sq[off:off + n].view(shape)
+                if is_w:
+                    ea, es = ea.t(), es.t()
+                state[idx] = {"step": torch.tensor(float(self.iteration)), "exp_avg": ea.contiguous().clone(),
+                              "exp_avg_sq": es.contiguous().clone()}
+                idx += 1
+        group = {"lr": self.learning_rate() if self.iteration else self.lr, "betas": self.betas, "eps": self.eps,
+                 "weight_decay": 0, "amsgrad": False, "maximize": False, "foreach": None, "capturable": False,
+                 "differentiable": False, "fused": None, "decoupled_weight_decay": False, "params": list(range(idx))}
+        if self.iteration == 0:
+            state = {}
+        return {"iter": self.iteration, "model_coarse_state_dict": self.models[0].state_dict(),
+                "model_fine_state_dict": self.models[1].state_dict(),
+                "optimizer_state_dict": {"state": state, "param_groups": [group]}, "loss": loss, "psnr": psnr}
+
+    def load_checkpoint_dict(self, ckpt):
+        """Resume from a checkpoint written by the reference script or by checkpoint_dict()."""
+        self.models[0].load_state_dict(ckpt["model_coarse_state_dict"])
+        if ckpt.get("model_fine_state_dict"):
+            self.models[1].load_state_dict(ckpt["model_fine_state_dict"])
+        off = 0
+        for m, n in zip(self.models, self.sizes):
+            m.__dict__.pop("_packed_cache", None)
+            self.params[off:off + n].copy_(m.packed_params())
+            off += n
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        state = (ckpt.get("optimizer_state_dict") or {}).get("state", {})
+        idx = 0
+        for w_off, b_off, lin in self._param_slices():
+            fin, fout = lin.in_features, lin.out_features
+            for off_, is_w in ((w_off, True), (b_off, False)):
+                st = state.get(idx)
+                idx += 1
+                if st is None or off_ is None:
+                    continue
+                n = fin * fout if is_w else fout
+                ea, es = st["exp_avg"].to(self.params.device), st["exp_avg_sq"].to(self.params.device)
+                if is_w:
+                    ea, es = ea.t().contiguous(), es.t().contiguous()
+                self.exp_avg[off_:off_ + n].copy_(ea.reshape(-1))
+                self.exp_avg_sq[off_:off_ + n].copy_(es.reshape(-1))
+        self.iteration = int(ckpt.get("iter", 0))
+        self._repack()
+
     # -- one iteration ------------------------------------------------------------------------
     def _forward(self, i, ro, rd, vd, z, noise, white):
         n, S = z.shape

@@ -491,3 +491,54 @@ def test_trainer_chunked_batch_equals_single_pass():
     upd_a, upd_b = ta.params.clone(), tb.params.clone()
     assert float((upd_a - upd_b).abs().max()) < 5e-3 + 1e-9      # at most one Adam step (lr) where |grad| ~ eps
     assert float(((upd_a - upd_b).abs() > 1e-5).float().mean()) < 0.02
+
+
+def test_trainer_checkpoint_round_trip_with_torch_adam(tmp_path):
+    """A checkpoint written by nerf.Trainer has the reference's layout (train_dexnerf_rgb.py:442-457):
+    fresh modules + a fresh torch.optim.Adam resume from it (as the reference script does at :167-174)
+    and their next iteration equals the trainer's next iteration; a new Trainer resumes from it too."""
+    import copy
+    torch.manual_seed(21)
+    mk = lambda: nerf.FlexibleNeRFModel(8, 128, 3, 6, 4).cuda()
+    mc, mf = mk(), mk()
+    ex, ed = nerf.get_embedding_function(6, True, True), nerf.get_embedding_function(4, True, True)
+    n, nc, nf = 64, 16, 24
+    cfg = make_cfg(nc, nf, 2.0, 6.0, False)
+    g = torch.Generator().manual_seed(3)
+    ro = (torch.randn(n, 3, generator=g) * 0.2).cuda()
+    rd = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1).cuda()
+    target = torch.rand(n, 3, generator=g).cuda()
+
+    def draws():
+        return dict(t_rand=torch.rand(n, nc, generator=g).cuda(), u=torch.rand(n, nf, generator=g).cuda(),
+                    noise_coarse=(0.2 * torch.randn(n, nc, generator=g)).cuda(),
+                    noise_fine=(0.2 * torch.randn(n, nc + nf, generator=g)).cuda())
+    trainer = nerf.Trainer(mc, mf, cfg, ex, ed, lr=5e-3)
+    for _ in range(3):
+        loss = trainer.step(ro, rd, target, rng=draws())
+    path = tmp_path / "checkpoint00003.ckpt"
+    torch.save(trainer.checkpoint_dict(loss=float(loss[0]), psnr=float(nerf.mse2psnr(float(loss[0])))), path)
+    ckpt = torch.load(path, weights_only=False)
+    assert set(ckpt) == {"iter", "model_coarse_state_dict", "model_fine_state_dict", "optimizer_state_dict", "loss", "psnr"}
+    assert ckpt["iter"] == 3 and set(ckpt["model_coarse_state_dict"]) == set(mk().state_dict())
+    # (a) the reference's resume path: modules + torch.optim.Adam
+    mc2, mf2 = mk(), mk()
+    mc2.load_state_dict(ckpt["model_coarse_state_dict"])
+    mf2.load_state_dict(ckpt["model_fine_state_dict"])
+    opt = torch.optim.Adam(list(mc2.parameters()) + list(mf2.parameters()), lr=5e-3)
+    opt.load_state_dict(ckpt["optimizer_state_dict"])
+    # (b) a new trainer
+    mc3, mf3 = mk(), mk()
+    t3 = nerf.Trainer(mc3, mf3, cfg, ex, ed, lr=5e-3)
+    t3.load_checkpoint_dict(ckpt)
+    assert t3.iteration == 3
+    rng = draws()
+    la = nerf.train_step(mc2, mf2, opt, ro, rd, target, cfg, ex, ed, m_thres_cand=[], rng=rng, height=8, width=8, focal=1.0)[0]
+    lb = trainer.step(ro, rd, target, rng=rng)[0].clone()
+    lc = t3.step(ro, rd, target, rng=rng)[0].clone()
+    assert abs(float(la) - float(lb)) < 1e-5 and abs(float(lb) - float(lc)) < 1e-6
+    trainer.sync_to_modules()
+    t3.sync_to_modules()
+    for a, b, c in zip(mc2.parameters(), mc.parameters(), mc3.parameters()):
+        assert float((b - c).abs().max()) < 1e-6                     # trainer vs resumed trainer: same kernels
+        assert float(((a - b).abs() > 2e-4).float().mean()) < 0.02   # vs torch Adam: entries with |grad| ~ eps aside
