@@ -80,7 +80,10 @@ composite_kernel(const float4* __restrict__ rf, const float* __restrict__ z,
           (float)sqrt((double)dx * (double)dx + (double)dy * (double)dy + (double)dz * (double)dz);
       const float4* rf_row = rf + ray * S;
       const float* z_row = z + ray * S;
-      double carry = 1.0, s_acc = 0.0, s_depth = 0.0, s_r = 0.0, s_g = 0.0, s_b = 0.0;
+      double carry = 1.0;
+      // per-lane partial sums in fp32 (6-12 terms each), then a warp tree: the reference's own torch.sum is an
+      // fp32 cascade; only the transmittance product needs the fp64 the reference's cumprod accumulates in
+      float s_acc = 0.f, s_depth = 0.f, s_r = 0.f, s_g = 0.f, s_b = 0.f;
       int level = 0;   // thresholds (in ascending rank) whose first crossing is already known
       // A lane owns kSpl CONSECUTIVE samples of every 32*kSpl-sample chunk: its loads are 16*kSpl
       // contiguous bytes, the transmittance needs one warp scan per chunk (of the lanes' local
@@ -126,14 +129,13 @@ composite_kernel(const float4* __restrict__ rf, const float* __restrict__ z,
           const float w = __fmul_rn(alpha[k], trans);
           if (valid[k]) {
             if (weights_out) weights_out[ray * S + j0 + k] = w;
-            const double wd = (double)w;
-            s_acc += wd;
-            s_depth += wd * (double)zj[k];
-            // sigmoid: 1 / (1 + e^-x); __frcp_rn is the correctly rounded reciprocal, i.e. the same bits
-            // as the division at a third of the instructions
-            s_r += wd * (double)__frcp_rn(__fadd_rn(1.0f, expf(-v[k].x)));
-            s_g += wd * (double)__frcp_rn(__fadd_rn(1.0f, expf(-v[k].y)));
-            s_b += wd * (double)__frcp_rn(__fadd_rn(1.0f, expf(-v[k].z)));
+            s_acc += w;
+            s_depth = fmaf(w, zj[k], s_depth);
+            // sigmoid = 1 / (1 + e^-x): MUFU exp (2 + |1.16 x| ulp, far inside the 1e-5 parity bar of the colour
+            // sums) and the correctly rounded reciprocal
+            s_r = fmaf(w, __frcp_rn(__fadd_rn(1.0f, __expf(-v[k].x))), s_r);
+            s_g = fmaf(w, __frcp_rn(__fadd_rn(1.0f, __expf(-v[k].y))), s_g);
+            s_b = fmaf(w, __frcp_rn(__fadd_rn(1.0f, __expf(-v[k].z))), s_b);
           }
         }
         // ---- Dex-NeRF first crossings.  A chunk can only add crossings if some sigma exceeds the
@@ -171,14 +173,17 @@ composite_kernel(const float4* __restrict__ rf, const float* __restrict__ z,
           }
         }
       }
-      s_acc = warp_sum_f64(s_acc);
-      s_depth = warp_sum_f64(s_depth);
-      s_r = warp_sum_f64(s_r);
-      s_g = warp_sum_f64(s_g);
-      s_b = warp_sum_f64(s_b);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s_acc += __shfl_xor_sync(0xffffffffu, s_acc, o);
+        s_depth += __shfl_xor_sync(0xffffffffu, s_depth, o);
+        s_r += __shfl_xor_sync(0xffffffffu, s_r, o);
+        s_g += __shfl_xor_sync(0xffffffffu, s_g, o);
+        s_b += __shfl_xor_sync(0xffffffffu, s_b, o);
+      }
       if (lane == 0) {
-        const float acc = (float)s_acc, depth = (float)s_depth;
-        float r = (float)s_r, g = (float)s_g, b = (float)s_b;
+        const float acc = s_acc, depth = s_depth;
+        float r = s_r, g = s_g, b = s_b;
         const float q = __fdiv_rn(depth, acc);
         const float m = (q != q) ? q : fmaxf(1e-10f, q);  // torch.max propagates NaN (acc == 0)
         if (white_background) {
