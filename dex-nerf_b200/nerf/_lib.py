@@ -133,6 +133,11 @@ def dev_f32(t, name, allow_none=False):
         raise ValueError("%s must be a CUDA tensor (this build has no CPU path)" % name)
     if t.dtype != torch.float32:
         raise ValueError("%s must be float32, got %s" % (name, t.dtype))
+    if t.device.index != torch.cuda.current_device():
+        # the C ABI launches on the CURRENT device and stream; a tensor of another GPU would be read through
+        # an invalid address there
+        raise ValueError("%s lives on %s but the current CUDA device is cuda:%d (use torch.cuda.set_device / "
+                         "torch.cuda.device)" % (name, t.device, torch.cuda.current_device()))
     return t.contiguous()
 
 
