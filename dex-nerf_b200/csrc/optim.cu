@@ -84,3 +84,63 @@ extern "C" DEXNERF_API int dexnerf_adam_step(float* params, const float* grads, 
   DN_CHECK_LAUNCH("adam_step");
   return 0;
 }
+
+// ---- nn.Linear parameters -> the flat program-layout buffer, one launch.
+// The drop-in training loop (torch.optim over nn.Parameters) changes every weight each iteration;
+// re-packing them with per-tensor transposes + cat costs ~100 small launches.  Here a device table of
+// (weight pointer, bias pointer) per layer is walked by one kernel: Wt[in][out] = W[out][in].
+namespace dexnerf {
+struct PackParamsTable {
+  int n_ops;
+  int in_dim[DEXNERF_MAX_OPS], out_dim[DEXNERF_MAX_OPS];
+  int64_t w_off[DEXNERF_MAX_OPS], b_off[DEXNERF_MAX_OPS];
+};
+
+__global__ void __launch_bounds__(256) pack_params_kernel(const float* const* __restrict__ ptrs,
+                                                          const __grid_constant__ PackParamsTable Q,
+                                                          float* __restrict__ flat) {
+  __shared__ float tile[32][33];
+  for (int op = blockIdx.y; op < Q.n_ops; op += gridDim.y) {
+    const float* W = ptrs[2 * op];
+    const float* b = ptrs[2 * op + 1];
+    const int fin = Q.in_dim[op], fout = Q.out_dim[op];
+    float* Wt = flat + Q.w_off[op];
+    // 32x32 tiles through shared memory: coalesced reads of W rows and writes of Wt rows
+    const int tiles_i = (fin + 31) / 32, tiles_o = (fout + 31) / 32;
+    for (int t = blockIdx.x; t < tiles_i * tiles_o; t += gridDim.x) {
+      const int ti = t % tiles_i, to = t / tiles_i;
+      const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8 threads
+      for (int r = ty; r < 32; r += 8) {
+        const int o = to * 32 + r, i = ti * 32 + tx;
+        tile[r][tx] = (o < fout && i < fin) ? W[(int64_t)o * fin + i] : 0.0f;
+      }
+      __syncthreads();
+      for (int r = ty; r < 32; r += 8) {
+        const int i = ti * 32 + r, o = to * 32 + tx;
+        if (i < fin && o < fout) Wt[(int64_t)i * fout + o] = tile[tx][r];
+      }
+      __syncthreads();
+    }
+    if (blockIdx.x == 0)
+      for (int o = threadIdx.x; o < fout; o += blockDim.x) flat[Q.b_off[op] + o] = b[o];
+  }
+}
+}  // namespace dexnerf
+
+extern "C" DEXNERF_API int dexnerf_pack_params(const dexnerf_mlp_program* prog, const void* ptr_table, float* flat,
+                                               void* stream) {
+  DN_REQUIRE(prog && ptr_table && flat, "pack_params: null pointer");
+  DN_REQUIRE(prog->n_ops >= 1 && prog->n_ops <= DEXNERF_MAX_OPS, "pack_params: bad op count %d", prog->n_ops);
+  dexnerf::PackParamsTable Q{};
+  Q.n_ops = prog->n_ops;
+  for (int i = 0; i < prog->n_ops; ++i) {
+    Q.in_dim[i] = prog->ops[i].src0_dim + prog->ops[i].src1_dim;
+    Q.out_dim[i] = prog->ops[i].out_dim;
+    Q.w_off[i] = prog->ops[i].w_off;
+    Q.b_off[i] = prog->ops[i].b_off;
+  }
+  dexnerf::pack_params_kernel<<<dim3(24, prog->n_ops), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float* const*>(ptr_table), Q, flat);
+  DN_CHECK_LAUNCH("pack_params");
+  return 0;
+}

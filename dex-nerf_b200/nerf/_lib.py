@@ -52,6 +52,7 @@ _SIGS = {
     "dexnerf_tc_query": (C.c_int, [C.POINTER(FlexibleSpec), _P, _P, _P, _P, _P, _L, _I, _P, _P, _I, _I, _P]),
     "dexnerf_volume_render_backward": (C.c_int, [_P, _P, _P, _P, _L, _I, _I, _P, _P, _P, _P, _P]),
     "dexnerf_mse_loss_grad": (C.c_int, [_P, _P, _L, _L, _P, _P, _P]),
+    "dexnerf_pack_params": (C.c_int, [C.POINTER(Program), _P, _P, _P]),
     "dexnerf_adam_step": (C.c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _L, _F, _P]),
     "dexnerf_depth_error_metrics": (C.c_int, [_P, _P, _P, _L, _I, _P, _P, _P, _P]),
     "dexnerf_tc_tape_bytes": (C.c_int64, [C.POINTER(FlexibleSpec), _L]),

@@ -69,24 +69,32 @@ class _ProgramModule(torch.nn.Module):
         return prog
 
     def packed_params(self):
-        """Flat fp32 device buffer [Wt(in,out) | bias] per layer, cached until a parameter changes."""
+        """Flat fp32 device buffer [Wt(in,out) | bias] per layer (every block 16-byte aligned), re-packed
+        when a parameter changes.  One kernel launch reads all nn.Linear tensors through a device pointer
+        table (rebuilt only when a parameter is re-allocated) and transposes them into a persistent buffer."""
         layers = self._layers()
         key = tuple((lin.weight.data_ptr(), lin.weight._version, lin.bias.data_ptr(), lin.bias._version)
                     for lin, *_ in layers)
         cache = self.__dict__.get("_packed_cache")
         if cache is None or cache[0] != key:
             with torch.no_grad():
-                parts = []
                 for lin, *_ in layers:
                     if not lin.weight.is_cuda:
                         raise ValueError("model parameters must live on a CUDA device (call .to('cuda'))")
-                    for blk in (lin.weight.detach().to(torch.float32).t().contiguous().reshape(-1),
-                                lin.bias.detach().to(torch.float32).reshape(-1)):
-                        parts.append(blk)
-                        pad = _align4(blk.numel()) - blk.numel()
-                        if pad:
-                            parts.append(blk.new_zeros(pad))
-                flat = torch.cat(parts).contiguous()
+                    if lin.weight.dtype != torch.float32 or not lin.weight.is_contiguous() or not lin.bias.is_contiguous():
+                        raise ValueError("model parameters must be contiguous float32 tensors")
+                prog = self.program()
+                ptrs = tuple(p for lin, *_ in layers for p in (lin.weight.data_ptr(), lin.bias.data_ptr()))
+                table = self.__dict__.get("_ptr_table")
+                if table is None or table[0] != ptrs:
+                    dev = layers[0][0].weight.device
+                    table = (ptrs, torch.tensor(ptrs, dtype=torch.int64).to(dev))
+                    self.__dict__["_ptr_table"] = table
+                    last = prog.ops[prog.n_ops - 1]
+                    self.__dict__["_flat_buf"] = torch.zeros(_align4(last.b_off + last.out_dim), dtype=torch.float32,
+                                                             device=dev)
+                flat = self.__dict__["_flat_buf"]
+                L.check(L.lib().dexnerf_pack_params(prog, L.ptr(table[1]), L.ptr(flat), L.stream_ptr()), "pack_params")
             cache = (key, flat)
             self.__dict__["_packed_cache"] = cache
         return cache[1]

@@ -192,6 +192,10 @@ DEXNERF_API int dexnerf_depth_error_metrics(const float* pred, const float* gt, 
  * `step` counts from 1; grads are multiplied by grad_scale first (1 / world for data parallel). */
 DEXNERF_API int dexnerf_mse_loss_grad(const float* pred, const float* target, int64_t count, int64_t total_count,
                           float* grad, float* loss_accum, void* stream);
+/* nn.Linear tensors -> the flat program-layout buffer in one launch.  ptr_table: DEVICE array of 2*n_ops
+ * pointers (weight (out,in) row-major, bias) in op order; flat: the buffer dexnerf_mlp_query / tc_pack read. */
+DEXNERF_API int dexnerf_pack_params(const dexnerf_mlp_program* prog /*host*/, const void* ptr_table, float* flat,
+                        void* stream);
 DEXNERF_API int dexnerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                       float lr, float beta1, float beta2, float eps, int64_t step, float grad_scale,
                       void* stream);
