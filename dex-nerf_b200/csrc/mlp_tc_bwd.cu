@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_tc_bwd_dw_kernel(const __gri
       const uint32_t g_lo = (((sbase + WSmem::g + st * kWStageG) >> 4) & 0x3FFF) | (lbo << 16);
       if (leader) {
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {        // 64 samples = 4 x K16; a K step = 2 core matrices = 256 B
+        for (int ks = 0; ks < ((P.variant & 4) ? 0 : 4); ++ks) {        // 64 samples = 4 x K16; a K step = 2 core matrices = 256 B
           for (int mb = 0; mb < I.n_mblk; ++mb)
             mma_ss(tmem_base + (uint32_t)(mb * 256),
                    desc_hi | (uint64_t)(a_lo + (uint32_t)(mb * 16384 + ks * 256) / 16),
@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_tc_bwd_dw_kernel(const __gri
       const int st = (int)(s % kWStages);
       const uint32_t ph = (uint32_t)((s / kWStages) & 1);
       mbar_wait(full(st), ph, 22);
-      if (mine) {
+      if (mine && !(P.variant & 2)) {
         const uint32_t gs = sbase + WSmem::g + st * kWStageG + fg * 1024;
 #pragma unroll 4
         for (int r = 0; r < 16; ++r) {

@@ -171,7 +171,8 @@ DEXNERF_API int dexnerf_tc_pack_bwd(const dexnerf_flexible_spec* spec, const dex
 /* d_rf (n,S,4) = dL/d(raw rgb, sigma) per sample -> grads: fp32 buffer in the program layout of
  * `params` (Wt[in][out] | bias per op), ACCUMULATED into (zero it first).  packed = forward blob,
  * packed_t = dexnerf_tc_pack_bwd blob.  what: bit 0 activation-gradient chain, bit 1
- * weight-gradient GEMM (3 = a full backward); variant: 0 (bring-up knob of the GEMM descriptors). */
+ * weight-gradient GEMM (3 = a full backward); variant: 0.  (Bring-up / experiment bits of the GEMM:
+ * 1 swaps the descriptor strides, 2 skips the bias column sums, 4 skips the MMAs - results invalid.) */
 DEXNERF_API int dexnerf_tc_backward(const dexnerf_flexible_spec* spec, const dexnerf_mlp_program* prog,
                         const void* packed, const void* packed_t, void* tape, const float* d_rf,
                         int64_t n, int S, float* grads, int what, int variant, void* stream);
