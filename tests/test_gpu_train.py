@@ -542,3 +542,43 @@ def test_trainer_checkpoint_round_trip_with_torch_adam(tmp_path):
     for a, b, c in zip(mc2.parameters(), mc.parameters(), mc3.parameters()):
         assert float((b - c).abs().max()) < 1e-6                     # trainer vs resumed trainer: same kernels
         assert float(((a - b).abs() > 2e-4).float().mean()) < 0.02   # vs torch Adam: entries with |grad| ~ eps aside
+
+
+def test_training_iteration_as_run_4x128_lego_checkpoint(golden):
+    """The network every reference script actually instantiates (4 x 128, the constructor defaults,
+    SURVEY.md section 8a-3) with the TRAINED pretrained/lego-lowres weights (a realistic, absorbing
+    sigma field; fixture lego_lowres.npz): one training iteration, 64 + 64 samples, white background as
+    in the blender configs, against the CPU oracle's autograd under the same bf16 operand contract."""
+    g = golden("lego_lowres")
+    mk = lambda: nerf.FlexibleNeRFModel(num_encoding_fn_xyz=10, num_encoding_fn_dir=4)
+    sds = [{k[len(p):]: t(g[k]) for k in g.files if k.startswith(p)} for p in ("coarse.", "fine.")]
+    mc, mf = mk(), mk()
+    mc.load_state_dict(sds[0])
+    mf.load_state_dict(sds[1])
+    mc, mf = mc.cuda(), mf.cuda()
+    H, W = map(int, g["HW"])
+    ro, rd = O.get_ray_bundle(H, W, None, t(g["T"]), t(g["K"]))
+    ro, rd = ro.reshape(-1, 3), rd.reshape(-1, 3)
+    n, nc, nf = ro.shape[0], 64, 64
+    gen = torch.Generator().manual_seed(12)
+    target = torch.rand(n, 3, generator=gen)
+    rng = dict(t_rand=torch.rand(n, nc, generator=gen), u=torch.rand(n, nf, generator=gen),
+               noise_coarse=0.2 * torch.randn(n, nc, generator=gen), noise_fine=0.2 * torch.randn(n, nc + nf, generator=gen))
+    opts = O.RenderOptions(near=2.0, far=6.0, num_coarse=nc, num_fine=nf, Lx=10, Ld=4, perturb=True, noise_std=0.2,
+                           white_background=True)
+    loss_o, _, _, gc, gf = O.train_loss_and_grads(sds[0], sds[1], ro, rd, target, opts, [], 4, 4, t_rand=rng["t_rand"],
+                                                  u=rng["u"], noise_coarse=rng["noise_coarse"], noise_fine=rng["noise_fine"],
+                                                  bf16=True)
+    ex, ed = nerf.get_embedding_function(10, True, True), nerf.get_embedding_function(4, True, True)
+    out = nerf.run_one_iter_of_nerf(H, W, 14.0, mc, mf, ro.cuda(), rd.cuda(), make_cfg(nc, nf, 2.0, 6.0, True), mode="train",
+                                    encode_position_fn=ex, encode_direction_fn=ed, m_thres_cand=[5.0, 50.0],
+                                    rng={k: v.cuda() for k, v in rng.items()})
+    assert float(out[5].mean()) > 0.15                     # the trained field absorbs
+    tg = target.cuda()
+    loss = torch.nn.functional.mse_loss(out[0], tg) + torch.nn.functional.mse_loss(out[3], tg)
+    loss.backward()
+    assert abs(float(loss.detach()) - float(loss_o)) < 2e-3
+    for m, grads in ((mc, gc), (mf, gf)):
+        num = sum(float(((p.grad.cpu() - grads[k]) ** 2).sum()) for k, p in m.named_parameters())
+        den = sum(float((grads[k] ** 2).sum()) for k, p in m.named_parameters())
+        assert (num / den) ** 0.5 < 4e-2, (num / den) ** 0.5
