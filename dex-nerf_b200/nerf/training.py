@@ -396,13 +396,21 @@ class Trainer:
         chunk = int(getattr(opt, "chunksize", n_total) or n_total)
         self.loss.zero_()
         self.grads.zero_()
-        for start in range(0, n_total, chunk):
+        starts = list(range(0, n_total, chunk))
+        pending = []
+        for start in starts:
             sl = slice(start, min(start + chunk, n_total))
             sub = {k: v[sl] for k, v in rng.items() if v is not None}
-            self._accumulate(ro[sl], rd[sl], tgt[sl], sub, n_total)
+            # the fine network's backward runs first: on the last chunk its gradients are final as soon as its
+            # weight-gradient GEMM is enqueued, so their all-reduce overlaps the coarse network's backward
+            after_fine = None
+            if self.world > 1 and start == starts[-1]:
+                after_fine = lambda: pending.append(self._allreduce_async(self._flat(self.grads, 1)))
+            self._accumulate(ro[sl], rd[sl], tgt[sl], sub, n_total, after_fine)
         if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=self.group)
+            pending.append(self._allreduce_async(self._flat(self.grads, 0)))
+            for work in pending:
+                work.wait()              # stream-level wait: the Adam launch below is ordered after both
         # Adam with the script's schedule: iteration i steps with the rate set after iteration i-1 (:283-289)
         lr = learning_rate(self.lr, self.iteration - 1, self.lr_decay, self.lr_decay_factor) if self.iteration else self.lr
         self.iteration += 1
@@ -413,7 +421,11 @@ class Trainer:
         self.loss[0:1] = self.loss[1:2] + self.loss[2:3]
         return self.loss
 
-    def _accumulate(self, ro, rd, tgt, rng, n_total):
+    def _allreduce_async(self, buf):
+        import torch.distributed as dist
+        return dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def _accumulate(self, ro, rd, tgt, rng, n_total, after_fine=None):
         """Forward + backward of one ray chunk; loss terms and gradients accumulate."""
         opt = self.cfg.nerf.train
         ro, rd, tgt = ro.contiguous(), rd.contiguous(), tgt.contiguous()
@@ -455,4 +467,6 @@ class Trainer:
             L.check(L.lib().dexnerf_mse_loss_grad(L.ptr(pred), L.ptr(tgt), pred.numel(), 3 * n_total, L.ptr(g),
                                                   L.ptr(self.loss[slot:slot + 1]), L.stream_ptr()), "mse_loss_grad")
         self._backward(1, rf_f, tape_f, z_fine, rd, noise_f, white, g_f)
+        if after_fine is not None:
+            after_fine()
         self._backward(0, rf_c, tape_c, z, rd, noise_c, white, g_c)
