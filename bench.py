@@ -68,8 +68,11 @@ def train_traffic():
 
 
 def camera():
-    from oracle.nerf_oracle import pose_spherical_world2cam
-    T = pose_spherical_world2cam(30.0, -30.0, 4.0)
+    """pose_spherical(30, -30, 4) of load_blender.py:33-38 in the fork's
+    world->cam convention (host-side helpers of the product package; the oracle is only touched by
+    the CPU legs below)."""
+    import nerf
+    T = nerf.world2cam_from_blender_pose(nerf.pose_spherical(30.0, -30.0, 4.0))
     K = torch.tensor([[FX, 0.0, W / 2.0], [0.0, FX, H / 2.0], [0.0, 0.0, 1.0]])
     return T, K
 
