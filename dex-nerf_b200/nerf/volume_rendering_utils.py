@@ -5,12 +5,26 @@ import torch
 from . import _lib as L
 
 
+_thr_cache = {}
+
+
 def _thresholds_tensor(m_thres_cand, device):
+    """Threshold candidates as a device tensor.  Cached per (values, device): building it from a Python
+    list is a pageable host->device copy, i.e. a stream synchronisation in every render call."""
     if m_thres_cand is None:
         # the reference iterates over it unconditionally (volume_rendering_utils.py:53)
         raise TypeError("'NoneType' object is not iterable")
-    vals = [float(m) for m in m_thres_cand]
-    return torch.tensor(vals, dtype=torch.float32, device=device) if vals else None, len(vals)
+    vals = tuple(float(m) for m in m_thres_cand)
+    if not vals:
+        return None, 0
+    key = (vals, str(device))
+    t = _thr_cache.get(key)
+    if t is None:
+        if len(_thr_cache) > 64:
+            _thr_cache.clear()
+        t = torch.tensor(vals, dtype=torch.float32, device=device)
+        _thr_cache[key] = t
+    return t, len(vals)
 
 
 def render_maps(radiance_field, depth_values, ray_directions, noise, white_background, thr, T,
