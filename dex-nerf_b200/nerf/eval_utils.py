@@ -76,8 +76,11 @@ def render_path(poses_w2c, height, width, intrinsic, model_coarse, model_fine, o
     row0, rows = row_block(height, rank, world)
     thr = list(m_thres_cand)
     frames, times = [], []
-    for i in range(len(poses_w2c)):
-        pose = torch.as_tensor(poses_w2c[i], dtype=torch.float32).cuda()
+    # one upload for the whole path: a pageable host->device copy per frame would synchronise the stream
+    # and expose the launch latency of every frame's first kernels
+    poses_dev = torch.stack([torch.as_tensor(p, dtype=torch.float32) for p in poses_w2c], 0).cuda()
+    for i in range(poses_dev.shape[0]):
+        pose = poses_dev[i]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         with torch.no_grad():
