@@ -20,3 +20,4 @@ from .training import Trainer, learning_rate, train_step
 from .eval_utils import (cast_to_image, compute_err_metric, dex_depth_error_metrics, pose_spherical, render_path,
                          render_poses_spherical, select_dex_threshold, world2cam_from_blender_pose)
 from .volume_rendering_utils import volume_render_radiance_field
+from . import cache_utils

@@ -83,3 +83,29 @@ def test_pose_spherical_and_render_path(golden):
         assert torch.equal(torch.cat([p[k] for p in parts], 0), frames[0][k])
     img = nerf.cast_to_image(frames[0][3])
     assert img.shape == (H, W, 3) and img.dtype == np.uint8
+
+
+def test_ray_cache_files_round_trip(tmp_path):
+    """The reference's ray-cache format (cache_dataset.py:104-135) written from this repo's ray generator and
+    consumed the way train_dexnerf_rgb.py:186-204 does."""
+    from nerf import cache_utils as CU
+    H, W = 12, 16
+    K = torch.tensor([[20.0, 0, 8.0], [0, 20.0, 6.0], [0, 0, 1]])
+    pose = nerf.world2cam_from_blender_pose(nerf.pose_spherical(40.0, -25.0, 4.0))
+    image = torch.rand(H, W, 3)
+    full = CU.train_cache_entry(H, W, 20.0, pose, K, image)                        # --sample-all
+    assert set(full) == {"height", "width", "focal_length", "ray_bundle", "target"}
+    assert full["ray_bundle"].shape == (2, H, W, 3) and not full["ray_bundle"].is_cuda
+    ro, rd = nerf.get_ray_bundle(H, W, None, pose.cuda(), K.cuda())
+    assert torch.equal(full["ray_bundle"][0], ro.cpu()) and torch.equal(full["ray_bundle"][1], rd.cpu())
+    sub = CU.train_cache_entry(H, W, 20.0, pose, K, image, num_random_rays=50, rng=np.random.RandomState(3))
+    assert sub["ray_bundle"].shape == (2, 50, 3) and sub["target"].shape == (50, 3)
+    val = CU.val_cache_entry(H, W, 20.0, pose, K, image)
+    assert set(val) == {"height", "width", "focal_length", "ray_origins", "ray_directions", "target"}
+    path = tmp_path / "0000.data"
+    CU.save_cache_entry(full, path)
+    back = CU.load_cache_entry(path)
+    o, d, tg = CU.training_rays_from_cache(back, 32, rng=np.random.RandomState(1))
+    assert o.shape == (32, 3) and o.is_cuda and tg.shape == (32, 3)
+    sel = torch.from_numpy(np.random.RandomState(1).choice(H * W, size=(32,), replace=False))
+    assert torch.equal(d.cpu(), rd.reshape(-1, 3).cpu()[sel]) and torch.equal(tg.cpu(), image.reshape(-1, 3)[sel])
