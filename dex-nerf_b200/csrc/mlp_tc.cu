@@ -9,22 +9,28 @@
 //                 128 out-features x 64 in-features) from L2 into a 9-slot shared-memory ring with
 //                 cp.async.bulk (TMA bulk copy, mbarrier complete_tx); each chunk is consumed by
 //                 both tiles before the slot is recycled.
-//   warp 1        MMA issuer: one thread issues tcgen05.mma (M=128, N=128, K=16).  Hidden
-//                 activations are the A operand READ FROM TENSOR MEMORY (bf16, 2 per column);
-//                 the positional encodings (layer 1, skip layer, view-direction layer) are A
-//                 operands read from shared memory.  A 256-wide layer runs as two N=128 passes
-//                 into a 128-column fp32 accumulator, so a tile needs 128 (A) + 128 (D) TMEM
-//                 columns and two tiles fill the 512 columns.
+//   warp 1        MMA issuer: one elected thread issues tcgen05.mma (M=128, N=128, K=16), the
+//                 passes of the two tiles alternating strictly.  Hidden activations are the A
+//                 operand READ FROM TENSOR MEMORY (bf16, 2 per column); the positional encodings
+//                 (layer 1, skip layer, view-direction layer) are A operands read from shared
+//                 memory.  A 256-wide layer runs as two N=128 passes into a 128-column fp32
+//                 accumulator, so a tile needs 128 (A) + 128 (D) TMEM columns and two tiles fill
+//                 the 512 columns.
 //   warp 2        TMEM allocator.
-//   warps 4-11    epilogue, 4 warps per tile, one thread per sample row: tcgen05.ld the accumulator,
-//                 + bias, ReLU, pack to bf16 and tcgen05.st it back as the next layer's A operand
-//                 (first-pass results wait in registers until the layer's second pass has
-//                 finished reading the old A).  fc_alpha and fc_rgb (1 and 3 outputs) are fp32
-//                 dot products on the CUDA cores inside the epilogue; the only HBM write is the
-//                 final (r,g,b,sigma) float4 per sample.
-//   warps 12-15   encoders: one thread per sample row of the NEXT tile pair computes
-//                 pts = ro + rd*z and the sin/cos encodings in registers and writes them as
-//                 bf16 UMMA core matrices into shared memory.
+//   warp 3        scout: walks the pass sequence one step ahead of the issuer and does all the
+//                 waiting for it (the tile's epilogue, the weight chunks, the encodings), then
+//                 releases the pass with ONE arrival on ready[tile].
+//   warps 4-19    epilogue, 8 warps per tile (two per 32-lane quarter, 64 columns each), one thread
+//                 per sample row: tcgen05.ld the accumulator, + bias, ReLU, pack to bf16 and
+//                 tcgen05.st it back as the next layer's A operand (first-pass results wait in
+//                 registers until the layer's second pass has finished reading the old A).
+//                 fc_alpha and fc_rgb (1 and 3 outputs) are fp32 dot products on the CUDA cores
+//                 inside the epilogue; the only HBM write of the inference variant is the final
+//                 (r,g,b,sigma) float4 per sample.  The training variant (kTape) also writes every
+//                 layer's bf16 operand image and ReLU bits - the tape the backward consumes.
+//   warps 20-23   encoders: one thread per sample row of the NEXT tile pair computes
+//                 pts = ro + rd*z and the sin/cos encodings in registers (Cody-Waite reduction +
+//                 MUFU) and writes them as bf16 UMMA core matrices into shared memory.
 //
 // Weight-image layout (no swizzle, K-major "interleaved" canonical layout): an operand tile is a
 // grid of 8-row x 16-byte core matrices, each 128 contiguous bytes; byte offset of element
