@@ -95,3 +95,54 @@ def test_argument_validation():
     with pytest.raises(TypeError):
         nerf.volume_render_radiance_field(torch.zeros(1, 2, 4, device="cuda"), torch.zeros(1, 2, device="cuda"),
                                           torch.ones(1, 3, device="cuda"), m_thres_cand=None)
+
+
+def test_random_shape_sweep_against_oracle():
+    """Seeded sweep over ray / sample / threshold counts that straddle every kernel variant (1, 2 or 4 samples per
+    lane in the compositing kernel, partial chunks, merge-by-rank vs sorting network): forward maps, Dex depths,
+    resampled depths and the compositing backward against the oracle."""
+    import random
+    from nerf import _lib as L, training
+    rnd = random.Random(2026)
+    for case in range(24):
+        n = rnd.choice([1, 2, 31, 33, 64, 257])
+        S = rnd.choice([1, 2, 7, 31, 32, 33, 64, 65, 100, 192, 255, 256, 257, 384, 500])
+        T = rnd.choice([0, 1, 3, 20, 33, 64])
+        white = rnd.random() < 0.5
+        g = torch.Generator().manual_seed(case)
+        rf = torch.randn(n, S, 4, generator=g)
+        rf[..., 3] = 25 * torch.randn(n, S, generator=g)
+        z = torch.sort(0.5 + 5 * torch.rand(n, S, generator=g), dim=-1).values
+        rd = torch.randn(n, 3, generator=g)
+        noise = 0.3 * torch.randn(n, S, generator=g) if rnd.random() < 0.5 else None
+        thr = sorted(rnd.sample(range(1, 120), T))
+        rnd.shuffle(thr)                                            # unsorted candidates are ranked in the kernel
+        thr = [float(x) for x in thr]
+        ref = O.volume_render_radiance_field(rf, z, rd, 0.0, white, thr, noise=noise)
+        got = nerf.volume_render_radiance_field(rf.cuda(), z.cuda(), rd.cuda(), 0.0, white, thr,
+                                                noise=None if noise is None else noise.cuda())
+        tag = (case, n, S, T, white)
+        for a, b in zip(got[:5], ref[:5]):
+            assert torch.allclose(a.cpu(), b, rtol=3e-5, atol=3e-6, equal_nan=True), tag
+        if T:
+            assert torch.equal(torch.stack(got[5:]).cpu(), torch.stack(ref[5:])), tag
+        # backward
+        grgb, gd, ga = torch.randn(n, 3, generator=g), torch.randn(n, generator=g), torch.randn(n, generator=g)
+        rfo = rf.clone().requires_grad_(True)
+        r2 = O.volume_render_radiance_field(rfo, z, rd, 0.0, white, [], noise=noise)
+        ((r2[0] * grgb).sum() + (r2[4] * gd).sum() + (r2[2] * ga).sum()).backward()
+        bw = training.volume_render_backward(rf.cuda(), z.cuda(), rd.cuda(), None if noise is None else noise.cuda(), white,
+                                             grgb.cuda(), gd.cuda(), ga.cuda()).cpu()
+        scale = float(rfo.grad.abs().max()) + 1e-12
+        assert float((bw - rfo.grad).abs().max()) <= 5e-5 * scale, tag
+        # resampling (needs at least 3 coarse depths)
+        if S >= 3:
+            Nf = rnd.choice([1, 5, 32, 64, 100, 128, 256])
+            w = torch.rand(n, S, generator=g) ** 6
+            for u in (None, torch.rand(n, Nf, generator=g)):
+                mids = 0.5 * (z[:, 1:] + z[:, :-1])
+                want = O.merge_fine(z, O.sample_pdf(mids, w[:, 1:-1], Nf, det=(u is None), u=u))
+                out = torch.empty(n, S + Nf, device="cuda")
+                zc, wc, uc = z.cuda(), w.cuda(), None if u is None else u.cuda()
+                L.check(L.lib().dexnerf_resample_merge(L.ptr(zc), L.ptr(wc), n, S, Nf, L.ptr(uc), L.ptr(out), L.stream_ptr()), "rm")
+                assert torch.equal(out.cpu(), want), tag + (Nf, u is None)
