@@ -202,12 +202,26 @@ def test_sample_pdf_bit_exact_vs_oracle(n, B, Nf):
 
 
 @pytest.mark.parametrize("n,Nc,Nf,det", [(4000, 64, 128, True), (4000, 64, 128, False), (1500, 128, 256, False),
-                                         (300, 16, 24, False), (77, 3, 1, True), (50, 40, 100, False)])
+                                         (1500, 128, 256, True), (2000, 64, 64, True), (2000, 64, 64, False),
+                                         (1000, 128, 128, True), (1000, 128, 128, False),
+                                         (300, 16, 24, False), (77, 3, 1, True), (50, 40, 100, False),
+                                         (50, 40, 100, True), (33, 64, 127, True)])
 def test_resample_merge_bit_exact(n, Nc, Nf, det):
+    """The template-sized kernel (64+64, 64+128, 128+128, 128+256) and the generic one, sorted-u merge and
+    random-u network; rows with all-zero weights, one-hot weights, repeated coarse depths (ties) and
+    weights that put every sample into one bin."""
     from nerf import _lib as L
     g = torch.Generator().manual_seed(Nc + Nf)
     z = torch.sort(2 + 4 * torch.rand(n, Nc, generator=g), dim=-1).values
     w = torch.rand(n, Nc, generator=g) ** 6
+    if n >= 8 and Nc >= 8:
+        w[0] = 0.0
+        w[1] = 0.0; w[1, Nc // 2] = 1.0
+        w[2] = 0.0; w[2, 1] = 1.0
+        w[3] = 0.0; w[3, Nc - 2] = 1.0
+        z[4, 3:9] = z[4, 3]                     # ties among the coarse depths
+        z[5] = 2.0                              # a degenerate ray: all depths equal
+        w[6] = 1.0
     u = None if det else torch.rand(n, Nf, generator=g)
     mids = 0.5 * (z[:, 1:] + z[:, :-1])
     ref = O.merge_fine(z, O.sample_pdf(mids, w[:, 1:-1], Nf, det=det, u=u))
