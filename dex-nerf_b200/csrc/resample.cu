@@ -209,19 +209,18 @@ __global__ void __launch_bounds__(256) resample_merge_kernel(const float* __rest
 // branch-free search covers it exactly.  ~4x fewer instructions per ray than the generic kernel.
 template <int kLog2>
 __device__ __forceinline__ int count_le_full(const float* s, float key) {   // over 2^kLog2 - 1 entries
-  int pos = 0;
+  const float* p = s;
 #pragma unroll
   for (int b = kLog2 - 1; b >= 0; --b)
-    if (s[pos + (1 << b) - 1] <= key) pos += 1 << b;
-  return pos;
+    if (p[(1 << b) - 1] <= key) p += 1 << b;
+  return (int)(p - s);
 }
-template <int kLog2>
-__device__ __forceinline__ int count_lt_full(const float* s, float key) {
-  int pos = 0;
-#pragma unroll
-  for (int b = kLog2 - 1; b >= 0; --b)
-    if (s[pos + (1 << b) - 1] < key) pos += 1 << b;
-  return pos;
+
+// x / y, correctly rounded, for x >= 0: a zero numerator would send the whole warp through the
+// division's slow path (~20 instructions); the quotient is 0 anyway.
+__device__ __forceinline__ float fdiv_rn_nonneg(float x, float y) {
+  const float q = __fdiv_rn(x == 0.0f ? 1.0f : x, y);
+  return x == 0.0f ? 0.0f : q;
 }
 
 template <int N> struct Log2Of { static constexpr int value = 1 + Log2Of<N / 2>::value; };
@@ -233,7 +232,7 @@ __global__ void __launch_bounds__(256) resample_merge_fixed_kernel(const float* 
                                                                    int64_t n, const float* __restrict__ u,
                                                                    float* __restrict__ z_fine) {
   constexpr int KC = NC / 32, KF = NF / 32, B = NC - 1, ST = NC + NF;
-  constexpr int LC = Log2Of<NC>::value, LF = Log2Of<NF>::value;
+  constexpr int LC = Log2Of<NC>::value;
   constexpr int P = 1 << (Log2Of<ST - 1>::value + 1);        // power of two >= ST (bitonic fallback)
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
@@ -242,6 +241,8 @@ __global__ void __launch_bounds__(256) resample_merge_fixed_kernel(const float* 
   float* s_cdf = s_merge + ST;                               // NC (B used)
   float* s_bins = s_cdf + NC;                                // NC (B used)
   float* s_samp = s_sort + NC;
+  // torch.linspace(0, 1, NF) (common.cuh linspace_at) with the step hoisted out of the ray loop
+  const float lin_step = __fdiv_rn(1.0f, (float)(NF - 1));
   for (int64_t ray = (int64_t)blockIdx.x * wpc + warp; ray < n; ray += (int64_t)gridDim.x * wpc) {
     const float* z_row = zc + ray * NC;
     const float* w_row = weights + ray * NC + 1;             // weights[..., 1:-1]
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(256) resample_merge_fixed_kernel(const float* 
     // the pdf is transposed through shared memory to KC consecutive entries per lane and ONE warp
     // scan of the lane totals gives every prefix.
 #pragma unroll
-    for (int k = 0; k < KC; ++k) s_merge[lane + 32 * k] = __fdiv_rn(wk[k], total);
+    for (int k = 0; k < KC; ++k) s_merge[lane + 32 * k] = fdiv_rn_nonneg(wk[k], total);
     __syncwarp();
     double pre[KC];
     {
@@ -292,12 +293,18 @@ __global__ void __launch_bounds__(256) resample_merge_fixed_kernel(const float* 
       }
     }
     __syncwarp();
-    // inverse-cdf samples, each with its rank among the coarse depths (see the generic kernel)
+    // Inverse-cdf samples, each with its rank among the coarse depths.  A sample drawn with index ind
+    // lies in [mid(z[ind-1], z[ind]), mid(z[ind], z[ind+1])] (t is in [0, 1] and every step rounds
+    // monotonically), so at least `ind` sorted coarse depths are <= it and normally ind or ind + 1; the
+    // loop only runs on when rounding pushed the sample an ulp past a run of tied depths.
     float vk[KF];
+    int rk[KF];
 #pragma unroll
     for (int k = 0; k < KF; ++k) {
       const int s = lane + 32 * k;
-      const float uu = u ? u[ray * NF + s] : linspace_at(0.0f, 1.0f, NF, s);
+      const float uu = u ? u[ray * NF + s]
+                         : (s < NF / 2 ? __fmaf_rn(lin_step, (float)s, 0.0f)
+                                       : __fmaf_rn(-lin_step, (float)(NF - 1 - s), 1.0f));
       const int ind = count_le_full<LC>(s_cdf, uu);           // searchsorted(cdf, u, side="right"), in [0, B]
       const int below = ind - 1 < 0 ? 0 : ind - 1;
       const int above = ind > B - 1 ? B - 1 : ind;
@@ -305,13 +312,15 @@ __global__ void __launch_bounds__(256) resample_merge_fixed_kernel(const float* 
       const float bb = s_bins[below], ba = s_bins[above];
       float denom = __fsub_rn(ca, cb);
       if (denom < 1e-5f) denom = 1.0f;
-      const float t = __fdiv_rn(__fsub_rn(uu, cb), denom);
+      const float num = __fsub_rn(uu, cb);
+      const float t = (num >= 0.0f) ? fdiv_rn_nonneg(num, denom) : __fdiv_rn(num, denom);
       const float v = __fadd_rn(bb, __fmul_rn(t, __fsub_rn(ba, bb)));
       vk[k] = v;
       s_samp[s] = v;
-      int r = ind;
+      int r = ind;                                            // <= B = NC - 1: s_sort[r] is a coarse depth
+      r += (s_sort[r] <= v) ? 1 : 0;
       while (r < NC && s_sort[r] <= v) ++r;
-      while (r > 0 && s_sort[r - 1] > v) --r;
+      rk[k] = r;
       s_merge[s + r] = v;                                     // speculative: used if everything is sorted
     }
 #pragma unroll
@@ -347,12 +356,41 @@ __global__ void __launch_bounds__(256) resample_merge_fixed_kernel(const float* 
       __syncwarp();
       continue;
     }
-    // coarse depths: position = index + number of samples strictly below (ties: coarse first)
+    // Coarse depths: position = index + number of samples strictly below (ties: coarse first).  No
+    // search either: the sample ranks r_j are non-decreasing, so the coarse depths i in
+    // [r_{j-1}, r_j) have exactly j samples below them.  Sample j places them (0.5 per sample on
+    // average; gaps longer than two - empty stretches of a peaked pdf - are done by the whole warp);
+    // the depths before r_0 and from r_{NF-1} on are placed by index.
+    const int r_first = __shfl_sync(0xffffffffu, rk[0], 0);
+    const int r_last = __shfl_sync(0xffffffffu, rk[KF - 1], 31);
 #pragma unroll
     for (int k = 0; k < KC; ++k) {
-      const float v = zk[k];
-      const int cnt = (s_samp[NF - 1] < v) ? NF : count_lt_full<LF>(s_samp, v);
-      s_merge[lane + 32 * k + cnt] = v;
+      const int i = lane + 32 * k;
+      if (i < r_first) s_merge[i] = zk[k];
+      if (i >= r_last) s_merge[i + NF] = zk[k];
+    }
+#pragma unroll
+    for (int k = 0; k < KF; ++k) {
+      const int j = lane + 32 * k;
+      int r_prev = __shfl_up_sync(0xffffffffu, rk[k], 1);
+      if (k > 0) {
+        const int last_prev = __shfl_sync(0xffffffffu, rk[k > 0 ? k - 1 : 0], 31);
+        if (lane == 0) r_prev = last_prev;
+      } else if (lane == 0) {
+        r_prev = rk[0];                                       // j = 0: the head is placed above
+      }
+      const int gap = rk[k] - r_prev;
+      if (gap >= 1) s_merge[r_prev + j] = s_sort[r_prev];
+      if (gap >= 2) s_merge[r_prev + 1 + j] = s_sort[r_prev + 1];
+      unsigned big = __ballot_sync(0xffffffffu, gap > 2);
+      while (big) {                                           // warp-uniform
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const int lo = __shfl_sync(0xffffffffu, r_prev, src) + 2;
+        const int hi = __shfl_sync(0xffffffffu, rk[k], src);
+        const int jj = src + 32 * k;
+        for (int i = lo + lane; i < hi; i += 32) s_merge[i + jj] = s_sort[i];
+      }
     }
     __syncwarp();
 #pragma unroll
