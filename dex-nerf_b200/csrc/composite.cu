@@ -37,7 +37,18 @@ __device__ __forceinline__ double warp_inclusive_product(double v, int lane) {
   return v;
 }
 
-template <int kSpl>
+// sigmoid(x) = 1 / (1 + e^-x) on the MUFU unit: ex2.approx (2 + |1.16 x| ulp) and rcp.approx (1 ulp) - a
+// few 1e-7 relative on a colour in [0, 1], far inside the 1e-5 parity bar of the colour sums.  (The
+// correctly rounded reciprocal cost 10 instructions per colour; compositing is bound by instruction issue.)
+__device__ __forceinline__ float sigmoid_mufu(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fadd_rn(1.0f, __expf(-x))));
+  return r;
+}
+
+// kSpl = consecutive samples per lane and chunk; kFull = S is a multiple of 32 * kSpl (no bounds
+// predicates: true for the shipped 64 / 128 / 192 / 384 samples per ray).
+template <int kSpl, bool kFull>
 __global__ void __launch_bounds__(kCompositeWarps * 32)
 composite_kernel(const float4* __restrict__ rf, const float* __restrict__ z,
                  const float* __restrict__ rd, const float* __restrict__ noise, int64_t n, int S,
@@ -52,11 +63,12 @@ composite_kernel(const float4* __restrict__ rf, const float* __restrict__ z,
   // exceeds all smaller ones, so "how many thresholds does sigma exceed" (a 6-step binary search)
   // replaces T compares, and the first crossings of a whole run of thresholds come out of ONE
   // ballot (see the level loop below).
-  float* s_thr = smem;                          // T ascending (padded to kMaxThresholds)
-  float* s_out = smem + kMaxThresholds;         // (6 + 2T) * 32
+  float* s_thr = smem;                          // T ascending, then +inf up to 2 * kMaxThresholds
+  float* s_out = smem + 2 * kMaxThresholds;     // (6 + 2T) * 32
   __shared__ int s_orig[kMaxThresholds];        // sorted rank -> caller's threshold index
   __shared__ int s_found[kCompositeWarps][kMaxThresholds];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t = T + threadIdx.x; t < 2 * kMaxThresholds; t += blockDim.x) s_thr[t] = __int_as_float(0x7f800000);
   for (int t = threadIdx.x; t < T; t += blockDim.x) {
     const float v = thresholds[t];
     int rank = 0;
@@ -71,13 +83,20 @@ composite_kernel(const float4* __restrict__ rf, const float* __restrict__ z,
 
   for (int64_t base = (int64_t)blockIdx.x * kRaysPerCta; base < n;
        base += (int64_t)gridDim.x * kRaysPerCta) {
+    // |rd| of the warp's rays, one per lane (the fp64 square root is ~40 instructions: once, not per ray)
+    float norm_l = 0.0f;
+    {
+      const int64_t ray = base + warp * kRaysPerWarp + lane;
+      if (lane < kRaysPerWarp && ray < n) {
+        const float dx = rd[ray * 3], dy = rd[ray * 3 + 1], dz = rd[ray * 3 + 2];
+        norm_l = (float)sqrt((double)dx * (double)dx + (double)dy * (double)dy + (double)dz * (double)dz);
+      }
+    }
     for (int rr = 0; rr < kRaysPerWarp; ++rr) {
       const int slot = warp * kRaysPerWarp + rr;
       const int64_t ray = base + slot;
       if (ray >= n) break;  // warp-uniform
-      const float dx = rd[ray * 3], dy = rd[ray * 3 + 1], dz = rd[ray * 3 + 2];
-      const float norm =
-          (float)sqrt((double)dx * (double)dx + (double)dy * (double)dy + (double)dz * (double)dz);
+      const float norm = __shfl_sync(0xffffffffu, norm_l, rr);
       const float4* rf_row = rf + ray * S;
       const float* z_row = z + ray * S;
       double carry = 1.0;
@@ -96,7 +115,7 @@ composite_kernel(const float4* __restrict__ rf, const float* __restrict__ z,
         float z_next = 0.f;            // depth of the sample after this lane's last one
 #pragma unroll
         for (int k = 0; k < kSpl; ++k) {
-          valid[k] = j0 + k < S;
+          valid[k] = kFull || (j0 + k < S);
           v[k] = valid[k] ? rf_row[j0 + k] : make_float4(0.f, 0.f, 0.f, 0.f);
           zj[k] = valid[k] ? z_row[j0 + k] : 0.f;
         }
@@ -131,11 +150,9 @@ composite_kernel(const float4* __restrict__ rf, const float* __restrict__ z,
             if (weights_out) weights_out[ray * S + j0 + k] = w;
             s_acc += w;
             s_depth = fmaf(w, zj[k], s_depth);
-            // sigmoid = 1 / (1 + e^-x): MUFU exp (2 + |1.16 x| ulp, far inside the 1e-5 parity bar of the colour
-            // sums) and the correctly rounded reciprocal
-            s_r = fmaf(w, __frcp_rn(__fadd_rn(1.0f, __expf(-v[k].x))), s_r);
-            s_g = fmaf(w, __frcp_rn(__fadd_rn(1.0f, __expf(-v[k].y))), s_g);
-            s_b = fmaf(w, __frcp_rn(__fadd_rn(1.0f, __expf(-v[k].z))), s_b);
+            s_r = fmaf(w, sigmoid_mufu(v[k].x), s_r);
+            s_g = fmaf(w, sigmoid_mufu(v[k].y), s_g);
+            s_b = fmaf(w, sigmoid_mufu(v[k].z), s_b);
           }
         }
         // ---- Dex-NeRF first crossings.  A chunk can only add crossings if some sigma exceeds the
@@ -146,30 +163,39 @@ composite_kernel(const float4* __restrict__ rf, const float* __restrict__ z,
 #pragma unroll
           for (int k = 0; k < kSpl; ++k) smax = fmaxf(smax, valid[k] ? sigma[k] : 0.0f);
           if (__any_sync(0xffffffffu, smax > s_thr[level])) {   // warp-uniform
-            int cnt[kSpl];
+            // cnt = thresholds a sample exceeds (branch-free search of the ascending table, padded with
+            // +inf to 127 entries).  Threshold rank q is first crossed by the first sample, in (lane, k)
+            // order, with cnt > q - i.e. by the samples that raise the running maximum of cnt.  The
+            // exclusive running maximum is a lane-local pass plus one warp max-scan, and every record
+            // sample then writes the ranks it is the first to cross: no serial loop over the thresholds.
+            int cnt[kSpl], before[kSpl];
+            int run = 0;
 #pragma unroll
             for (int k = 0; k < kSpl; ++k) {
-              int lo = 0, hi = T;
               const float sg = valid[k] ? sigma[k] : 0.0f;
-              while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (s_thr[mid] < sg) lo = mid + 1; else hi = mid;
-              }
-              cnt[k] = lo;
-            }
-            while (true) {
-              int first = kSpl, reach = 0;      // this lane's first sample that closes an open threshold
+              const float* p = s_thr;
 #pragma unroll
-              for (int k = kSpl - 1; k >= 0; --k)
-                if (cnt[k] > level) { first = k; reach = cnt[k]; }
-              const unsigned hit = __ballot_sync(0xffffffffu, first < kSpl);
-              if (hit == 0u) break;
-              const int src = __ffs(hit) - 1;
-              const int kk = __shfl_sync(0xffffffffu, first, src);
-              const int reached = __shfl_sync(0xffffffffu, reach, src);
-              for (int q = level + lane; q < reached; q += 32) s_found[warp][q] = c0 + src * kSpl + kk;
-              level = reached;
+              for (int b = 6; b >= 0; --b)
+                if (p[(1 << b) - 1] < sg) p += 1 << b;
+              cnt[k] = (int)(p - s_thr);
+              before[k] = run;
+              run = max(run, cnt[k]);
             }
+            int incl = run;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+              const int o = __shfl_up_sync(0xffffffffu, incl, d);
+              if (lane >= d) incl = max(incl, o);
+            }
+            int excl = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) excl = 0;
+            excl = max(excl, level);
+#pragma unroll
+            for (int k = 0; k < kSpl; ++k) {
+              const int from = max(excl, before[k]);
+              for (int q = from; q < cnt[k]; ++q) s_found[warp][q] = c0 + lane * kSpl + k;
+            }
+            level = max(level, __shfl_sync(0xffffffffu, incl, 31));
           }
         }
       }
@@ -365,19 +391,24 @@ extern "C" DEXNERF_API int dexnerf_volume_render(const float* rf, const float* z
   DN_REQUIRE(T >= 0 && T <= kMaxThresholds, "volume_render: at most %d thresholds", kMaxThresholds);
   DN_REQUIRE(T == 0 || thresholds, "volume_render: thresholds is null");
   DN_REQUIRE((reinterpret_cast<uintptr_t>(rf) & 15) == 0, "volume_render: rf must be 16-byte aligned");
-  const size_t smem = sizeof(float) * (kMaxThresholds + (6 + 2 * (size_t)T) * 32);
+  const size_t smem = sizeof(float) * (2 * kMaxThresholds + (6 + 2 * (size_t)T) * 32);
   int64_t blocks = ceil_div64(n, kRaysPerCta);
   const int64_t cap = (int64_t)kNumSMs * 8 * 4;
   if (blocks > cap) blocks = cap;
-  // samples per lane: 1 up to 32 samples, 2 up to 256 (C2: 64 and 192 fill every lane), 4 beyond (C5: 384)
+  // consecutive samples per lane: a ray of 64 / 128 / 192 samples is ONE chunk (2 / 4 / 6 per lane: one
+  // transmittance scan and one threshold vote per ray), 384 (C5) is two chunks of 6; other sizes take the
+  // predicated 2-per-lane form (4 beyond 256 samples)
   auto launch = [&](auto kernel) {
     kernel<<<(int)blocks, kCompositeWarps * 32, smem, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(rf), z, rd, noise, n, S, white_background, thresholds, T, rgb,
         disp, acc, weights, depth, dex_depth, dex_index);
   };
-  if (S <= 32) launch(composite_kernel<1>);
-  else if (S <= 256) launch(composite_kernel<2>);
-  else launch(composite_kernel<4>);
+  if (S <= 32) launch(composite_kernel<1, false>);
+  else if (S % 192 == 0) launch(composite_kernel<6, true>);
+  else if (S % 128 == 0) launch(composite_kernel<4, true>);
+  else if (S % 64 == 0) launch(composite_kernel<2, true>);
+  else if (S <= 256) launch(composite_kernel<2, false>);
+  else launch(composite_kernel<4, false>);
   DN_CHECK_LAUNCH("volume_render");
   return 0;
 }
