@@ -49,7 +49,7 @@ __device__ __forceinline__ float sigmoid_mufu(float x) {
 // kSpl = consecutive samples per lane and chunk; kFull = S is a multiple of 32 * kSpl (no bounds
 // predicates: true for the shipped 64 / 128 / 192 / 384 samples per ray).
 template <int kSpl, bool kFull>
-__global__ void __launch_bounds__(kCompositeWarps * 32)
+__global__ void __launch_bounds__(kCompositeWarps * 32, kSpl >= 6 ? 4 : 1)
 composite_kernel(const float4* __restrict__ rf, const float* __restrict__ z,
                  const float* __restrict__ rd, const float* __restrict__ noise, int64_t n, int S,
                  int white_background, const float* __restrict__ thresholds, int T,
