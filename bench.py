@@ -36,6 +36,42 @@ THRESHOLDS = [float(m) for m in range(5, 105, 5)]
 FLOP_PER_EVAL = 2 * 593408                        # SURVEY.md section 8(d), unpadded
 FLOP_PER_RAY = (NC + NC + NF) * FLOP_PER_EVAL     # 303 824 896
 CPU_SAMPLE_RAYS = 16384
+MODEL_ARGS = (8, 256, 4, 10, 4)                   # FlexibleNeRFModel(num_layers, hidden, skip, Lx, Ld)
+METRIC = "rays/sec render (64+128 samples, 8x256 MLP)"
+WORKLOAD = ("C2: full-paper NeRF render 800x800, 64 coarse + 128 fine samples, two 8x256 skip-4 "
+            "FlexibleNeRFModels (L=10/4, viewdirs), T=20 Dex thresholds, validation mode, random-init")
+SCENE = "c2"
+
+# Secondary render scenes (parity-test configurations of BASELINE.json, measured
+# with the same step and the same JSON line so that their HBM-side kernels are on record too):
+#   c3  Dex-NeRF sigma-threshold depth render at the messytable size: 270x480, 64+64 samples, 8x128 skip-3
+#       (config/messytable-obj.yml:36-53), near 0.3 / far 4, T=20
+#   c5  IR variant at 1280x720 with 128+256 samples (train_nerf_ir.py; config/messytable-obj-edward.yml),
+#       8x256 skip-4, near 0.3 / far 4, T=20 - the configuration that stresses sample_pdf and compositing
+C3_ALPHA_SCALE = 1000.0
+SCENES = {
+    "c3": dict(H=270, W=480, NC=64, NF=64, NEAR=0.3, FAR=4.0, FX=1386.4 / 4, MODEL_ARGS=(8, 128, 3, 10, 4),
+               METRIC="rays/sec render (64+64 samples, 8x128 MLP, Dex depth)",
+               WORKLOAD="C3: Dex-NeRF sigma-threshold depth render 270x480, 64+64 samples, two 8x128 skip-3 "
+                        "FlexibleNeRFModels (L=10/4, viewdirs), T=20 Dex thresholds, near 0.3 / far 4, "
+                        "validation mode, random-init with fc_alpha x1000 (sigma spans the thresholds)"),
+    "c5": dict(H=720, W=1280, NC=128, NF=256, NEAR=0.3, FAR=4.0, FX=1386.4, MODEL_ARGS=(8, 256, 4, 10, 4),
+               METRIC="rays/sec render (128+256 samples, 8x256 MLP)",
+               WORKLOAD="C5: Dex-NeRF IR variant render 1280x720, 128 coarse + 256 fine samples, two 8x256 skip-4 "
+                        "FlexibleNeRFModels (L=10/4, viewdirs), T=20 Dex thresholds, near 0.3 / far 4, "
+                        "validation mode, random-init"),
+}
+
+
+def apply_scene(name):
+    """Point the module-level workload constants at a secondary scene."""
+    global H, W, NC, NF, NEAR, FAR, FX, MODEL_ARGS, METRIC, WORKLOAD, SCENE, FLOP_PER_EVAL, FLOP_PER_RAY
+    sc = SCENES[name]
+    H, W, NC, NF, NEAR, FAR, FX = sc["H"], sc["W"], sc["NC"], sc["NF"], sc["NEAR"], sc["FAR"], sc["FX"]
+    MODEL_ARGS, METRIC, WORKLOAD, SCENE = sc["MODEL_ARGS"], sc["METRIC"], sc["WORKLOAD"], name
+    mc, _ = state_dicts()
+    FLOP_PER_EVAL = 2 * sum(p.numel() for k, p in mc.named_parameters() if k.endswith("weight"))
+    FLOP_PER_RAY = (NC + NC + NF) * FLOP_PER_EVAL
 
 
 def peaks():
@@ -89,8 +125,15 @@ def state_dicts():
     the reference scripts would construct them (coarse first, then fine)."""
     import nerf
     torch.manual_seed(42)
-    mc = nerf.FlexibleNeRFModel(8, 256, 4, 10, 4)
-    mf = nerf.FlexibleNeRFModel(8, 256, 4, 10, 4)
+    mc = nerf.FlexibleNeRFModel(*MODEL_ARGS)
+    mf = nerf.FlexibleNeRFModel(*MODEL_ARGS)
+    if SCENE == "c3":
+        # SURVEY.md section 8d C3 (ii): a random-init field is nearly empty; scale fc_alpha so that sigma
+        # spans the 5...100 threshold range and the first-crossing logic has crossings to find
+        with torch.no_grad():
+            for m in (mc, mf):
+                m.fc_alpha.weight.mul_(C3_ALPHA_SCALE)
+                m.fc_alpha.bias.mul_(C3_ALPHA_SCALE)
     return mc, mf
 
 
@@ -149,7 +192,8 @@ def cpu_oracle_rays_per_s(n_rays=CPU_SAMPLE_RAYS, reps=1):
     sdc = {k: v.detach() for k, v in mc.state_dict().items()}
     sdf = {k: v.detach() for k, v in mf.state_dict().items()}
     opts = O.RenderOptions(near=NEAR, far=FAR, num_coarse=NC, num_fine=NF, Lx=10, Ld=4, chunksize=65536)
-    fc, ff = (lambda x: O.flexible_forward(sdc, x)), (lambda x: O.flexible_forward(sdf, x))
+    fc = lambda x: O.flexible_forward(sdc, x, skip_connect_every=MODEL_ARGS[2])   # noqa: E731
+    ff = lambda x: O.flexible_forward(sdf, x, skip_connect_every=MODEL_ARGS[2])   # noqa: E731
     with torch.no_grad():
         O.render_rays(ro[start:start + 128], rd[start:start + 128], fc, ff, opts, THRESHOLDS)   # warm-up
         times = []
@@ -172,9 +216,10 @@ def run_reference(args):
             T.append(CPU_SAMPLE_RAYS / v)
     ms = 1e3 * sum(T) / len(T)
     value = CPU_SAMPLE_RAYS / (ms / 1e3)
-    sample = "%d rays of the 800x800 C2 frame (centre rows) per step, full 64+128 / 8x256 pipeline" % CPU_SAMPLE_RAYS
+    sample = "%d rays of the %dx%d %s frame (centre rows) per step, full %d+%d pipeline" % (
+        CPU_SAMPLE_RAYS, W, H, SCENE.upper(), NC, NF)
     print(json.dumps({
-        "impl": "reference", "metric": "rays/sec render (64+128 samples, 8x256 MLP)", "value": value,
+        "impl": "reference", "metric": METRIC, "value": value,
         "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.gpus),
@@ -348,8 +393,7 @@ def run_train(args, dist, rank, world, dev, quiet=False):
 
 
 def workload_config(n_gpus):
-    return {"workload": "C2: full-paper NeRF render 800x800, 64 coarse + 128 fine samples, two 8x256 skip-4 "
-                        "FlexibleNeRFModels (L=10/4, viewdirs), T=20 Dex thresholds, validation mode, random-init",
+    return {"workload": WORKLOAD,
             "rays_per_step": H * W, "rows_per_gpu": H // n_gpus, "parallelism": "rows%d" % n_gpus,
             "l2": "per-step intermediates (z_fine + radiance field, >2 GB/GPU at N=1) exceed the 126 MB L2; "
                   "a 256 MB buffer is also rewritten between steps"}
@@ -366,9 +410,13 @@ def main():
     ap.add_argument("--no-train", action="store_true", help="skip the short C4 training measurement of the default run")
     ap.add_argument("--train-api", default="trainer", choices=["trainer", "autograd"],
                     help="C4: nerf.Trainer (default) or the reference-style autograd loop")
-    ap.add_argument("--workload", default="render", choices=["render", "train"],
-                    help="render: BASELINE config 2 (the headline metric); train: BASELINE config 4")
+    ap.add_argument("--workload", default="render", choices=["render", "train", "c3", "c5"],
+                    help="render: BASELINE config 2 (the headline metric); train: BASELINE config 4; "
+                         "c3 / c5: the Dex-depth and IR render configurations (secondary lines)")
     args = ap.parse_args()
+    if args.workload in SCENES:
+        apply_scene(args.workload)
+        args.no_train = True
     if args.impl == "reference":
         return run_reference(args)
 
@@ -490,7 +538,7 @@ def main():
         achieved = flop_launch / (kern_ms * 1e-3) / 1e12
         peak = pk["tf_sustained"]
         line = {
-            "metric": "rays/sec render (64+128 samples, 8x256 MLP)", "value": rays / (ms_dev * 1e-3),
+            "metric": METRIC, "value": rays / (ms_dev * 1e-3),
             "unit": "rays/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16" if kern_name == "mlp_tc" else "f32", "data": "synthetic",
@@ -501,7 +549,7 @@ def main():
             "roofline": {"bound": "tensor", "kernel": kern_name + " (fine pass, %d samples/ray)" % (NC + NF),
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "peak_source": pk["source"] + " bf16 sustained",
-                         "traffic": ncu_traffic("mlp_tc_fine_c2", fine[0][1]),
+                         "traffic": ncu_traffic("mlp_tc_fine_c2", fine[0][1]) if SCENE == "c2" else None,
                          "kernel_ms": kern_ms, "mlp_share_of_step": all_mlp_ms / ms_dev,
                          "flop_per_launch": flop_launch},
             "clocks": clocks,
@@ -523,8 +571,8 @@ def main():
         if not args.no_cpu_baseline:
             v, cores = cpu_oracle_rays_per_s()
             line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
-                                    "sample": "%d rays of the same C2 frame (centre rows), 1 repetition after "
-                                              "a 128-ray warm-up" % CPU_SAMPLE_RAYS}
+                                    "sample": "%d rays of the same %s frame (centre rows), 1 repetition after "
+                                              "a 128-ray warm-up" % (CPU_SAMPLE_RAYS, SCENE.upper())}
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
