@@ -238,6 +238,37 @@ def _load(model, g, prefix):
     return model.cuda()
 
 
+@pytest.mark.parametrize("n,Nc,Nf", [(640_000, 64, 128), (921_600, 128, 256)])
+def test_resample_merge_full_size_properties(n, Nc, Nf):
+    """BASELINE sizes (a C2 / C5 frame of rays in one launch): properties that do not need the oracle -
+    sorted rows, every coarse depth present (the merge is a permutation of cat(coarse, samples)), samples
+    inside the coarse range, the same bits on a second run - plus a bit-exact comparison of 512 rays spread
+    over the launch against the oracle."""
+    from nerf import _lib as L
+    g = torch.Generator(device="cuda").manual_seed(Nc)
+    z = torch.sort(0.3 + 3.7 * torch.rand(n, Nc, device="cuda", generator=g), dim=-1).values
+    w = torch.rand(n, Nc, device="cuda", generator=g) ** 6
+    w[::7] *= 1e-3
+    w[::1001] = 0.0
+
+    def run():
+        out = torch.empty(n, Nc + Nf, device="cuda")
+        L.check(L.lib().dexnerf_resample_merge(L.ptr(z), L.ptr(w), n, Nc, Nf, L.ptr(None), L.ptr(out), L.stream_ptr()), "rm")
+        return out
+    out = run()
+    assert torch.all(out[:, 1:] >= out[:, :-1])
+    assert torch.all(out[:, 0] == z[:, 0]) and torch.all(out[:, -1] == z[:, -1])
+    # each coarse depth is found in its row: searchsorted position holds an equal value
+    pos = torch.searchsorted(out, z)
+    assert torch.equal(out.gather(1, pos.clamp_(max=Nc + Nf - 1)), z)
+    assert torch.equal(out, run())
+    pick = torch.linspace(0, n - 1, 512).long()
+    zc, wc = z[pick.cuda()].cpu(), w[pick.cuda()].cpu()
+    mids = 0.5 * (zc[:, 1:] + zc[:, :-1])
+    ref = O.merge_fine(zc, O.sample_pdf(mids, wc[:, 1:-1], Nf, det=True))
+    assert torch.equal(out[pick.cuda()].cpu(), ref)
+
+
 def test_models_forward_vs_reference_golden(golden):
     """fp32 CUDA-core MLP against the reference's own forward on the reference's own init
     (same seed -> same weights, checked by digest in test_host_logic.py)."""
