@@ -76,9 +76,53 @@ __global__ void depth_metrics_finish_kernel(const double* __restrict__ partial, 
   if (threadIdx.x == 0 && best) *best = best_t;
 }
 
+// Depth-error colour image of the validation block (nerf/train_utils.py:31-70 gen_error_colormap_depth +
+// depth_error_img): error = |gt - est| / abs_thres on the masked pixels, coloured by eleven buckets
+// [0, 1e-5), [1e-5, 2000/2^10), [2000/2^10, 2000/2^9), ... [2000/2^2, inf); unmasked pixels black; the
+// colour legend in the top-left corner (10 rows, 20 columns per bucket).  One thread per pixel, 12 B written.
+__constant__ float kErrEdges[12] = {0.0f, 0.00001f, 2000.0f / 1024, 2000.0f / 512, 2000.0f / 256, 2000.0f / 128,
+                                    2000.0f / 64, 2000.0f / 32, 2000.0f / 16, 2000.0f / 8, 2000.0f / 4, 0.0f};
+__constant__ float kErrRgb[11][3] = {{0, 0, 0},       {49, 54, 149},   {69, 117, 180}, {116, 173, 209},
+                                     {171, 217, 233}, {224, 243, 248}, {254, 224, 144}, {253, 174, 97},
+                                     {244, 109, 67},  {215, 48, 39},   {165, 0, 38}};
+
+__global__ void __launch_bounds__(256)
+depth_error_image_kernel(const float* __restrict__ est, const float* __restrict__ gt, const uint8_t* __restrict__ mask,
+                         int H, int W, float abs_thres, float* __restrict__ out) {
+  const int64_t n = (int64_t)H * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / W), c = (int)(i - (int64_t)r * W);
+    int bucket = -1;
+    if (r < 10 && c < 11 * 20) {
+      bucket = c / 20;                                   // the legend overwrites the image
+    } else if (mask[i]) {
+      const float e = __fdiv_rn(fabsf(__fsub_rn(gt[i], est[i])), abs_thres);
+      for (int b = 0; b < 11; ++b) {
+        const bool below_hi = (b == 10) ? (e < __int_as_float(0x7f800000)) : (e < kErrEdges[b + 1]);
+        if (e >= kErrEdges[b] && below_hi) bucket = b;
+      }
+    }
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch)
+      out[i * 3 + ch] = bucket < 0 ? 0.0f : __fdiv_rn(kErrRgb[bucket][ch], 255.0f);
+  }
+}
+
 }  // namespace dexnerf
 
 using namespace dexnerf;
+
+extern "C" DEXNERF_API int dexnerf_depth_error_image(const float* est, const float* gt, const uint8_t* mask, int H,
+                                                     int W, float abs_thres, float* out, void* stream) {
+  if (H <= 0 || W <= 0) return 0;
+  DN_REQUIRE(est && gt && mask && out, "depth_error_image: null pointer");
+  int64_t blocks = ceil_div64((int64_t)H * W, 256);
+  const int64_t cap = (int64_t)kNumSMs * 8;
+  if (blocks > cap) blocks = cap;
+  depth_error_image_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(est, gt, mask, H, W, abs_thres, out);
+  DN_CHECK_LAUNCH("depth_error_image");
+  return 0;
+}
 
 extern "C" DEXNERF_API int dexnerf_depth_error_metrics(const float* pred, const float* gt, const uint8_t* mask,
                                                        int64_t n, int T, float* out, int32_t* best,

@@ -17,7 +17,8 @@ from .train_utils import (get_precision, predict_and_render_radiance, run_networ
                           sample_pdf, set_precision)
 from .sharding import allreduce_gradients, gather_rows, row_block
 from .training import Trainer, learning_rate, train_step
-from .eval_utils import (cast_to_image, compute_err_metric, dex_depth_error_metrics, pose_spherical, render_path,
+from .datasets import load_blender_data, load_llff_data, load_messytable_data
+from .eval_utils import (cast_to_image, compute_err_metric, depth_error_img, dex_depth_error_metrics, pose_spherical, render_path,
                          render_poses_spherical, select_dex_threshold, world2cam_from_blender_pose)
 from .volume_rendering_utils import volume_render_radiance_field
 from . import cache_utils

@@ -55,6 +55,7 @@ _SIGS = {
     "dexnerf_pack_params": (C.c_int, [C.POINTER(Program), _P, _P, _P]),
     "dexnerf_adam_step": (C.c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _L, _F, _P]),
     "dexnerf_depth_error_metrics": (C.c_int, [_P, _P, _P, _L, _I, _P, _P, _P, _P]),
+    "dexnerf_depth_error_image": (C.c_int, [_P, _P, _P, _I, _I, _F, _P, _P]),
     "dexnerf_tc_tape_bytes": (C.c_int64, [C.POINTER(FlexibleSpec), _L]),
     "dexnerf_tc_tape_layout": (C.c_int, [C.POINTER(FlexibleSpec), _L, C.POINTER(C.c_int64)]),
     "dexnerf_tc_query_train": (C.c_int, [C.POINTER(FlexibleSpec), _P, _P, _P, _P, _P, _L, _I, _P, _P, _P]),

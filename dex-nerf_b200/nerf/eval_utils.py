@@ -141,6 +141,23 @@ def compute_err_metric(depth_gt, depth_pred, mask):
     return {"depth_abs_err": v[0], "depth_err2": v[1], "depth_err4": v[2], "depth_err8": v[3]}
 
 
+def depth_error_img(D_est_tensor, D_gt_tensor, mask, abs_thres=1.0, dilate_radius=1):
+    """train_utils.py:45-70: the colour-coded depth error image of the validation block
+    (train_dexnerf_rgb.py:415), same signature and return value - a numpy (H, W, 3) float32 image of batch
+    entry 0 with the colour legend in the top-left corner - computed by one kernel on the device
+    (csrc/metrics.cu); `dilate_radius` is unused, as in the reference."""
+    if D_est_tensor.dim() != 3 or D_gt_tensor.shape != D_est_tensor.shape or mask.shape != D_est_tensor.shape:
+        raise ValueError("depth_error_img expects (B, H, W) depth maps and a (B, H, W) mask")
+    est = L.dev_f32(D_est_tensor.detach()[0], "D_est_tensor")
+    gt = L.dev_f32(D_gt_tensor.detach()[0].to(torch.float32), "D_gt_tensor")
+    m = mask.detach()[0].to(device=est.device, dtype=torch.uint8).contiguous()
+    H, W = est.shape
+    out = torch.empty((H, W, 3), dtype=torch.float32, device=est.device)
+    L.check(L.lib().dexnerf_depth_error_image(L.ptr(est), L.ptr(gt), L.ptr(m), H, W, float(abs_thres), L.ptr(out),
+                                              L.stream_ptr()), "depth_error_img")
+    return out.cpu().numpy()
+
+
 def select_dex_threshold(depth_planes, depth_gt, mask=None):
     """The selection loop of train_dexnerf_rgb.py:393-404: the first threshold whose mean absolute
     depth error (mm) is the smallest and below 1000.  Returns (index, err dict, metrics (T, 4))

@@ -185,6 +185,12 @@ DEXNERF_API int dexnerf_tc_backward(const dexnerf_flexible_spec* spec, const dex
 DEXNERF_API int dexnerf_depth_error_metrics(const float* pred, const float* gt, const uint8_t* mask, int64_t n,
                                 int T, float* out, int32_t* best, void* workspace, void* stream);
 
+/* ---- depth_error_img (nerf/train_utils.py:31-70): the colour-coded depth error image of the validation
+ * block (train_dexnerf_rgb.py:415).  est, gt: (H, W) floats of ONE image (the reference returns image 0 of
+ * its batch), mask (H, W) uint8, out (H, W, 3). */
+DEXNERF_API int dexnerf_depth_error_image(const float* est, const float* gt, const uint8_t* mask, int H, int W,
+                              float abs_thres, float* out, void* stream);
+
 /* ---- training-loop glue on the flat parameter buffer (train_dexnerf_rgb.py:264-289).
  * dexnerf_mse_loss_grad: *loss_accum += sum((pred - target)^2) / total_count over `count` floats
  * (img2mse, nerf_helpers.py:9-10; total_count = count unless the batch is processed in chunks) and

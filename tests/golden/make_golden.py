@@ -5,7 +5,7 @@ Run in the authoring container only (the GPU box has no /root/reference):
     python tests/golden/make_golden.py
 
 It imports the unmodified reference package `nerf` from /root/reference/nerf-pytorch with the three
-import shims in `_shims/` (torchsearchsorted -> torch.searchsorted, empty imageio / matplotlib),
+import shims in `_shims/` (torchsearchsorted -> torch.searchsorted, imageio.imread through PIL, empty matplotlib),
 runs the hot-path functions of SURVEY.md section 8(a) on seeded CPU inputs and stores inputs and
 outputs as small .npz files.  The two 8-layer forwards are the one-line REPAIRS documented in
 SURVEY.md section 8(a-3), applied as subclasses of the reference classes so that parameter
@@ -426,6 +426,48 @@ def gen_next_rows():
     print("next_rows.npz best", int(out["metric_best"]), errs[int(out["metric_best"])])
 
 
+def gen_datasets():
+    """the three dataset loaders of the reference on the tiny synthetic
+    datasets of tests/dataset_fixture.py (files are rebuilt byte-identically by the test)."""
+    import tempfile
+    sys.path.insert(0, os.path.dirname(HERE))
+    import dataset_fixture as DF
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        b = DF.build_blender(os.path.join(tmp, "blender"))
+        for tag, kw in (("full", dict()), ("half", dict(half_res=True, testskip=2)), ("debug", dict(debug=True))):
+            imgs, poses, render_poses, hwf, i_split = ref.load_blender_data(b, **kw)
+            out.update({f"bl_{tag}_imgs": npy(imgs), f"bl_{tag}_poses": npy(poses), f"bl_{tag}_render": npy(render_poses),
+                        f"bl_{tag}_hwf": np.asarray(hwf, dtype=np.float64),
+                        f"bl_{tag}_split": np.concatenate([np.asarray([len(x) for x in i_split])] + list(i_split))})
+        m = DF.build_messytable(os.path.join(tmp, "messy"))
+        for tag, kw in (("ir", dict(half_res=True)), ("full", dict(half_res=False)),
+                        ("rgb", dict(half_res=True, imgname="rgb.png", is_real_rgb=True)), ("debug", dict(debug=True))):
+            imgs, poses, render_poses, hwf, i_split, intr, depths = ref.load_messytable_data(m, **kw)
+            out.update({f"mt_{tag}_imgs": npy(imgs), f"mt_{tag}_poses": npy(poses), f"mt_{tag}_render": npy(render_poses),
+                        f"mt_{tag}_hwf": np.asarray(hwf, dtype=np.float64), f"mt_{tag}_intr": npy(intr),
+                        f"mt_{tag}_depths": npy(depths),
+                        f"mt_{tag}_split": np.concatenate([np.asarray([len(x) for x in i_split])] + list(i_split))})
+        ll = DF.build_llff(os.path.join(tmp, "llff"))
+        for tag, kw in (("std", dict(factor=8)), ("sph", dict(factor=8, spherify=True)),
+                        ("zflat", dict(factor=8, path_zflat=True, recenter=False))):
+            if tag == "zflat":
+                continue   # the reference divides N_views by 2 into a float and np.linspace then raises (load_llff.py:319,330)
+            images, poses, bds, render_poses, i_test = ref.load_llff_data(ll, **kw)
+            out.update({f"ll_{tag}_imgs": npy(images), f"ll_{tag}_poses": npy(poses), f"ll_{tag}_bds": npy(bds),
+                        f"ll_{tag}_render": npy(render_poses), f"ll_{tag}_itest": np.asarray(i_test)})
+    # depth_error_img (train_utils.py:45-70) on a seeded pair of depth maps
+    g = torch.Generator().manual_seed(11)
+    gt = 300 + 3000 * torch.rand(1, 40, 260, generator=g)
+    est = gt + torch.randn(1, 40, 260, generator=g) * torch.tensor([0.1, 1.0, 10.0, 100.0]).repeat(65)[None, None, :]
+    mask = torch.rand(1, 40, 260, generator=g) > 0.2
+    out["dei_gt"], out["dei_est"], out["dei_mask"] = npy(gt), npy(est), npy(mask)
+    out["dei_img"] = ref.depth_error_img(est, gt, mask)
+    out["dei_img_thr"] = ref.depth_error_img(est, gt, mask, abs_thres=2.5)
+    np.savez_compressed(os.path.join(HERE, "datasets.npz"), **out)
+    print("datasets.npz", len(out), "arrays")
+
+
 def gen_train_grads():
     """One TRAINING iteration of the reference (train_dexnerf_rgb.py:246-278): train-mode
     run_one_iter_of_nerf with the four RNG draws replayed, loss = mse(rgb_coarse, target) +
@@ -506,3 +548,4 @@ if __name__ == "__main__":
     gen_tiny()
     gen_train_grads()
     gen_next_rows()
+    gen_datasets()
