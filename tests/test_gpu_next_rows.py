@@ -109,3 +109,150 @@ def test_ray_cache_files_round_trip(tmp_path):
     assert o.shape == (32, 3) and o.is_cuda and tg.shape == (32, 3)
     sel = torch.from_numpy(np.random.RandomState(1).choice(H * W, size=(32,), replace=False))
     assert torch.equal(d.cpu(), rd.reshape(-1, 3).cpu()[sel]) and torch.equal(tg.cpu(), image.reshape(-1, 3)[sel])
+
+
+SCRIPT_YAML = """
+experiment: {id: flow, logdir: logs, randomseed: 42, train_iters: 40, validate_every: 20, save_every: 20, print_every: 10}
+dataset: {type: messytable, basedir: X, half_res: True, testskip: 1, no_ndc: True, near: 0.3, far: 4}
+models:
+  coarse: {type: FlexibleNeRFModel, num_layers: 8, hidden_size: 128, skip_connect_every: 3, include_input_xyz: True,
+           log_sampling_xyz: True, num_encoding_fn_xyz: 10, use_viewdirs: True, include_input_dir: True,
+           num_encoding_fn_dir: 4, log_sampling_dir: True}
+  fine: {type: FlexibleNeRFModel, num_layers: 8, hidden_size: 128, skip_connect_every: 3, include_input_xyz: True,
+         log_sampling_xyz: True, num_encoding_fn_xyz: 10, use_viewdirs: True, include_input_dir: True,
+         num_encoding_fn_dir: 4, log_sampling_dir: True}
+optimizer: {type: Adam, lr: 5.0E-3}
+scheduler: {lr_decay: 250, lr_decay_factor: 0.1}
+nerf:
+  use_viewdirs: True
+  encode_position_fn: positional_encoding
+  encode_direction_fn: positional_encoding
+  train: {num_random_rays: 256, chunksize: 16384, perturb: True, num_coarse: 64, num_fine: 64, white_background: False,
+          radiance_field_noise_std: 0.2, lindisp: False}
+  validation: {chunksize: 16384, perturb: False, num_coarse: 64, num_fine: 64, white_background: False,
+               radiance_field_noise_std: 0., lindisp: False}
+"""
+
+
+def test_training_script_flow_on_a_messytable_dataset(tmp_path):
+    """The statements of train_dexnerf_rgb.py, in its order and with its names, on a synthetic dataset in the
+    messytable format: YAML -> CfgNode (:36-40), load_messytable_data (:61-67), encoders and models built by
+    name with the five keyword arguments the script forwards (:106-140 - hence 4x128 networks whatever the
+    YAML says), torch.optim.Adam (:142-148), per iteration get_ray_bundle / meshgrid_xy / np.random.choice ray
+    selection / run_one_iter_of_nerf(mode="train") / two mse losses / backward / step / exponential learning
+    rate (:221-289), then the validation block (:317-428): full-image render under no_grad, the Dex threshold
+    selection against the ground-truth depth, the error colour image, and the checkpoint dict (:442-457)."""
+    import yaml
+    import dataset_fixture as DF
+    from nerf import (CfgNode, compute_err_metric, depth_error_img, get_embedding_function, get_ray_bundle, img2mse,
+                      load_messytable_data, meshgrid_xy, models, mse2psnr, run_one_iter_of_nerf)
+    cfg = CfgNode(yaml.safe_load(SCRIPT_YAML))
+    cfg.dataset.basedir = DF.build_messytable(str(tmp_path / "messy"))
+    images, poses, render_poses, hwf, i_split, intrinsics, depths = load_messytable_data(
+        cfg.dataset.basedir, half_res=cfg.dataset.half_res, testskip=cfg.dataset.testskip)
+    i_train, i_val, i_test = i_split
+    H, W, focal = int(hwf[0]), int(hwf[1]), hwf[2]
+    # the fixture's intrinsics describe a 1920x1080 sensor; point them at the 32x18 images it really holds
+    intrinsics[:, 0, 0] = intrinsics[:, 1, 1] = 40.0
+    intrinsics[:, 0, 2], intrinsics[:, 1, 2] = W / 2, H / 2
+    np.random.seed(cfg.experiment.randomseed)
+    torch.manual_seed(cfg.experiment.randomseed)
+    device = "cuda"
+    encode_position_fn = get_embedding_function(num_encoding_functions=cfg.models.coarse.num_encoding_fn_xyz,
+                                                include_input=cfg.models.coarse.include_input_xyz,
+                                                log_sampling=cfg.models.coarse.log_sampling_xyz)
+    encode_direction_fn = get_embedding_function(num_encoding_functions=cfg.models.coarse.num_encoding_fn_dir,
+                                                 include_input=cfg.models.coarse.include_input_dir,
+                                                 log_sampling=cfg.models.coarse.log_sampling_dir)
+    nets = []
+    for which in ("coarse", "fine"):
+        assert hasattr(cfg.models, which)
+        c = getattr(cfg.models, which)
+        nets.append(getattr(models, c.type)(num_encoding_fn_xyz=c.num_encoding_fn_xyz, num_encoding_fn_dir=c.num_encoding_fn_dir,
+                                            include_input_xyz=c.include_input_xyz, include_input_dir=c.include_input_dir,
+                                            use_viewdirs=c.use_viewdirs).to(device))
+    model_coarse, model_fine = nets
+    assert model_coarse.layer1.weight.shape == (128, 63) and len(model_coarse.layers_xyz) == 3    # the as-run 4x128
+    optimizer = getattr(torch.optim, cfg.optimizer.type)(list(model_coarse.parameters()) + list(model_fine.parameters()),
+                                                         lr=cfg.optimizer.lr)
+    m_thres_cand = np.arange(5, 105, 5)
+    # targets a NeRF can fit: the training view rendered by a frozen teacher pair (the fixture's pixels are noise)
+    torch.manual_seed(7)
+    teacher = [models.FlexibleNeRFModel(num_encoding_fn_xyz=10, num_encoding_fn_dir=4).to(device) for _ in range(2)]
+    with torch.no_grad():
+        for tm in teacher:
+            tm.fc_alpha.weight.mul_(300.0)
+    losses = []
+    for i in range(cfg.experiment.train_iters):
+        model_coarse.train(); model_fine.train()
+        img_idx = np.random.choice(i_train)
+        pose_target = poses[img_idx, :, :].to(device)
+        intrinsic_target = intrinsics[img_idx, :, :].to(device)
+        ray_origins, ray_directions = get_ray_bundle(H, W, focal, pose_target, intrinsic_target)
+        if i == 0:
+            with torch.no_grad():
+                img_target = run_one_iter_of_nerf(H, W, intrinsic_target[0, 0], teacher[0], teacher[1], ray_origins,
+                                                  ray_directions, cfg, mode="validation",
+                                                  encode_position_fn=encode_position_fn,
+                                                  encode_direction_fn=encode_direction_fn, m_thres_cand=m_thres_cand)[3]
+            assert img_target.shape == (H, W, 3)
+        coords = torch.stack(meshgrid_xy(torch.arange(H).to(device), torch.arange(W).to(device)), dim=-1).reshape((-1, 2))
+        select_inds = np.random.choice(coords.shape[0], size=(cfg.nerf.train.num_random_rays), replace=False)
+        select_inds = coords[select_inds]
+        ro = ray_origins[select_inds[:, 0], select_inds[:, 1], :]
+        rd = ray_directions[select_inds[:, 0], select_inds[:, 1], :]
+        target_s = img_target[select_inds[:, 0], select_inds[:, 1]]
+        nerf_out = run_one_iter_of_nerf(H, W, intrinsic_target[0, 0], model_coarse, model_fine, ro, rd, cfg, mode="train",
+                                        encode_position_fn=encode_position_fn, encode_direction_fn=encode_direction_fn,
+                                        m_thres_cand=m_thres_cand)
+        assert len(nerf_out) == 6 + len(m_thres_cand)
+        rgb_coarse, rgb_fine = nerf_out[0], nerf_out[3]
+        loss = torch.nn.functional.mse_loss(rgb_coarse[..., :3], target_s[..., :3]) + \
+            torch.nn.functional.mse_loss(rgb_fine[..., :3], target_s[..., :3])
+        loss.backward()
+        psnr = mse2psnr(loss.item())
+        optimizer.step()
+        optimizer.zero_grad()
+        lr_new = cfg.optimizer.lr * (cfg.scheduler.lr_decay_factor ** (i / (cfg.scheduler.lr_decay * 1000)))
+        for param_group in optimizer.param_groups:
+            param_group["lr"] = lr_new
+        losses.append(loss.item())
+    assert np.isfinite(losses).all() and np.isfinite(psnr)
+    assert np.mean(losses[-5:]) < 0.5 * np.mean(losses[:5]), (losses[:5], losses[-5:])
+
+    # ---- validation block
+    model_coarse.eval(); model_fine.eval()
+    with torch.no_grad():
+        img_idx = np.random.choice(i_val)
+        pose_target = poses[img_idx, :, :].to(device)
+        intrinsic_target = intrinsics[img_idx, :, :].to(device)
+        depth_target = depths[img_idx].to(device)
+        ray_origins, ray_directions = get_ray_bundle(H, W, focal, pose_target, intrinsic_target)
+        out = run_one_iter_of_nerf(H, W, intrinsic_target[0, 0], model_coarse, model_fine, ray_origins, ray_directions, cfg,
+                                   mode="validation", encode_position_fn=encode_position_fn,
+                                   encode_direction_fn=encode_direction_fn, m_thres_cand=m_thres_cand)
+        rgb_fine, depth_fine_dex = out[3], list(out[6:])
+        assert rgb_fine.shape == (H, W, 3) and all(d.shape == (H, W) for d in depth_fine_dex)
+        val_loss = img2mse(rgb_fine[..., :3], images[img_idx].to(device)[..., :3])
+        assert np.isfinite(mse2psnr(val_loss.item()))
+        img_ground_mask = (depth_target > 0) & (depth_target < 1.25)
+        min_err, min_abs_err, min_abs_depth, min_cand = None, 1000.0, None, 0
+        for cand in range(m_thres_cand.shape[0]):
+            err = compute_err_metric(depth_target, depth_fine_dex[cand], img_ground_mask)
+            if err["depth_abs_err"] < min_abs_err:
+                min_abs_err, min_err, min_abs_depth, min_cand = err["depth_abs_err"], err, depth_fine_dex[cand], m_thres_cand[cand]
+        assert min_err is not None and set(min_err) == {"depth_abs_err", "depth_err2", "depth_err4", "depth_err8"}
+        # the one-launch selection of this repo finds the same candidate
+        idx, err2, _ = nerf.select_dex_threshold(torch.stack(depth_fine_dex).reshape(len(depth_fine_dex), -1),
+                                                 depth_target.reshape(-1))
+        assert m_thres_cand[idx] == min_cand and abs(err2["depth_abs_err"] - min_abs_err) < 1e-3
+        err_img = depth_error_img(min_abs_depth.unsqueeze(0) * 1000, depth_target.unsqueeze(0) * 1000,
+                                  img_ground_mask.unsqueeze(0))
+        assert err_img.shape == (H, W, 3)
+    checkpoint_dict = {"iter": i, "model_coarse_state_dict": model_coarse.state_dict(),
+                       "model_fine_state_dict": model_fine.state_dict(), "optimizer_state_dict": optimizer.state_dict(),
+                       "loss": loss, "psnr": psnr}
+    torch.save(checkpoint_dict, str(tmp_path / "checkpoint.ckpt"))
+    back = torch.load(str(tmp_path / "checkpoint.ckpt"), weights_only=False)
+    model_fine.load_state_dict(back["model_fine_state_dict"])
+    assert isinstance(cfg.dump(), str)
