@@ -192,10 +192,9 @@ __device__ __forceinline__ void epilogue_pass(uint32_t d_tmem, uint32_t a_park, 
 #pragma unroll
     for (int i = 0; i < 16; i += 4) {
       const float4 b4 = lds128(bias + (uint32_t)((c * 16 + i) * 4));
-      const float x0 = __uint_as_float(v[c & 1][i]) + b4.x;
-      const float x1 = __uint_as_float(v[c & 1][i + 1]) + b4.y;
-      const float x2 = __uint_as_float(v[c & 1][i + 2]) + b4.z;
-      const float x3 = __uint_as_float(v[c & 1][i + 3]) + b4.w;
+      float x0, x1, x2, x3;
+      add_f32x2(v[c & 1][i], v[c & 1][i + 1], b4.x, b4.y, x0, x1);
+      add_f32x2(v[c & 1][i + 2], v[c & 1][i + 3], b4.z, b4.w, x2, x3);
       if (kSig) {   // fc_alpha on the rectified, unrounded trunk output
         const float4 w4 = lds128(wa + (uint32_t)((c * 16 + i) * 4));
         sigma = fmaf(fmaxf(x0, 0.0f), w4.x, sigma);

@@ -179,6 +179,16 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
                : "memory");
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// (a0, a1) + (b0, b1) as ONE packed fp32x2 add (sm_100 FADD2; same round-to-nearest results as two scalar
+// adds): the epilogue warps share the SM's issue slots with everything else, and at hidden = 128 - where a
+// pass is only 8 MMAs long - their instruction count is what the tensor pipe ends up waiting for.
+__device__ __forceinline__ void add_f32x2(uint32_t a0, uint32_t a1, float b0, float b1, float& x0, float& x1) {
+  uint64_t a, b, d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(a0), "r"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(d));
+}
 // two fp32 -> packed bf16x2 (lo = first K element), optional ReLU
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi, bool relu) {
   uint32_t d;
