@@ -418,20 +418,24 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
           const uint32_t slot_p = w_slot, phase_p = w_phase;
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
-            if (p == 0 && l > 0) {
-              mbar_wait(bar(B_aready(t)), ph_aready[t], 3);
-              ph_aready[t] ^= 1;
-            } else {
-              mbar_wait(bar(B_dfree(t)), ph_dfree[t] ^ 1, 1);
-              if (l == 0) mbar_wait(bar(B_xyzfull(t)), pe_ph, 2);
-            }
-            ph_dfree[t] ^= 1;
+            // The weights and the encodings come first: they arrive independently of this tile's epilogue
+            // (the producer and the encoders run ahead) and are normally complete already, but each poll
+            // costs ~100 cycles.  The gate - the one wait that is on the tile's MMA -> epilogue -> MMA
+            // critical path - comes last, so that nothing but one fence and one arrival follows it.
             uint32_t slot = slot_p, phase = phase_p;
             for (int c = 0; c < n_chunks; ++c) {
               if (t == 0) mbar_wait(bar(B_wfull(slot)), phase, 4);
               if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
             }
             if (L.smem_src == 2 && p == 0) mbar_wait(bar(B_dirfull(t)), pe_ph, 2);
+            if (l == 0 && p == 0) mbar_wait(bar(B_xyzfull(t)), pe_ph, 2);
+            if (p == 0 && l > 0) {
+              mbar_wait(bar(B_aready(t)), ph_aready[t], 3);
+              ph_aready[t] ^= 1;
+            } else {
+              mbar_wait(bar(B_dfree(t)), ph_dfree[t] ^ 1, 1);
+            }
+            ph_dfree[t] ^= 1;
             tc_fence_after();
             tc_fence_before();
             if (leader) mbar_arrive(bar(B_ready(t)));

@@ -19,7 +19,11 @@ def main():
     S = int(sys.argv[2]) if len(sys.argv) > 2 else 64
     tap = int(sys.argv[3]) if len(sys.argv) > 3 else 0        # which tile pair of CTA 0 is recorded (0 = first)
     torch.manual_seed(1)
-    model = nerf.FlexibleNeRFModel(8, 256, 4, 10, 4).cuda()
+    shape = sys.argv[4] if len(sys.argv) > 4 else "8x256"   # "8x256" | "8x128" | "4x128" (the as-run networks)
+    model = {"8x256": lambda: nerf.FlexibleNeRFModel(8, 256, 4, 10, 4),
+             "8x128": lambda: nerf.FlexibleNeRFModel(8, 128, 3, 10, 4),
+             "4x128": lambda: nerf.FlexibleNeRFModel(num_encoding_fn_xyz=10, num_encoding_fn_dir=4)}[shape]().cuda()
+    flop = 2 * sum(p.numel() for k, p in model.named_parameters() if k.endswith("weight"))
     ex, ed = nerf.get_embedding_function(10, True, True), nerf.get_embedding_function(4, True, True)
     prog = model.program(ex, ed)
     g = torch.Generator().manual_seed(0)
@@ -39,7 +43,7 @@ def main():
     ms = e0.elapsed_time(e1)
     tiles = (n * S + 127) // 128
     print("kernel %.3f ms for %d samples (%d tiles, %.1f pairs/SM): %.2f ns/sample, %.1f TFLOP/s"
-          % (ms, n * S, tiles, tiles / 2 / 148, ms * 1e6 / (n * S), n * S * 1186816 / ms / 1e9))
+          % (ms, n * S, tiles, tiles / 2 / 148, ms * 1e6 / (n * S), n * S * flop / ms / 1e9))
     for mode, name in ((-3, "weights traffic cut to 1 KB/chunk (results invalid)"), (-4, "debug build, full traffic")):
         e0.record()
         tensorcore.query(model, prog, ro, rd, vd, z, rf, dbg=tl.view(torch.float32), dbg_layer=mode)
