@@ -35,6 +35,8 @@
 // Weight-image layout (no swizzle, K-major "interleaved" canonical layout): an operand tile is a
 // grid of 8-row x 16-byte core matrices, each 128 contiguous bytes; byte offset of element
 // (row r, k) = (k/8)*LBO + (r/8)*SBO + (r%8)*16 + (k%8)*2 with SBO = 128 and LBO = rows*16.
+#include <type_traits>
+
 #include "tc_plan.cuh"
 #include "tc_ptx.cuh"
 
@@ -317,79 +319,96 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     // The layer record of the NEXT layer is fetched (indexed constant loads, a few hundred cycles of
     // dependent latency) while the last pass of the current layer is being issued, not between layers.
     TcLayer L = P.layers[0];
+    // One pass (both tiles) of layer l.  kPlain = a hidden layer H -> H without a shared-memory operand (most
+    // layers): N, the instruction descriptor and the chunk structure are then compile-time constants and the
+    // issuing warp - a single dependent instruction stream that shares its scheduler with five other warps,
+    // ~10 cycles per instruction - has next to nothing to compute between two passes.
+    auto issue_pass = [&](auto plain_tag, int l, int p, bool last_pass) {
+      constexpr bool kPlain = decltype(plain_tag)::value;
+      const int np = kPlain ? 128 : (L.n_out < 128 ? L.n_out : 128);
+      const uint32_t idesc = instr_desc(np);
+      const bool has_main = kPlain || L.k_main != 0;
+      const uint32_t b_lbo16 = (uint32_t)np;            // LBO = np*16 bytes -> np in 16-byte units
+      const bool timing = kDbg && P.dbg_layer == -2 && blockIdx.x == 0 && it == (uint32_t)P.dbg_pass && leader;
+      const uint32_t slot_p = w_slot, phase_p = w_phase;   // first chunk of this pass
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const uint32_t a_tmem = tmem_base + (uint32_t)(t * 256);
+        const uint32_t d_tmem = a_tmem + 128;
+        // Everything this pass waits for (its tile's epilogue, the weight chunks, the encoders) is
+        // awaited by the SCOUT warp (warp 3, below), which then arrives on ready[t]: the issuer's
+        // own critical path between two passes is one barrier poll.
+        if (timing) reinterpret_cast<long long*>(P.dbg)[900 + ((l * 2 + p) * 2 + t) * 3] = clock64();
+        mbar_wait(bar(B_ready(t)), ph_ready[t], 1);
+        ph_ready[t] ^= 1;
+        if (timing) reinterpret_cast<long long*>(P.dbg)[900 + ((l * 2 + p) * 2 + t) * 3 + 1] = clock64();
+        uint32_t slot = slot_p, phase = phase_p;
+        tc_fence_after();
+        if (timing) reinterpret_cast<long long*>(P.dbg)[((l * 2 + p) * 2 + t) * 2] = clock64();
+        if (has_main) {
+#pragma unroll 1
+          for (int c = 0; c < kMain; ++c) {
+            // descriptor low word: address (16-byte units) | LBO << 16; K-step advance = 2*LBO
+            const uint32_t b_lo = (slot0_lo + slot * (kSlotBytes >> 4)) | (b_lbo16 << 16);
+            if (leader) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                mma_ts(d_tmem, a_tmem + (uint32_t)(c * 32 + ks * 8),
+                       desc_hi | (uint64_t)(b_lo + (uint32_t)ks * 2 * b_lbo16), idesc, (c | ks) ? 1u : 0u);
+              tc_commit(bar(B_wempty(slot)));   // slot is refilled once both tiles' MMAs retire
+            }
+            __syncwarp();
+            if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
+          }
+        }
+        if (!kPlain && L.smem_src) {
+          const uint32_t b_lo = (slot0_lo + slot * (kSlotBytes >> 4)) | (b_lbo16 << 16);
+          const uint32_t a_addr = (L.smem_src == 1)
+              ? sbase + Smem::pe_xyz + (uint32_t)t * kPeXyzBytes
+              : sbase + Smem::pe_dir + (uint32_t)t * kPeDirBytes;
+          const uint32_t a_lo = ((a_addr >> 4) & 0x3FFF) | ((uint32_t)kTileM << 16);   // LBO = 128*16 B
+          if (leader) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              if (ks * 16 < L.k_smem)
+                mma_ss(d_tmem, desc_hi | (uint64_t)(a_lo + (uint32_t)ks * 2 * kTileM),
+                       desc_hi | (uint64_t)(b_lo + (uint32_t)ks * 2 * b_lbo16), idesc,
+                       (has_main || ks) ? 1u : 0u);
+            }
+            tc_commit(bar(B_wempty(slot)));
+          }
+          __syncwarp();
+          if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
+        }
+        if (leader) {
+          tc_commit(bar(B_dfull(t)));
+          if (!kPlain && last_pass) {
+            if (l == P.last_xyz_layer) tc_commit(bar(B_xyzempty(t)));   // encoders may refill
+            if (L.smem_src == 2) tc_commit(bar(B_dirempty(t)));
+          }
+        }
+        __syncwarp();
+        if (timing) reinterpret_cast<long long*>(P.dbg)[((l * 2 + p) * 2 + t) * 2 + 1] = clock64();
+        if (t == 1) { w_slot = slot; w_phase = phase; }
+      }
+    };
 #pragma unroll 1
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++it) {
 #pragma unroll 1
       for (int l = 0; l < P.n_layers; ++l) {
         TcLayer Lnext = L;
-        const int np = L.n_out < 128 ? L.n_out : 128;
-        const uint32_t idesc = instr_desc(np);
-        const bool has_main = L.k_main != 0;
-        const uint32_t b_lbo16 = (uint32_t)np;            // LBO = np*16 bytes -> np in 16-byte units
-        const bool timing = kDbg && P.dbg_layer == -2 && blockIdx.x == 0 && it == (uint32_t)P.dbg_pass && leader;
+        const int l_next = l + 1 < P.n_layers ? l + 1 : 0;
+        if (L.k_main == H && L.smem_src == 0 && L.n_out == H) {
+#pragma unroll
+          for (int p = 0; p < H / 128; ++p) {
+            if (p == H / 128 - 1) Lnext = P.layers[l_next];
+            issue_pass(std::true_type{}, l, p, p == H / 128 - 1);
+          }
+        } else {
 #pragma unroll 1
-        for (int p = 0; p < L.n_pass; ++p) {
-          if (p == L.n_pass - 1) Lnext = P.layers[l + 1 < P.n_layers ? l + 1 : 0];
-          const uint32_t slot_p = w_slot, phase_p = w_phase;   // first chunk of this pass
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const uint32_t a_tmem = tmem_base + (uint32_t)(t * 256);
-            const uint32_t d_tmem = a_tmem + 128;
-            // Everything this pass waits for (its tile's epilogue, the weight chunks, the encoders) is
-            // awaited by the SCOUT warp (warp 3, below), which then arrives on ready[t]: the issuer's
-            // own critical path between two passes is one barrier poll.
-            if (timing) reinterpret_cast<long long*>(P.dbg)[900 + ((l * 2 + p) * 2 + t) * 3] = clock64();
-            mbar_wait(bar(B_ready(t)), ph_ready[t], 1);
-            ph_ready[t] ^= 1;
-            if (timing) reinterpret_cast<long long*>(P.dbg)[900 + ((l * 2 + p) * 2 + t) * 3 + 1] = clock64();
-            uint32_t slot = slot_p, phase = phase_p;
-            tc_fence_after();
-            if (timing) reinterpret_cast<long long*>(P.dbg)[((l * 2 + p) * 2 + t) * 2] = clock64();
-            if (has_main) {
-#pragma unroll 1
-              for (int c = 0; c < kMain; ++c) {
-                // descriptor low word: address (16-byte units) | LBO << 16; K-step advance = 2*LBO
-                const uint32_t b_lo = (slot0_lo + slot * (kSlotBytes >> 4)) | (b_lbo16 << 16);
-                if (leader) {
-#pragma unroll
-                  for (int ks = 0; ks < 4; ++ks)
-                    mma_ts(d_tmem, a_tmem + (uint32_t)(c * 32 + ks * 8),
-                           desc_hi | (uint64_t)(b_lo + (uint32_t)ks * 2 * b_lbo16), idesc, (c | ks) ? 1u : 0u);
-                  tc_commit(bar(B_wempty(slot)));   // slot is refilled once both tiles' MMAs retire
-                }
-                __syncwarp();
-                if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
-              }
-            }
-            if (L.smem_src) {
-              const uint32_t b_lo = (slot0_lo + slot * (kSlotBytes >> 4)) | (b_lbo16 << 16);
-              const uint32_t a_addr = (L.smem_src == 1)
-                  ? sbase + Smem::pe_xyz + (uint32_t)t * kPeXyzBytes
-                  : sbase + Smem::pe_dir + (uint32_t)t * kPeDirBytes;
-              const uint32_t a_lo = ((a_addr >> 4) & 0x3FFF) | ((uint32_t)kTileM << 16);   // LBO = 128*16 B
-              if (leader) {
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  if (ks * 16 < L.k_smem)
-                    mma_ss(d_tmem, desc_hi | (uint64_t)(a_lo + (uint32_t)ks * 2 * kTileM),
-                           desc_hi | (uint64_t)(b_lo + (uint32_t)ks * 2 * b_lbo16), idesc,
-                           (has_main || ks) ? 1u : 0u);
-                }
-                tc_commit(bar(B_wempty(slot)));
-              }
-              __syncwarp();
-              if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
-            }
-            if (leader) {
-              tc_commit(bar(B_dfull(t)));
-              if (p == L.n_pass - 1) {
-                if (l == P.last_xyz_layer) tc_commit(bar(B_xyzempty(t)));   // encoders may refill
-                if (L.smem_src == 2) tc_commit(bar(B_dirempty(t)));
-              }
-            }
-            __syncwarp();
-            if (timing) reinterpret_cast<long long*>(P.dbg)[((l * 2 + p) * 2 + t) * 2 + 1] = clock64();
-            if (t == 1) { w_slot = slot; w_phase = phase; }
+          for (int p = 0; p < L.n_pass; ++p) {
+            if (p == L.n_pass - 1) Lnext = P.layers[l_next];
+            issue_pass(std::false_type{}, l, p, p == L.n_pass - 1);
           }
         }
         L = Lnext;
