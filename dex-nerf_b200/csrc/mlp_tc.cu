@@ -10,7 +10,8 @@
 //                 cp.async.bulk (TMA bulk copy, mbarrier complete_tx); each chunk is consumed by
 //                 both tiles before the slot is recycled.
 //   warp 1        MMA issuer: one elected thread issues tcgen05.mma (M=128, N=128, K=16), the
-//                 passes of the two tiles alternating strictly.  Hidden activations are the A
+//                 passes of the two tiles alternating strictly; hidden H -> H layers run a pass
+//                 specialised at compile time (nothing to compute between two passes).  Hidden activations are the A
 //                 operand READ FROM TENSOR MEMORY (bf16, 2 per column); the positional encodings
 //                 (layer 1, skip layer, view-direction layer) are A operands read from shared
 //                 memory.  A 256-wide layer runs as two N=128 passes into a 128-column fp32
@@ -18,8 +19,9 @@
 //                 the 512 columns.
 //   warp 2        TMEM allocator.
 //   warp 3        scout: walks the pass sequence one step ahead of the issuer and does all the
-//                 waiting for it (the tile's epilogue, the weight chunks, the encodings), then
-//                 releases the pass with ONE arrival on ready[tile].
+//                 waiting for it - the weight chunks and the encodings first, the tile's epilogue
+//                 (the gate on the critical path) last - then releases the pass with ONE arrival
+//                 on ready[tile].
 //   warps 4-19    epilogue, 8 warps per tile (two per 32-lane quarter, 64 columns each), one thread
 //                 per sample row: tcgen05.ld the accumulator, + bias, ReLU, pack to bf16 and
 //                 tcgen05.st it back as the next layer's A operand (first-pass results wait in
