@@ -163,3 +163,22 @@ def test_meshgrid_and_helpers():
     assert np.array_equal(ii.numpy(), a) and np.array_equal(jj.numpy(), b)
     assert [c.shape[0] for c in nerf.get_minibatches(torch.zeros(10, 2), 4)] == [4, 4, 2]
     assert nerf.mse2psnr(0) == 50.0
+
+
+def test_bench_scene_tables_are_consistent():
+    """bench.py's secondary scenes (c3 / c5): sizes as SURVEY.md section 8 states them, and the per-evaluation
+    FLOP count follows from the weight shapes of the network the scene builds."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.FLOP_PER_EVAL == 1186816 and bench.FLOP_PER_RAY == 303824896      # C2 (SURVEY 8d)
+    bench.apply_scene("c5")
+    assert (bench.H, bench.W, bench.NC, bench.NF) == (720, 1280, 128, 256)
+    assert bench.FLOP_PER_EVAL == 1186816 and bench.FLOP_PER_RAY == (128 + 128 + 256) * 1186816
+    bench.apply_scene("c3")
+    assert (bench.H, bench.W, bench.NC, bench.NF) == (270, 480, 64, 64) and bench.H * bench.W == 129600
+    mc, mf = bench.state_dicts()
+    assert mc.hidden_size == 128 and len(mc.layers_xyz) == 7 and mc.skip_connect_every == 3
+    assert bench.FLOP_PER_EVAL == 2 * sum(p.numel() for k, p in mc.named_parameters() if k.endswith("weight"))
+    assert float(mc.fc_alpha.weight.abs().max()) > 10.0          # the x1000 scale that makes sigma cross thresholds
