@@ -199,12 +199,12 @@ __device__ __forceinline__ void epilogue_pass(uint32_t d_tmem, uint32_t a_park, 
       float x0, x1, x2, x3;
       add_f32x2(v[c & 1][i], v[c & 1][i + 1], b4.x, b4.y, x0, x1);
       add_f32x2(v[c & 1][i + 2], v[c & 1][i + 3], b4.z, b4.w, x2, x3);
-      if (kSig) {   // fc_alpha on the rectified, unrounded trunk output
+      if (kSig) {   // fc_alpha on the unrounded layer output: rectified (Flexible: trunk output) or not (Paper: feat)
         const float4 w4 = lds128(wa + (uint32_t)((c * 16 + i) * 4));
-        sigma = fmaf(fmaxf(x0, 0.0f), w4.x, sigma);
-        sigma = fmaf(fmaxf(x1, 0.0f), w4.y, sigma);
-        sigma = fmaf(fmaxf(x2, 0.0f), w4.z, sigma);
-        sigma = fmaf(fmaxf(x3, 0.0f), w4.w, sigma);
+        sigma = fmaf(kRelu ? fmaxf(x0, 0.0f) : x0, w4.x, sigma);
+        sigma = fmaf(kRelu ? fmaxf(x1, 0.0f) : x1, w4.y, sigma);
+        sigma = fmaf(kRelu ? fmaxf(x2, 0.0f) : x2, w4.z, sigma);
+        sigma = fmaf(kRelu ? fmaxf(x3, 0.0f) : x3, w4.w, sigma);
       }
       if (kHold) {
         held[c * 8 + i / 2] = pack_bf16(x0, x1, kRelu);
@@ -233,7 +233,9 @@ __device__ __forceinline__ void epilogue_pass(uint32_t d_tmem, uint32_t a_park, 
 }
 
 // ------------------------------------------------------------------ the kernel
-template <int H, bool kDbg, bool kTape>
+// kPaper: PaperNeRFModel's layer table (tc_plan.cuh) - layers narrower than H (128 -> 128 in an H = 256 kernel),
+// a sigma head on an unrectified layer; a separate instantiation so that the Flexible kernels stay as they are.
+template <int H, bool kDbg, bool kTape, bool kPaper = false>
 __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -348,8 +350,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
         tc_fence_after();
         if (timing) reinterpret_cast<long long*>(P.dbg)[((l * 2 + p) * 2 + t) * 2] = clock64();
         if (has_main) {
+          const int n_main = (kPaper && !kPlain) ? L.k_main / 64 : kMain;
 #pragma unroll 1
-          for (int c = 0; c < kMain; ++c) {
+          for (int c = 0; c < n_main; ++c) {
             // descriptor low word: address (16-byte units) | LBO << 16; K-step advance = 2*LBO
             const uint32_t b_lo = (slot0_lo + slot * (kSlotBytes >> 4)) | (b_lbo16 << 16);
             if (leader) {
@@ -565,15 +568,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
         } else {
           const uint32_t bias = sbase + Smem::consts + ((uint32_t)L.bias_off + hs * 64) * 4;
           const uint32_t wa = sbase + Smem::consts + ((uint32_t)P.off_walpha + hs * 64) * 4;
-          const int kind = L.relu ? (L.head == 1 ? 2 : 1) : 0;
+          const int kind = L.relu ? (L.head == 1 ? 2 : 1) : (kPaper && L.head == 1 ? 3 : 0);
 #pragma unroll
           for (int p = 0; p < H / 128; ++p) {
+            if (kPaper && p >= L.n_pass) break;     // a 128-wide layer of the H = 256 Paper kernel: one pass
             mbar_wait(bar(B_dfull(t)), ph_dfull, 5);
             ph_dfull ^= 1;
             tc_fence_after();
             if (timing && pair == tap_pair) tl[256 + ((l * 2 + p) * 2 + t) * 2] = clock64();
             constexpr bool kTwoPass = (H == 256);
-            const bool hold = kTwoPass && p == 0;
+            const bool two_pass = kPaper ? L.n_pass == 2 : kTwoPass;
+            const bool hold = two_pass && p == 0;
             float* dbg_dst = (kDbg && P.dbg_layer == l && P.dbg_pass == p && g < P.m_total)
                                  ? P.dbg + g * 128 + hs * 64 : nullptr;
             const uint32_t bp = bias + (uint32_t)(p * 128 * 4);
@@ -594,11 +599,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
             if (hold) {
               if (kind == 0) epilogue_pass<false, false, true, false, kDbg, kTape>(d_tmem, a_park, a_store, bp, wp, sigma, held, dfree, dbg_dst, stamps, tape_row, tape_mask);
               else if (kind == 1) epilogue_pass<true, false, true, false, kDbg, kTape>(d_tmem, a_park, a_store, bp, wp, sigma, held, dfree, dbg_dst, stamps, tape_row, tape_mask);
+              else if (kPaper && kind == 3) epilogue_pass<false, true, true, false, kDbg, kTape>(d_tmem, a_park, a_store, bp, wp, sigma, held, dfree, dbg_dst, stamps, tape_row, tape_mask);
               else epilogue_pass<true, true, true, false, kDbg, kTape>(d_tmem, a_park, a_store, bp, wp, sigma, held, dfree, dbg_dst, stamps, tape_row, tape_mask);
+            } else if (kPaper && !two_pass) {
+              // single-pass layer (dir branch of the Paper model): nothing held, nothing to park
+              if (kind == 0) epilogue_pass<false, false, false, false, kDbg, kTape>(d_tmem, a_park, a_store, bp, wp, sigma, held, dfree, dbg_dst, stamps, tape_row, tape_mask);
+              else epilogue_pass<true, false, false, false, kDbg, kTape>(d_tmem, a_park, a_store, bp, wp, sigma, held, dfree, dbg_dst, stamps, tape_row, tape_mask);
+              tmem_wait_st();
+              tc_fence_before();
+              mbar_arrive(bar(B_aready(t)));
             } else {
               constexpr bool park = kTwoPass;
               if (kind == 0) epilogue_pass<false, false, false, park, kDbg, kTape>(d_tmem, a_park, a_store, bp, wp, sigma, held, dfree, dbg_dst, stamps, tape_row, tape_mask);
               else if (kind == 1) epilogue_pass<true, false, false, park, kDbg, kTape>(d_tmem, a_park, a_store, bp, wp, sigma, held, dfree, dbg_dst, stamps, tape_row, tape_mask);
+              else if (kPaper && kind == 3) epilogue_pass<false, true, false, park, kDbg, kTape>(d_tmem, a_park, a_store, bp, wp, sigma, held, dfree, dbg_dst, stamps, tape_row, tape_mask);
               else epilogue_pass<true, true, false, park, kDbg, kTape>(d_tmem, a_park, a_store, bp, wp, sigma, held, dfree, dbg_dst, stamps, tape_row, tape_mask);
               if (kDbg && stamps) stamps[9] = clock64();
               tmem_wait_st();
@@ -782,8 +796,9 @@ extern "C" DEXNERF_API int dexnerf_tc_pack(const dexnerf_flexible_spec* spec, co
         PackChunk& pc = h_chunks[nch++];
         const bool main = c < L.k_main / 64;
         pc.dst = dst; pc.w_off = (int)op.w_off; pc.n_out = L.n_out; pc.n0 = p * 128; pc.np = np;
-        // layer1: the smem operand is the whole input; skip/dir layers: it follows the k_main hidden inputs
-        pc.k0 = main ? c * 64 : L.k_main;
+        // layer1: the smem operand is the whole input; skip/dir layers: it follows the k_main hidden inputs -
+        // except in the Paper model's skip layer, cat((xyz, x)), where the encoding comes first
+        pc.k0 = plan.layers[l].smem_first ? (main ? real_smem + c * 64 : 0) : (main ? c * 64 : L.k_main);
         pc.kc = main ? 64 : L.k_smem;
         pc.k_valid = main ? 64 : real_smem;
         dst += (int64_t)np * pc.kc * 2;
@@ -854,7 +869,10 @@ static int tc_query_impl(const dexnerf_flexible_spec* spec, const void* packed, 
     return 0;
   };
   int rc;
-  if (spec->hidden == 256)
+  DN_REQUIRE(!(tape && spec->arch != 0), "tc_query_train: the training variant exists for FlexibleNeRFModel only");
+  if (spec->arch == 1)
+    rc = dbg ? launch(mlp_tc_kernel<256, true, false, true>) : launch(mlp_tc_kernel<256, false, false, true>);
+  else if (spec->hidden == 256)
     rc = tape ? launch(mlp_tc_kernel<256, false, true>)
               : (dbg ? launch(mlp_tc_kernel<256, true, false>) : launch(mlp_tc_kernel<256, false, false>));
   else
@@ -875,6 +893,7 @@ extern "C" DEXNERF_API int dexnerf_tc_query(const dexnerf_flexible_spec* spec, c
 extern "C" DEXNERF_API int64_t dexnerf_tc_tape_bytes(const dexnerf_flexible_spec* spec, int64_t n_samples) {
   Plan plan;
   if (make_plan(spec, &plan)) return -1;
+  if (spec->arch != 0) { set_error("tc_tape_bytes: the training variant exists for FlexibleNeRFModel only"); return -1; }
   if (n_samples < 0) { set_error("tc_tape_bytes: negative sample count"); return -1; }
   const int64_t n_pairs = ((n_samples + kTileM - 1) / kTileM + 1) / 2;
   TapeLayout T;

@@ -588,6 +588,7 @@ extern "C" DEXNERF_API int dexnerf_tc_pack_bwd(const dexnerf_flexible_spec* spec
                                                const float* params, void* packed_t, void* stream) {
   Plan plan;
   if (int rc = make_plan(spec, &plan)) return rc;
+  DN_REQUIRE(spec->arch == 0, "tc: the backward kernels exist for FlexibleNeRFModel only");
   DN_REQUIRE(prog && params && packed_t, "tc_pack_bwd: null pointer");
   DN_REQUIRE(prog->n_ops == plan.n_layers + 2, "tc_pack_bwd: program has %d ops, expected %d", prog->n_ops,
              plan.n_layers + 2);
@@ -616,6 +617,7 @@ extern "C" DEXNERF_API int dexnerf_tc_pack_bwd(const dexnerf_flexible_spec* spec
 extern "C" DEXNERF_API int dexnerf_tc_tape_layout(const dexnerf_flexible_spec* spec, int64_t n_samples, int64_t* out) {
   Plan plan;
   if (int rc = make_plan(spec, &plan)) return rc;
+  DN_REQUIRE(spec->arch == 0, "tc: the backward kernels exist for FlexibleNeRFModel only");
   DN_REQUIRE(out && n_samples >= 0, "tc_tape_layout: bad argument");
   const int64_t n_pairs = ((n_samples + kTileM - 1) / kTileM + 1) / 2;
   TapeLayout T;
@@ -632,6 +634,7 @@ extern "C" DEXNERF_API int dexnerf_tc_backward(const dexnerf_flexible_spec* spec
                                                int variant, void* stream) {
   Plan plan;
   if (int rc = make_plan(spec, &plan)) return rc;
+  DN_REQUIRE(spec->arch == 0, "tc: the backward kernels exist for FlexibleNeRFModel only");
   DN_REQUIRE(prog && packed && packed_t && tape && d_rf && grads, "tc_backward: null pointer");
   DN_REQUIRE(prog->n_ops == plan.n_layers + 2, "tc_backward: program has %d ops, expected %d", prog->n_ops,
              plan.n_layers + 2);

@@ -20,7 +20,7 @@ struct TcLayer {
   int bias_off;  // into the const block (floats)
 };
 
-struct HostLayer { TcLayer tc; int prog_op; };
+struct HostLayer { TcLayer tc; int prog_op; int smem_first; };   // smem_first: the encoding precedes the hidden inputs in the weight's K order
 
 struct Plan {
   int n_layers = 0;
@@ -35,9 +35,10 @@ inline int pad16(int v) { return (v + 15) / 16 * 16; }
 
 inline int make_plan(const dexnerf_flexible_spec* s, Plan* plan) {
   DN_REQUIRE(s, "tc: null spec");
-  DN_REQUIRE(s->hidden == 256 || s->hidden == 128, "tc: hidden must be 128 or 256 (got %d)", s->hidden);
-  DN_REQUIRE(s->n_trunk >= 1 && s->n_trunk + 3 <= kMaxLayers, "tc: unsupported trunk depth %d", s->n_trunk);
-  DN_REQUIRE(s->skip_every >= 1, "tc: skip_every < 1");
+  DN_REQUIRE(s->arch == 0 || s->arch == 1, "tc: unknown architecture %d", s->arch);
+  DN_REQUIRE(s->hidden == 256 || (s->hidden == 128 && s->arch == 0), "tc: hidden must be 128 or 256 (got %d)", s->hidden);
+  DN_REQUIRE(s->arch == 1 || (s->n_trunk >= 1 && s->n_trunk + 3 <= kMaxLayers), "tc: unsupported trunk depth %d", s->n_trunk);
+  DN_REQUIRE(s->arch == 1 || s->skip_every >= 1, "tc: skip_every < 1");
   DN_REQUIRE(s->dim_xyz >= 1 && s->dim_xyz <= 64, "tc: dim_xyz must be <= 64 (got %d)", s->dim_xyz);
   DN_REQUIRE(s->dim_dir >= 1 && s->dim_dir <= 32, "tc: dim_dir must be in 1..32 (got %d)", s->dim_dir);
   Plan& P = *plan;
@@ -45,24 +46,39 @@ inline int make_plan(const dexnerf_flexible_spec* s, Plan* plan) {
   P.kx = pad16(s->dim_xyz);
   P.kd = pad16(s->dim_dir);
   int bias = 0, op = 0;
-  auto add = [&](int k_main, int src, int k_smem, int n_out, int relu, int head, int prog_op) {
+  auto add = [&](int k_main, int src, int k_smem, int n_out, int relu, int head, int prog_op, int smem_first = 0) {
     HostLayer& L = P.layers[P.n_layers++];
     L.tc.k_main = k_main; L.tc.smem_src = src; L.tc.k_smem = k_smem; L.tc.n_out = n_out;
     L.tc.n_pass = (n_out + 127) / 128; L.tc.relu = relu; L.tc.head = head; L.tc.bias_off = bias;
     L.prog_op = prog_op;
+    L.smem_first = smem_first;
     bias += (n_out + 127) / 128 * 128;
     const int np = n_out < 128 ? n_out : 128;
     P.weight_bytes += (int64_t)L.tc.n_pass * np * (k_main + (src ? k_smem : 0)) * 2;
   };
-  add(0, 1, P.kx, H, 0, 0, op++);                                    // layer1 (no ReLU)
-  for (int i = 0; i < s->n_trunk; ++i) {
-    const bool skip = (i % s->skip_every == 0) && i > 0;
-    add(H, skip ? 1 : 0, skip ? P.kx : 0, H, 1, i == s->n_trunk - 1 ? 1 : 0, op++);
+  if (s->arch == 1) {
+    // PaperNeRFModel (nerf/models.py:123-182, repaired forward): 8 x 256 trunk from xyz, cat((xyz, x)) into
+    // layer 4, feat = fc_feat(x) WITHOUT ReLU, alpha = fc_alpha(feat), then cat((feat, dirs)) ->
+    // 128 -> 128 -> 128 (ReLU each) -> fc_rgb.  Program ops: xyz0..7, fc_feat, fc_alpha, dir0..2, fc_rgb.
+    add(0, 1, P.kx, 256, 1, 0, op++);                                 // layers_xyz[0] (with ReLU)
+    for (int i = 1; i < 8; ++i) add(256, i == 4 ? 1 : 0, i == 4 ? P.kx : 0, 256, 1, 0, op++, i == 4);
+    add(256, 0, 0, 256, 0, 1, op++);                                  // fc_feat (no ReLU) + sigma head on feat
+    P.op_alpha = op++;
+    add(256, 2, P.kd, 128, 1, 0, op++);                               // layers_dir[0]
+    add(128, 0, 0, 128, 1, 0, op++);                                  // layers_dir[1]
+    add(128, 0, 0, 128, 1, 2, op++);                                  // layers_dir[2] (+ fc_rgb head)
+    P.op_rgb = op++;
+  } else {
+    add(0, 1, P.kx, H, 0, 0, op++);                                    // layer1 (no ReLU)
+    for (int i = 0; i < s->n_trunk; ++i) {
+      const bool skip = (i % s->skip_every == 0) && i > 0;
+      add(H, skip ? 1 : 0, skip ? P.kx : 0, H, 1, i == s->n_trunk - 1 ? 1 : 0, op++);
+    }
+    P.op_alpha = op++;
+    add(H, 0, 0, H, 1, 0, op++);                                        // fc_feat
+    add(H, 2, P.kd, H / 2, 1, 2, op++);                                 // layers_dir[0] (+ fc_rgb head)
+    P.op_rgb = op++;
   }
-  P.op_alpha = op++;
-  add(H, 0, 0, H, 1, 0, op++);                                        // fc_feat
-  add(H, 2, P.kd, H / 2, 1, 2, op++);                                 // layers_dir[0] (+ fc_rgb head)
-  P.op_rgb = op++;
   P.off_walpha = bias; bias += H;
   P.off_balpha = bias; bias += 4;
   P.off_wrgb = bias; bias += 3 * (H / 2);

@@ -30,7 +30,7 @@ class FlexibleSpec(C.Structure):
     _fields_ = [("hidden", C.c_int32), ("n_trunk", C.c_int32), ("skip_every", C.c_int32),
                 ("dim_xyz", C.c_int32), ("dim_dir", C.c_int32), ("Lx", C.c_int32), ("Ld", C.c_int32),
                 ("include_xyz", C.c_int32), ("include_dir", C.c_int32), ("log_xyz", C.c_int32),
-                ("log_dir", C.c_int32), ("pad_", C.c_int32)]
+                ("log_dir", C.c_int32), ("arch", C.c_int32)]
 
 
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float

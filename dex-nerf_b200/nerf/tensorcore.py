@@ -4,21 +4,25 @@ parameter changes) and launches the fused encode + MLP kernel."""
 import torch
 
 from . import _lib as L
-from .models import FlexibleNeRFModel
+from .models import FlexibleNeRFModel, PaperNeRFModel
 
 
 def spec_for(model, prog):
-    """FlexibleSpec for a FlexibleNeRFModel the kernel supports, else None."""
-    if not isinstance(model, FlexibleNeRFModel) or not model.use_viewdirs:
-        return None
-    H = model.hidden_size
-    n_trunk = len(model.layers_xyz)
-    if H not in (128, 256) or n_trunk < 1 or n_trunk + 3 > 16:
+    """FlexibleSpec for a model the kernel supports - FlexibleNeRFModel with view directions (hidden 128 / 256)
+    or PaperNeRFModel (arch = 1, inference only) - else None."""
+    if not isinstance(model, (FlexibleNeRFModel, PaperNeRFModel)) or not model.use_viewdirs:
         return None
     if not (1 <= model.dim_xyz <= 64 and 1 <= model.dim_dir <= 32):
         return None
     s = L.FlexibleSpec()
-    s.hidden, s.n_trunk, s.skip_every = H, n_trunk, int(model.skip_connect_every)
+    if isinstance(model, PaperNeRFModel):
+        s.hidden, s.n_trunk, s.skip_every, s.arch = 256, 7, 4, 1
+    else:
+        H = model.hidden_size
+        n_trunk = len(model.layers_xyz)
+        if H not in (128, 256) or n_trunk < 1 or n_trunk + 3 > 16:
+            return None
+        s.hidden, s.n_trunk, s.skip_every, s.arch = H, n_trunk, int(model.skip_connect_every), 0
     s.dim_xyz, s.dim_dir = int(model.dim_xyz), int(model.dim_dir)
     s.Lx, s.Ld = prog.Lx, prog.Ld
     s.include_xyz, s.include_dir, s.log_xyz, s.log_dir = prog.include_xyz, prog.include_dir, prog.log_xyz, prog.log_dir
@@ -27,6 +31,11 @@ def spec_for(model, prog):
 
 def supported(model, prog):
     return spec_for(model, prog) is not None
+
+
+def trainable(model, prog):
+    """The tape / backward kernels exist for the FlexibleNeRFModel layer table only."""
+    return isinstance(model, FlexibleNeRFModel) and supported(model, prog)
 
 
 def packed_weights(model, prog, spec):

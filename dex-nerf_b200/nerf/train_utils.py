@@ -41,7 +41,7 @@ def _fusable(model, embed_fn, embeddirs_fn):
 def _trainable(model, embed_fn, embeddirs_fn):
     from . import tensorcore
     return (_fusable(model, embed_fn, embeddirs_fn)
-            and tensorcore.supported(model, model.program(embed_fn, embeddirs_fn if model.dim_dir else None)))
+            and tensorcore.trainable(model, model.program(embed_fn, embeddirs_fn if model.dim_dir else None)))
 
 
 _warned_no_grad = False

@@ -143,7 +143,7 @@ class FieldRender(torch.autograd.Function):
     def forward(ctx, model, embed_fn, embeddirs_fn, ro, rd, viewdirs, z, noise, white_background, thr, T,
                 *params):
         prog = model.program(embed_fn, embeddirs_fn)
-        spec = tensorcore.spec_for(model, prog)
+        spec = tensorcore.spec_for(model, prog) if tensorcore.trainable(model, prog) else None
         if spec is None:
             raise L.DexNerfError("training runs on the tensor-core path: FlexibleNeRFModel with view directions, "
                                  "hidden size 128 or 256")
@@ -232,7 +232,7 @@ class Trainer:
         self.progs, self.specs, self.sizes = [], [], []
         for m in self.models:
             prog = m.program(self.ex, self.ed)
-            spec = tensorcore.spec_for(m, prog)
+            spec = tensorcore.spec_for(m, prog) if tensorcore.trainable(m, prog) else None
             if spec is None:
                 raise L.DexNerfError("Trainer needs tensor-core-capable FlexibleNeRFModels (view directions, "
                                      "hidden 128/256)")

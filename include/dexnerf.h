@@ -117,7 +117,8 @@ DEXNERF_API int dexnerf_mlp_query(const dexnerf_mlp_program* prog /*host*/, cons
                       const float* ro, const float* rd, const float* viewdirs, const float* z,
                       int64_t n, int S, float* rf, void* stream);
 
-/* ---- tensor-core path (sm_100a tcgen05): FlexibleNeRFModel family only.
+/* ---- tensor-core path (sm_100a tcgen05): FlexibleNeRFModel (nerf/models.py:185-256, inference and training)
+ * and PaperNeRFModel (nerf/models.py:123-182, arch = 1: hidden 256, inference only).
  * Packing converts nn.Linear weights into the bf16 UMMA shared-memory images the kernel streams
  * with bulk TMA.  See dex-nerf_b200/csrc/mlp_tc.cu. */
 typedef struct {
@@ -125,7 +126,7 @@ typedef struct {
   int32_t n_trunk;    /* number of layers_xyz (num_layers - 1) */
   int32_t skip_every; /* skip_connect_every */
   int32_t dim_xyz, dim_dir, Lx, Ld, include_xyz, include_dir, log_xyz, log_dir;
-  int32_t pad_;
+  int32_t arch;       /* 0: FlexibleNeRFModel; 1: PaperNeRFModel (hidden must be 256; n_trunk / skip_every ignored) */
 } dexnerf_flexible_spec;
 /* size in bytes of the packed weight blob for `spec` (negative on error) */
 DEXNERF_API int64_t dexnerf_tc_packed_bytes(const dexnerf_flexible_spec* spec /*host*/);

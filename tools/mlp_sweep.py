@@ -32,9 +32,10 @@ def main():
     ex, ed = nerf.get_embedding_function(10, True, True), nerf.get_embedding_function(4, True, True)
     for name, kw in (("8x256 skip 4", dict(num_layers=8, hidden_size=256, skip_connect_every=4)),
                      ("8x128 skip 3", dict(num_layers=8, hidden_size=128, skip_connect_every=3)),
-                     ("4x128 (as run)", dict())):
+                     ("4x128 (as run)", dict()), ("PaperNeRFModel", None)):
         torch.manual_seed(0)
-        m = nerf.FlexibleNeRFModel(num_encoding_fn_xyz=10, num_encoding_fn_dir=4, **kw).cuda()
+        m = (nerf.PaperNeRFModel(num_encoding_fn_xyz=10, num_encoding_fn_dir=4) if kw is None
+             else nerf.FlexibleNeRFModel(num_encoding_fn_xyz=10, num_encoding_fn_dir=4, **kw)).cuda()
         flop = 2 * sum(p.numel() for k, p in m.named_parameters() if k.endswith("weight"))
         with torch.no_grad():
             for _ in range(2):
