@@ -5,8 +5,9 @@
 //
 // One CTA owns a tile of 64 samples.  The encodings and two ping-pong activation buffers live in
 // shared memory; each of the 256 threads accumulates a 4-row x (out/16)-column register tile,
-// reading activations as shared-memory broadcasts and the transposed weights Wt[in][out] as
-// coalesced, L1/L2-resident global loads.  Nothing per-sample except the final (r,g,b,sigma)
+// reading activations as shared-memory broadcasts and the transposed weights Wt[in][out] either from
+// two cp.async-fed shared-memory stages (layers whose width is a multiple of 64: 128-bit loads) or as
+// coalesced, L1/L2-resident global loads (heads, odd widths).  Nothing per-sample except the final (r,g,b,sigma)
 // is written to HBM.
 #include "common.cuh"
 
@@ -16,9 +17,12 @@ constexpr int kTileM = 64;
 constexpr int kThreads = 256;
 constexpr int kMaxOut = 256;
 
+constexpr int kStageK = 16;                         // weight rows (input features) per staged chunk
+
 struct SimtLayout {
   int ld_xyz, ld_dir, ld_buf;
   int off_xyz, off_dir, off_a, off_b, off_out;  // float offsets
+  int off_stage, stage_floats;                  // two weight stages (16-byte aligned, stage_floats each), or -1 when they do not fit
   int total_floats;
 };
 
@@ -33,6 +37,18 @@ static SimtLayout make_layout(const dexnerf_mlp_program& p) {
   L.off_b = L.off_a + kTileM * L.ld_buf;
   L.off_out = L.off_b + kTileM * L.ld_buf;
   L.total_floats = L.off_out + kTileM * 4;
+  // two weight stages sized for the widest layer that takes the staged path
+  L.off_stage = -1;
+  L.stage_floats = 0;
+  int widest = 0;
+  for (int i = 0; i < p.n_ops; ++i)
+    if ((p.ops[i].out_dim & 63) == 0 && p.ops[i].out_dim <= kMaxOut && p.ops[i].out_dim > widest) widest = p.ops[i].out_dim;
+  const int stage0 = (L.total_floats + 3) & ~3;
+  if (widest > 0 && (size_t)(stage0 + 2 * kStageK * widest) * sizeof(float) <= 227 * 1024) {
+    L.off_stage = stage0;
+    L.stage_floats = kStageK * widest;
+    L.total_floats = stage0 + 2 * L.stage_floats;
+  }
   return L;
 }
 
@@ -67,6 +83,98 @@ __device__ __forceinline__ void accumulate(float (&acc)[4][NJ], const float* __r
       acc[1][j] = fmaf(x1, w, acc[1][j]);
       acc[2][j] = fmaf(x2, w, acc[2][j]);
       acc[3][j] = fmaf(x3, w, acc[3][j]);
+    }
+  }
+}
+
+// ---- wide layers (N a multiple of 64): the transposed weights are streamed through shared memory in chunks
+// of 16 input features (cp.async, two stages), so that the inner loop reads them as 128-bit shared loads
+// (4 + J loads for 16 J FMAs per k instead of 4 + 4 J scalar global loads).  A thread owns 4 rows x 4 J columns,
+// columns 4 tx + 64 j + (0..3).  The accumulation order per output is unchanged (k ascending), so the results
+// are bit-identical to the direct path below.
+__device__ __forceinline__ void stage_rows(float* dst, const float* __restrict__ src, int n_floats, int tid) {
+  for (int e = tid * 4; e < n_floats; e += kThreads * 4) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst + e);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + e) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <int J>
+__device__ __forceinline__ void accumulate_staged(float (&acc)[4][4 * J], const float* __restrict__ src, int ld,
+                                                  int K, const float* __restrict__ Wt, float* stage,
+                                                  int stage_floats, int tx, int row0, int tid) {
+  constexpr int N = 64 * J;
+  const float* a0 = src + (row0 + 0) * ld;
+  const float* a1 = src + (row0 + 1) * ld;
+  const float* a2 = src + (row0 + 2) * ld;
+  const float* a3 = src + (row0 + 3) * ld;
+  const int n_chunks = (K + kStageK - 1) / kStageK;
+  auto rows_of = [&](int c) { return K - c * kStageK < kStageK ? K - c * kStageK : kStageK; };
+  stage_rows(stage, Wt, rows_of(0) * N, tid);
+  for (int c = 0; c < n_chunks; ++c) {
+    if (c + 1 < n_chunks) {
+      stage_rows(stage + ((c + 1) & 1) * stage_floats, Wt + (size_t)(c + 1) * kStageK * N, rows_of(c + 1) * N, tid);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const float* w = stage + (c & 1) * stage_floats + 4 * tx;
+    const int rows = rows_of(c), k0 = c * kStageK;
+#pragma unroll 4
+    for (int kk = 0; kk < rows; ++kk) {
+      const float x0 = a0[k0 + kk], x1 = a1[k0 + kk], x2 = a2[k0 + kk], x3 = a3[k0 + kk];
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const float4 w4 = *reinterpret_cast<const float4*>(w + kk * N + 64 * j);
+        const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          acc[0][4 * j + i] = fmaf(x0, wv[i], acc[0][4 * j + i]);
+          acc[1][4 * j + i] = fmaf(x1, wv[i], acc[1][4 * j + i]);
+          acc[2][4 * j + i] = fmaf(x2, wv[i], acc[2][4 * j + i]);
+          acc[3][4 * j + i] = fmaf(x3, wv[i], acc[3][4 * j + i]);
+        }
+      }
+    }
+    __syncthreads();     // the stage is refilled two chunks later
+  }
+}
+
+template <int J>
+__device__ __forceinline__ void run_op_staged(const dexnerf_op& op, const SimtLayout& L, float* smem,
+                                              const float* __restrict__ params, int tx, int ty, int tid) {
+  constexpr int N = 64 * J;
+  float acc[4][4 * J];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4 * J; ++c) acc[r][c] = 0.0f;
+  const int row0 = ty * 4;
+  const float* Wt = params + op.w_off;
+  float* stage = smem + L.off_stage;
+  float* src; int ld;
+  src_lookup(L, smem, op.src0, &src, &ld);
+  accumulate_staged<J>(acc, src, ld, op.src0_dim, Wt, stage, L.stage_floats, tx, row0, tid);
+  if (op.src1 != DEXNERF_NONE && op.src1_dim > 0) {
+    src_lookup(L, smem, op.src1, &src, &ld);
+    accumulate_staged<J>(acc, src, ld, op.src1_dim, Wt + (size_t)op.src0_dim * N, stage, L.stage_floats, tx, row0, tid);
+  }
+  const float* bias = params + op.b_off;
+  float* dst = smem + (op.dst == DEXNERF_BUF_A ? L.off_a : L.off_b);
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int nidx = 4 * tx + 64 * j + i;
+      const float b = __ldg(bias + nidx);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        float v = acc[r][4 * j + i] + b;
+        if (op.relu) v = fmaxf(v, 0.0f);
+        dst[(row0 + r) * L.ld_buf + nidx] = v;
+      }
     }
   }
 }
@@ -167,7 +275,15 @@ mlp_simt_kernel(const __grid_constant__ dexnerf_mlp_program prog, const SimtLayo
     // ---- run the layer program
     for (int i = 0; i < prog.n_ops; ++i) {
       const dexnerf_op& op = prog.ops[i];
-      if (op.out_dim <= 16) run_op<1>(op, L, smem, a.params, tx, ty);
+      // wide hidden layers whose weight block is 16-byte aligned take the staged path (block-uniform choice)
+      const bool staged = L.off_stage >= 0 && (op.out_dim & 63) == 0 && (op.w_off & 3) == 0 &&
+                          (op.dst == DEXNERF_BUF_A || op.dst == DEXNERF_BUF_B) &&
+                          ((reinterpret_cast<uintptr_t>(a.params) & 15) == 0);
+      if (staged && op.out_dim == 256) run_op_staged<4>(op, L, smem, a.params, tx, ty, tid);
+      else if (staged && op.out_dim == 192) run_op_staged<3>(op, L, smem, a.params, tx, ty, tid);
+      else if (staged && op.out_dim == 128) run_op_staged<2>(op, L, smem, a.params, tx, ty, tid);
+      else if (staged && op.out_dim == 64) run_op_staged<1>(op, L, smem, a.params, tx, ty, tid);
+      else if (op.out_dim <= 16) run_op<1>(op, L, smem, a.params, tx, ty);
       else if (op.out_dim <= 64) run_op<4>(op, L, smem, a.params, tx, ty);
       else if (op.out_dim <= 128) run_op<8>(op, L, smem, a.params, tx, ty);
       else run_op<16>(op, L, smem, a.params, tx, ty);
