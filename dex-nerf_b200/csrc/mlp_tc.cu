@@ -565,6 +565,61 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
             reinterpret_cast<float4*>(P.rf)[g] = o;
           }
           asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // xchg may be rewritten
+        } else if (kPaper && L.head == 3) {
+          // ---- last trunk layer of a model without view directions: ReLU, fc_out (4 outputs) on the CUDA
+          // cores over this warp's 64 columns of every pass, final (r,g,b,sigma) store; no A operand follows
+          float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+#pragma unroll
+          for (int p = 0; p < H / 128; ++p) {
+            mbar_wait(bar(B_dfull(t)), ph_dfull, 5);
+            ph_dfull ^= 1;
+            tc_fence_after();
+            const uint32_t col0 = (uint32_t)(p * 128 + hs * 64);
+            const uint32_t bias = sbase + Smem::consts + ((uint32_t)L.bias_off + col0) * 4;
+            const uint32_t wo = sbase + Smem::consts + ((uint32_t)P.off_wrgb + col0) * 4;
+            uint32_t v[2][16];
+            tmem_ld16_issue(d_tmem, v[0]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              tmem_ld16_wait(v[c & 1]);
+              if (c + 1 < 4) tmem_ld16_issue(d_tmem + (uint32_t)((c + 1) * 16), v[(c + 1) & 1]);
+              if (c == 3) {            // this warp's columns of the accumulator are in registers
+                tc_fence_before();
+                mbar_arrive(bar(B_dfree(t)));
+              }
+              if (kDbg && P.dbg_layer == l && P.dbg_pass == p && g < P.m_total) {
+                float* dst = P.dbg + g * 128 + hs * 64 + c * 16;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) dst[i] = __uint_as_float(v[c & 1][i]);
+              }
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                const float4 b4 = lds128(bias + (uint32_t)((c * 16 + i) * 4));
+                const float4 w0 = lds128(wo + (uint32_t)((c * 16 + i) * 4));
+                const float4 w1 = lds128(wo + (uint32_t)((H + c * 16 + i) * 4));
+                const float4 w2 = lds128(wo + (uint32_t)((2 * H + c * 16 + i) * 4));
+                const float4 w3 = lds128(wo + (uint32_t)((3 * H + c * 16 + i) * 4));
+                const float x0 = fmaxf(__uint_as_float(v[c & 1][i]) + b4.x, 0.0f);
+                const float x1 = fmaxf(__uint_as_float(v[c & 1][i + 1]) + b4.y, 0.0f);
+                const float x2 = fmaxf(__uint_as_float(v[c & 1][i + 2]) + b4.z, 0.0f);
+                const float x3 = fmaxf(__uint_as_float(v[c & 1][i + 3]) + b4.w, 0.0f);
+                o0 = fmaf(x0, w0.x, fmaf(x1, w0.y, fmaf(x2, w0.z, fmaf(x3, w0.w, o0))));
+                o1 = fmaf(x0, w1.x, fmaf(x1, w1.y, fmaf(x2, w1.z, fmaf(x3, w1.w, o1))));
+                o2 = fmaf(x0, w2.x, fmaf(x1, w2.y, fmaf(x2, w2.z, fmaf(x3, w2.w, o2))));
+                o3 = fmaf(x0, w3.x, fmaf(x1, w3.y, fmaf(x2, w3.z, fmaf(x3, w3.w, o3))));
+              }
+            }
+          }
+          if (hs == 1) *xchg = make_float4(o0, o1, o2, o3);
+          asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+          if (hs == 0 && g < P.m_total) {
+            const float4 o2nd = *xchg;
+            const float* bo = s_const + P.off_brgb;
+            float4 o;
+            o.x = o0 + o2nd.x + bo[0]; o.y = o1 + o2nd.y + bo[1]; o.z = o2 + o2nd.z + bo[2]; o.w = o3 + o2nd.w + bo[3];
+            reinterpret_cast<float4*>(P.rf)[g] = o;
+          }
+          asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // xchg may be rewritten
         } else {
           const uint32_t bias = sbase + Smem::consts + ((uint32_t)L.bias_off + hs * 64) * 4;
           const uint32_t wa = sbase + Smem::consts + ((uint32_t)P.off_walpha + hs * 64) * 4;
@@ -670,7 +725,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
         fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
         mbar_arrive(bar(B_xyzfull(t)));
       }
-      for (int t = 0; t < 2; ++t) {
+      for (int t = 0; t < 2 && (!kPaper || P.dim_dir > 0); ++t) {
         const int64_t g = (pair * 2 + t) * kTileM + row;
         float dir[3] = {0.f, 0.f, 0.f};
         const bool valid = g < P.m_total;
@@ -748,9 +803,9 @@ __global__ void pack_consts_kernel(const float* __restrict__ params, const __gri
     const int4 mv = Q.moves[m];
     for (int i = threadIdx.x; i < mv.z; i += blockDim.x) {
       int src = mv.y + i;
-      if (mv.w > 0) {               // W_rgb: consts[c*hw + k] = Wt[k*3 + c]
-        const int hw = mv.w, cch = i / hw, k = i - cch * hw;
-        src = mv.y + k * 3 + cch;
+      if (mv.w > 0) {               // head weights: consts[c*hw + k] = Wt[k*nch + c] (fc_rgb: 3 channels, fc_out: 4)
+        const int hw = mv.w, nch = mv.z / hw, cch = i / hw, k = i - cch * hw;
+        src = mv.y + k * nch + cch;
       }
       consts[mv.x + i] = params[src];
     }
@@ -775,7 +830,9 @@ extern "C" DEXNERF_API int dexnerf_tc_pack(const dexnerf_flexible_spec* spec, co
   if (int rc = make_plan(spec, &plan)) return rc;
   DN_REQUIRE(prog && params && packed, "tc_pack: null pointer");
   (void)workspace;   // kept in the ABI; the tables travel as kernel parameters now
-  DN_REQUIRE(prog->n_ops == plan.n_layers + 2, "tc_pack: program has %d ops, expected %d", prog->n_ops, plan.n_layers + 2);
+  const int n_head_ops = spec->arch == 2 ? 1 : 2;
+  DN_REQUIRE(prog->n_ops == plan.n_layers + n_head_ops, "tc_pack: program has %d ops, expected %d", prog->n_ops,
+             plan.n_layers + n_head_ops);
   cudaStream_t st = (cudaStream_t)stream;
   // chunk table (host) -> workspace (device)
   static thread_local PackTables tables;
@@ -807,14 +864,20 @@ extern "C" DEXNERF_API int dexnerf_tc_pack(const dexnerf_flexible_spec* spec, co
     h_moves[nmv++] = make_int4(L.bias_off, (int)op.b_off, L.n_out, 0);
   }
   const int H = spec->hidden;
-  const dexnerf_op& oa = prog->ops[plan.op_alpha];
   const dexnerf_op& orgb = prog->ops[plan.op_rgb];
-  DN_REQUIRE(oa.out_dim == 1 && oa.src0_dim == H && orgb.out_dim == 3 && orgb.src0_dim == H / 2,
-             "tc_pack: head ops do not match");
-  h_moves[nmv++] = make_int4(plan.off_walpha, (int)oa.w_off, H, 0);        // Wt[k][0]
-  h_moves[nmv++] = make_int4(plan.off_balpha, (int)oa.b_off, 1, 0);
-  h_moves[nmv++] = make_int4(plan.off_wrgb, (int)orgb.w_off, 3 * (H / 2), H / 2);
-  h_moves[nmv++] = make_int4(plan.off_brgb, (int)orgb.b_off, 3, 0);
+  if (spec->arch == 2) {
+    DN_REQUIRE(orgb.out_dim == 4 && orgb.src0_dim == H, "tc_pack: fc_out does not match");
+    h_moves[nmv++] = make_int4(plan.off_wrgb, (int)orgb.w_off, 4 * H, H);
+    h_moves[nmv++] = make_int4(plan.off_brgb, (int)orgb.b_off, 4, 0);
+  } else {
+    const dexnerf_op& oa = prog->ops[plan.op_alpha];
+    DN_REQUIRE(oa.out_dim == 1 && oa.src0_dim == H && orgb.out_dim == 3 && orgb.src0_dim == H / 2,
+               "tc_pack: head ops do not match");
+    h_moves[nmv++] = make_int4(plan.off_walpha, (int)oa.w_off, H, 0);        // Wt[k][0]
+    h_moves[nmv++] = make_int4(plan.off_balpha, (int)oa.b_off, 1, 0);
+    h_moves[nmv++] = make_int4(plan.off_wrgb, (int)orgb.w_off, 3 * (H / 2), H / 2);
+    h_moves[nmv++] = make_int4(plan.off_brgb, (int)orgb.b_off, 3, 0);
+  }
   tables.n_chunks = nch;
   tables.n_moves = nmv;
   DN_CUDA(cudaMemsetAsync(packed, 0, (size_t)kMaxConstFloats * 4, st));
@@ -830,7 +893,7 @@ static int tc_query_impl(const dexnerf_flexible_spec* spec, const void* packed, 
                          float* dbg, int dbg_layer, int dbg_pass, void* stream) {
   Plan plan;
   if (int rc = make_plan(spec, &plan)) return rc;
-  DN_REQUIRE(packed && ro && rd && viewdirs && z && rf, "tc_query: null pointer");
+  DN_REQUIRE(packed && ro && rd && z && rf && (viewdirs || spec->arch == 2), "tc_query: null pointer");
   DN_REQUIRE(S >= 1, "tc_query: S < 1");
   DN_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 15) == 0 && (reinterpret_cast<uintptr_t>(rf) & 15) == 0,
              "tc_query: packed weights and rf must be 16-byte aligned");
@@ -870,8 +933,10 @@ static int tc_query_impl(const dexnerf_flexible_spec* spec, const void* packed, 
   };
   int rc;
   DN_REQUIRE(!(tape && spec->arch != 0), "tc_query_train: the training variant exists for FlexibleNeRFModel only");
-  if (spec->arch == 1)
+  if (spec->arch != 0 && spec->hidden == 256)
     rc = dbg ? launch(mlp_tc_kernel<256, true, false, true>) : launch(mlp_tc_kernel<256, false, false, true>);
+  else if (spec->arch != 0)
+    rc = dbg ? launch(mlp_tc_kernel<128, true, false, true>) : launch(mlp_tc_kernel<128, false, false, true>);
   else if (spec->hidden == 256)
     rc = tape ? launch(mlp_tc_kernel<256, false, true>)
               : (dbg ? launch(mlp_tc_kernel<256, true, false>) : launch(mlp_tc_kernel<256, false, false>));

@@ -35,12 +35,13 @@ inline int pad16(int v) { return (v + 15) / 16 * 16; }
 
 inline int make_plan(const dexnerf_flexible_spec* s, Plan* plan) {
   DN_REQUIRE(s, "tc: null spec");
-  DN_REQUIRE(s->arch == 0 || s->arch == 1, "tc: unknown architecture %d", s->arch);
-  DN_REQUIRE(s->hidden == 256 || (s->hidden == 128 && s->arch == 0), "tc: hidden must be 128 or 256 (got %d)", s->hidden);
+  DN_REQUIRE(s->arch >= 0 && s->arch <= 2, "tc: unknown architecture %d", s->arch);
+  DN_REQUIRE(s->hidden == 256 || (s->hidden == 128 && s->arch != 1), "tc: hidden must be 128 or 256 (got %d)", s->hidden);
   DN_REQUIRE(s->arch == 1 || (s->n_trunk >= 1 && s->n_trunk + 3 <= kMaxLayers), "tc: unsupported trunk depth %d", s->n_trunk);
   DN_REQUIRE(s->arch == 1 || s->skip_every >= 1, "tc: skip_every < 1");
   DN_REQUIRE(s->dim_xyz >= 1 && s->dim_xyz <= 64, "tc: dim_xyz must be <= 64 (got %d)", s->dim_xyz);
-  DN_REQUIRE(s->dim_dir >= 1 && s->dim_dir <= 32, "tc: dim_dir must be in 1..32 (got %d)", s->dim_dir);
+  DN_REQUIRE(s->arch == 2 ? s->dim_dir == 0 : (s->dim_dir >= 1 && s->dim_dir <= 32),
+             "tc: dim_dir must be in 1..32 (0 without view directions), got %d", s->dim_dir);
   Plan& P = *plan;
   const int H = s->hidden;
   P.kx = pad16(s->dim_xyz);
@@ -68,6 +69,23 @@ inline int make_plan(const dexnerf_flexible_spec* s, Plan* plan) {
     add(128, 0, 0, 128, 1, 0, op++);                                  // layers_dir[1]
     add(128, 0, 0, 128, 1, 2, op++);                                  // layers_dir[2] (+ fc_rgb head)
     P.op_rgb = op++;
+  } else if (s->arch == 2) {
+    // FlexibleNeRFModel(use_viewdirs=False) (nerf/models.py:250-256): trunk, then fc_out (H -> 4 = rgb, sigma)
+    // evaluated on the CUDA cores in the last trunk layer's epilogue (head 3).  Program ops: layer1, trunk, fc_out.
+    add(0, 1, P.kx, H, 0, 0, op++);
+    for (int i = 0; i < s->n_trunk; ++i) {
+      const bool skip = (i % s->skip_every == 0) && i > 0;
+      add(H, skip ? 1 : 0, skip ? P.kx : 0, H, 1, i == s->n_trunk - 1 ? 3 : 0, op++);
+    }
+    P.op_alpha = -1;
+    P.op_rgb = op++;                                                   // fc_out
+    P.off_walpha = bias;
+    P.off_balpha = bias;
+    P.off_wrgb = bias; bias += 4 * H;                                  // W_out as [4][H]
+    P.off_brgb = bias; bias += 4;
+    P.n_const = bias;
+    DN_REQUIRE(P.n_const <= kMaxConstFloats, "tc: const block too large");
+    return 0;
   } else {
     add(0, 1, P.kx, H, 0, 0, op++);                                    // layer1 (no ReLU)
     for (int i = 0; i < s->n_trunk; ++i) {

@@ -8,11 +8,15 @@ from .models import FlexibleNeRFModel, PaperNeRFModel
 
 
 def spec_for(model, prog):
-    """FlexibleSpec for a model the kernel supports - FlexibleNeRFModel with view directions (hidden 128 / 256)
-    or PaperNeRFModel (arch = 1, inference only) - else None."""
-    if not isinstance(model, (FlexibleNeRFModel, PaperNeRFModel)) or not model.use_viewdirs:
+    """FlexibleSpec for a model the kernel supports - FlexibleNeRFModel (hidden 128 / 256; with view directions:
+    inference and training, without: arch = 2, inference only) or PaperNeRFModel (arch = 1, inference only) -
+    else None."""
+    if not isinstance(model, (FlexibleNeRFModel, PaperNeRFModel)):
         return None
-    if not (1 <= model.dim_xyz <= 64 and 1 <= model.dim_dir <= 32):
+    no_dirs = isinstance(model, FlexibleNeRFModel) and not model.use_viewdirs
+    if not model.use_viewdirs and not no_dirs:
+        return None
+    if not (1 <= model.dim_xyz <= 64 and (model.dim_dir == 0 if no_dirs else 1 <= model.dim_dir <= 32)):
         return None
     s = L.FlexibleSpec()
     if isinstance(model, PaperNeRFModel):
@@ -22,7 +26,7 @@ def spec_for(model, prog):
         n_trunk = len(model.layers_xyz)
         if H not in (128, 256) or n_trunk < 1 or n_trunk + 3 > 16:
             return None
-        s.hidden, s.n_trunk, s.skip_every, s.arch = H, n_trunk, int(model.skip_connect_every), 0
+        s.hidden, s.n_trunk, s.skip_every, s.arch = H, n_trunk, int(model.skip_connect_every), 2 if no_dirs else 0
     s.dim_xyz, s.dim_dir = int(model.dim_xyz), int(model.dim_dir)
     s.Lx, s.Ld = prog.Lx, prog.Ld
     s.include_xyz, s.include_dir, s.log_xyz, s.log_dir = prog.include_xyz, prog.include_dir, prog.log_xyz, prog.log_dir
@@ -35,7 +39,7 @@ def supported(model, prog):
 
 def trainable(model, prog):
     """The tape / backward kernels exist for the FlexibleNeRFModel layer table only."""
-    return isinstance(model, FlexibleNeRFModel) and supported(model, prog)
+    return isinstance(model, FlexibleNeRFModel) and model.use_viewdirs and supported(model, prog)
 
 
 def packed_weights(model, prog, spec):

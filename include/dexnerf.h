@@ -126,7 +126,8 @@ typedef struct {
   int32_t n_trunk;    /* number of layers_xyz (num_layers - 1) */
   int32_t skip_every; /* skip_connect_every */
   int32_t dim_xyz, dim_dir, Lx, Ld, include_xyz, include_dir, log_xyz, log_dir;
-  int32_t arch;       /* 0: FlexibleNeRFModel; 1: PaperNeRFModel (hidden must be 256; n_trunk / skip_every ignored) */
+  int32_t arch;       /* 0: FlexibleNeRFModel; 1: PaperNeRFModel (hidden must be 256; n_trunk / skip_every ignored);
+                         2: FlexibleNeRFModel(use_viewdirs=False): dim_dir = 0, viewdirs may be NULL */
 } dexnerf_flexible_spec;
 /* size in bytes of the packed weight blob for `spec` (negative on error) */
 DEXNERF_API int64_t dexnerf_tc_packed_bytes(const dexnerf_flexible_spec* spec /*host*/);

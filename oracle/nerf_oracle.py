@@ -266,7 +266,7 @@ def flexible_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, skip_connect_
             h = torch.cat((h, xyz), dim=-1)
         h = torch.relu(_linear(h, sd, f"layers_xyz.{i}", bf16))
     if not use_viewdirs:
-        return _linear(h, sd, "fc_out", bf16)
+        return _linear(h, sd, "fc_out", False)     # a head: fp32 on the CUDA cores, like fc_alpha / fc_rgb
     feat = torch.relu(_linear(h, sd, "fc_feat", bf16))
     alpha = _linear(h, sd, "fc_alpha", False)
     y = torch.relu(_linear(torch.cat((feat, view), dim=-1), sd, "layers_dir.0", bf16))

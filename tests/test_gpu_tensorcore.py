@@ -116,6 +116,35 @@ def test_tc_query_paper_model_vs_bf16_emulation(Lx, n, S):
     assert float((out_tc[3] - out_32[3]).abs().max()) < 2e-3
 
 
+@pytest.mark.parametrize("layers,hidden,skip,Lx,n,S", [(8, 256, 4, 10, 37, 64), (4, 128, 4, 6, 11, 50), (8, 128, 3, 10, 2, 192)])
+def test_tc_query_without_view_directions(layers, hidden, skip, Lx, n, S):
+    """FlexibleNeRFModel(use_viewdirs=False) (models.py:250-256): trunk, then fc_out (4 outputs) as an fp32 head in
+    the last trunk layer's epilogue; no direction encoding, viewdirs = None."""
+    torch.manual_seed(7 * layers + hidden)
+    model = nerf.FlexibleNeRFModel(layers, hidden, skip, Lx, 4, use_viewdirs=False)
+    with torch.no_grad():
+        model.fc_out.weight[3].mul_(30.0)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.cuda()
+    ex = nerf.get_embedding_function(Lx, True, True)
+    prog = model.program(ex, None)
+    assert tensorcore.supported(model, prog) and not tensorcore.trainable(model, prog)
+    ro, rd, vd, z = rays(n, S, seed=S)
+    rf = torch.full((n, S, 4), float("nan"), device="cuda")
+    tensorcore.query(model, prog, ro.cuda(), rd.cuda(), None, z.cuda(), rf)
+    pts = (ro[:, None, :] + rd[:, None, :] * z[:, :, None]).reshape(-1, 3)
+    x = O.positional_encoding(pts, Lx)
+    emu = O.flexible_forward(sd, x, skip_connect_every=skip, use_viewdirs=False, bf16=True).reshape(n, S, 4)
+    full = O.flexible_forward(sd, x, skip_connect_every=skip, use_viewdirs=False, bf16=False).reshape(n, S, 4)
+    got = rf.cpu()
+    assert torch.isfinite(got).all()
+    np.testing.assert_allclose(got[..., :3].numpy(), emu[..., :3].numpy(), rtol=0, atol=5e-4)
+    np.testing.assert_allclose(got[..., 3].numpy(), emu[..., 3].numpy(), rtol=0,
+                               atol=4e-3 * max(1.0, float(emu[..., 3].abs().max())))
+    assert float((got[..., :3] - full[..., :3]).abs().max()) < 5e-3
+    assert float((got[..., 3] - full[..., 3]).abs().max()) < 2e-2 * max(1.0, float(full[..., 3].abs().max()))
+
+
 def test_tc_weights_repack_after_update():
     """The packed bf16 image is cached per parameter version: an optimiser-style in-place update
     must be picked up."""
@@ -135,7 +164,7 @@ def test_tc_weights_repack_after_update():
 def test_unsupported_models_fall_to_fp32_kernel():
     m = nerf.FlexibleNeRFModel(5, 32, 2, 6, 4).cuda()
     assert not tensorcore.supported(m, m.program())
-    m = nerf.FlexibleNeRFModel(8, 256, 4, 10, 4, use_viewdirs=False).cuda()
+    m = nerf.FlexibleNeRFModel(8, 192, 4, 10, 4).cuda()
     assert not tensorcore.supported(m, m.program())
     m = nerf.PaperNeRFModel(use_viewdirs=False)
     assert not tensorcore.supported(m, None)
