@@ -56,7 +56,7 @@ composite_kernel(const float4* __restrict__ rf, const float* __restrict__ z,
                  float* __restrict__ rgb_out, float* __restrict__ disp_out,
                  float* __restrict__ acc_out, float* __restrict__ weights_out,
                  float* __restrict__ depth_out, float* __restrict__ dex_depth,
-                 int64_t* __restrict__ dex_index) {
+                 int64_t* __restrict__ dex_index, int64_t dex_stride) {
   extern __shared__ float smem[];
   // staging: [6 + 2T][32]: rgb0 rgb1 rgb2 disp acc depth | dex depth (T) | dex index (T, as int)
   // Thresholds are ranked ascending once per CTA: a sample that exceeds the k-th smallest threshold
@@ -245,8 +245,8 @@ composite_kernel(const float4* __restrict__ rf, const float* __restrict__ z,
       else if (plane == 3) { if (disp_out) disp_out[ray] = val; }
       else if (plane == 4) { if (acc_out) acc_out[ray] = val; }
       else if (plane == 5) { if (depth_out) depth_out[ray] = val; }
-      else if (plane < 6 + T) { if (dex_depth) dex_depth[(int64_t)(plane - 6) * n + ray] = val; }
-      else if (dex_index) dex_index[(int64_t)(plane - 6 - T) * n + ray] =
+      else if (plane < 6 + T) { if (dex_depth) dex_depth[(int64_t)(plane - 6) * dex_stride + ray] = val; }
+      else if (dex_index) dex_index[(int64_t)(plane - 6 - T) * dex_stride + ray] =
           (int64_t) reinterpret_cast<const int*>(s_out)[e];
     }
     __syncthreads();
@@ -380,11 +380,13 @@ __global__ void __launch_bounds__(256) cumprod_exclusive_kernel(const float* __r
 
 using namespace dexnerf;
 
-extern "C" DEXNERF_API int dexnerf_volume_render(const float* rf, const float* z, const float* rd,
+// dex_stride: distance (in elements) between two threshold planes of dex_depth / dex_index - n for a stand-alone
+// call, the full ray count when a chunk writes its columns of a (T, n_total) output (render.cu).
+int dexnerf::volume_render_impl(const float* rf, const float* z, const float* rd,
                                      const float* noise, int64_t n, int S, int white_background,
                                      const float* thresholds, int T, float* rgb, float* disp,
                                      float* acc, float* weights, float* depth, float* dex_depth,
-                                     int64_t* dex_index, void* stream) {
+                                     int64_t* dex_index, int64_t dex_stride, void* stream) {
   if (n <= 0) return 0;   // an empty batch (null data pointers) is a no-op
   DN_REQUIRE(rf && z && rd, "volume_render: null input");
   DN_REQUIRE(S >= 1, "volume_render: S < 1");
@@ -401,7 +403,7 @@ extern "C" DEXNERF_API int dexnerf_volume_render(const float* rf, const float* z
   auto launch = [&](auto kernel) {
     kernel<<<(int)blocks, kCompositeWarps * 32, smem, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(rf), z, rd, noise, n, S, white_background, thresholds, T, rgb,
-        disp, acc, weights, depth, dex_depth, dex_index);
+        disp, acc, weights, depth, dex_depth, dex_index, dex_stride);
   };
   if (S <= 32) launch(composite_kernel<1, false>);
   else if (S % 192 == 0) launch(composite_kernel<6, true>);
@@ -411,6 +413,15 @@ extern "C" DEXNERF_API int dexnerf_volume_render(const float* rf, const float* z
   else launch(composite_kernel<4, false>);
   DN_CHECK_LAUNCH("volume_render");
   return 0;
+}
+
+extern "C" DEXNERF_API int dexnerf_volume_render(const float* rf, const float* z, const float* rd,
+                                     const float* noise, int64_t n, int S, int white_background,
+                                     const float* thresholds, int T, float* rgb, float* disp,
+                                     float* acc, float* weights, float* depth, float* dex_depth,
+                                     int64_t* dex_index, void* stream) {
+  return volume_render_impl(rf, z, rd, noise, n, S, white_background, thresholds, T, rgb, disp, acc, weights, depth,
+                            dex_depth, dex_index, n, stream);
 }
 
 extern "C" DEXNERF_API int dexnerf_cumprod_exclusive(const float* x, int64_t n, int S, float* out, void* stream) {

@@ -825,11 +825,10 @@ extern "C" DEXNERF_API int64_t dexnerf_tc_packed_bytes(const dexnerf_flexible_sp
 }
 
 extern "C" DEXNERF_API int dexnerf_tc_pack(const dexnerf_flexible_spec* spec, const dexnerf_mlp_program* prog,
-                                           const float* params, void* packed, void* workspace, void* stream) {
+                                           const float* params, void* packed, void* stream) {
   Plan plan;
   if (int rc = make_plan(spec, &plan)) return rc;
   DN_REQUIRE(prog && params && packed, "tc_pack: null pointer");
-  (void)workspace;   // kept in the ABI; the tables travel as kernel parameters now
   const int n_head_ops = spec->arch == 2 ? 1 : 2;
   DN_REQUIRE(prog->n_ops == plan.n_layers + n_head_ops, "tc_pack: program has %d ops, expected %d", prog->n_ops,
              plan.n_layers + n_head_ops);

@@ -29,16 +29,47 @@ __global__ void __launch_bounds__(256) mse_loss_grad_kernel(const float* __restr
   }
 }
 
+// the training loss of train_dexnerf_rgb.py:264-277 in one launch: blockIdx.y = 0 / 1 -> coarse / fine prediction against
+// the same target; loss3 = [total, coarse, fine] accumulates (chunked batches), g_c / g_f = d loss / d pred
+__global__ void __launch_bounds__(256) mse_loss_pair_kernel(const float* __restrict__ pred_c, const float* __restrict__ pred_f,
+                                                            const float* __restrict__ target, int64_t count, float inv_count,
+                                                            float* __restrict__ g_c, float* __restrict__ g_f,
+                                                            float* __restrict__ loss3) {
+  const float* pred = blockIdx.y ? pred_f : pred_c;
+  float* g = blockIdx.y ? g_f : g_c;
+  double part = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    const float d = __fsub_rn(pred[i], target[i]);
+    part += (double)__fmul_rn(d, d);
+    g[i] = __fmul_rn(__fmul_rn(2.0f, d), inv_count);
+  }
+  part = warp_sum_f64(part);
+  __shared__ double s[8];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0;
+    for (int w = 0; w < 8; ++w) a += s[w];
+    const float v = (float)(a * (double)inv_count);
+    atomicAdd(loss3 + 1 + blockIdx.y, v);
+    atomicAdd(loss3, v);
+  }
+}
+
 // torch.optim.Adam (amsgrad = False, weight_decay = 0, maximize = False), element for element:
 //   exp_avg = beta1 exp_avg + (1 - beta1) g;  exp_avg_sq = beta2 exp_avg_sq + (1 - beta2) g g
 //   denom = sqrt(exp_avg_sq) / sqrt(1 - beta2^t) + eps;  p -= (lr / (1 - beta1^t)) exp_avg / denom
 // grad_scale folds the 1 / world of the data-parallel mean into the same pass.
-__global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, const float* __restrict__ g,
+// kZero: the gradient buffer is cleared as it is consumed, so the next iteration's weight-gradient GEMMs (which
+// ACCUMULATE with red.global.add) need no separate memset launch.
+template <bool kZero>
+__global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, float* __restrict__ g,
                                                         float* __restrict__ m, float* __restrict__ v, int64_t n,
                                                         float beta1, float beta2, float eps, float step_size,
                                                         float bc2_sqrt, float grad_scale) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float gi = __fmul_rn(g[i], grad_scale);
+    if (kZero) g[i] = 0.0f;
     // exp_avg.lerp_(grad, 1 - beta1) == exp_avg + (1 - beta1) (grad - exp_avg)
     const float mi = __fmaf_rn(1.0f - beta1, __fsub_rn(gi, m[i]), m[i]);
     // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value = 1 - beta2)
@@ -67,9 +98,38 @@ extern "C" DEXNERF_API int dexnerf_mse_loss_grad(const float* pred, const float*
   return 0;
 }
 
+extern "C" DEXNERF_API int dexnerf_mse_loss_pair(const float* pred_coarse, const float* pred_fine, const float* target,
+                                                 int64_t count, int64_t total_count, float* grad_coarse,
+                                                 float* grad_fine, float* loss3, void* stream) {
+  if (count <= 0) return 0;
+  DN_REQUIRE(pred_coarse && pred_fine && target && grad_coarse && grad_fine && loss3, "mse_loss_pair: null pointer");
+  DN_REQUIRE(total_count >= count, "mse_loss_pair: total_count < count");
+  int64_t blocks = ceil_div64(count, 256 * 4);
+  if (blocks > kNumSMs * 2) blocks = kNumSMs * 2;
+  mse_loss_pair_kernel<<<dim3((unsigned)blocks, 2), 256, 0, (cudaStream_t)stream>>>(
+      pred_coarse, pred_fine, target, count, 1.0f / (float)total_count, grad_coarse, grad_fine, loss3);
+  DN_CHECK_LAUNCH("mse_loss_pair");
+  return 0;
+}
+
+static int adam_impl(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                     float beta2, float eps, int64_t step, float grad_scale, bool zero, void* stream);
+
 extern "C" DEXNERF_API int dexnerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                                              int64_t n, float lr, float beta1, float beta2, float eps, int64_t step,
                                              float grad_scale, void* stream) {
+  return adam_impl(params, const_cast<float*>(grads), exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, grad_scale,
+                   false, stream);
+}
+
+extern "C" DEXNERF_API int dexnerf_adam_step_zero_grad(float* params, float* grads, float* exp_avg, float* exp_avg_sq,
+                                                       int64_t n, float lr, float beta1, float beta2, float eps,
+                                                       int64_t step, float grad_scale, void* stream) {
+  return adam_impl(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, grad_scale, true, stream);
+}
+
+static int adam_impl(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                     float beta2, float eps, int64_t step, float grad_scale, bool zero, void* stream) {
   if (n <= 0) return 0;   // an empty batch (null data pointers) is a no-op
   DN_REQUIRE(params && grads && exp_avg && exp_avg_sq, "adam_step: null pointer");
   DN_REQUIRE(step >= 1, "adam_step: step counts from 1");
@@ -79,8 +139,12 @@ extern "C" DEXNERF_API int dexnerf_adam_step(float* params, const float* grads, 
   const float bc2_sqrt = (float)sqrt(bc2);
   int64_t blocks = ceil_div64(n, 256 * 4);
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  adam_step_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, beta1, beta2,
-                                                                  eps, step_size, bc2_sqrt, grad_scale);
+  if (zero)
+    adam_step_kernel<true><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, beta1,
+                                                                          beta2, eps, step_size, bc2_sqrt, grad_scale);
+  else
+    adam_step_kernel<false><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, beta1,
+                                                                           beta2, eps, step_size, bc2_sqrt, grad_scale);
   DN_CHECK_LAUNCH("adam_step");
   return 0;
 }

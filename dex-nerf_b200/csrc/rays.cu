@@ -9,43 +9,6 @@ namespace dexnerf {
 
 // ---------------------------------------------------------------- get_ray_bundle
 // Reference: nerf/nerf_helpers.py:67-112 (+ meshgrid_xy :28-40).
-__device__ void invert4x4_f64(const float* T, double inv[16]) {
-  double a[4][8];
-  for (int r = 0; r < 4; ++r)
-    for (int c = 0; c < 4; ++c) {
-      a[r][c] = (double)T[r * 4 + c];
-      a[r][c + 4] = (r == c) ? 1.0 : 0.0;
-    }
-  for (int col = 0; col < 4; ++col) {
-    int piv = col;
-    double best = fabs(a[col][col]);
-    for (int r = col + 1; r < 4; ++r)
-      if (fabs(a[r][col]) > best) { best = fabs(a[r][col]); piv = r; }
-    if (piv != col)
-      for (int c = 0; c < 8; ++c) { double t = a[col][c]; a[col][c] = a[piv][c]; a[piv][c] = t; }
-    const double d = 1.0 / a[col][col];
-    for (int c = 0; c < 8; ++c) a[col][c] *= d;
-    for (int r = 0; r < 4; ++r)
-      if (r != col) {
-        const double f = a[r][col];
-        for (int c = 0; c < 8; ++c) a[r][c] -= f * a[col][c];
-      }
-  }
-  for (int r = 0; r < 4; ++r)
-    for (int c = 0; c < 4; ++c) inv[r * 4 + c] = a[r][c + 4];
-}
-
-__device__ void invert3x3_f64(const float* T /*4x4, top-left block*/, double inv[9]) {
-  const double a = T[0], b = T[1], c = T[2], d = T[4], e = T[5], f = T[6], g = T[8], h = T[9],
-               i = T[10];
-  const double A = e * i - f * h, B = -(d * i - f * g), C = d * h - e * g;
-  const double det = a * A + b * B + c * C;
-  const double r = 1.0 / det;
-  inv[0] = A * r; inv[1] = -(b * i - c * h) * r; inv[2] = (b * f - c * e) * r;
-  inv[3] = B * r; inv[4] = (a * i - c * g) * r;  inv[5] = -(a * f - c * d) * r;
-  inv[6] = C * r; inv[7] = -(a * h - b * g) * r; inv[8] = (a * e - b * d) * r;
-}
-
 __global__ void __launch_bounds__(256) ray_bundle_kernel(const float* __restrict__ T,
                                                          const float* __restrict__ K, int W,
                                                          int row0, int64_t n_pix,
@@ -53,27 +16,16 @@ __global__ void __launch_bounds__(256) ray_bundle_kernel(const float* __restrict
                                                          float* __restrict__ rd) {
   __shared__ float s_rinv[9];
   __shared__ float s_org[3];
-  if (threadIdx.x == 0) {
-    double inv4[16], inv3[9];
-    invert4x4_f64(T, inv4);
-    invert3x3_f64(T, inv3);
-    for (int k = 0; k < 9; ++k) s_rinv[k] = (float)inv3[k];
-    for (int k = 0; k < 3; ++k) s_org[k] = (float)inv4[k * 4 + 3];
-  }
+  if (threadIdx.x == 0) camera_inverse(T, s_rinv, s_org);
   __syncthreads();
   const float fx = K[0], cx = K[2], cy = K[5];
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pix;
        p += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(p / W) + row0;
-    const int c = (int)(p % W);
-    const float dx = __fdiv_rn(__fsub_rn((float)c, cx), fx);
-    const float dy = __fdiv_rn(__fsub_rn((float)r, cy), fx);  // reference divides by fx here too
+    float d[3];
+    pixel_direction((int)(p / W) + row0, (int)(p % W), fx, cx, cy, s_rinv, d);
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      const float v = __fadd_rn(__fadd_rn(__fmul_rn(dx, s_rinv[a * 3 + 0]),
-                                          __fmul_rn(dy, s_rinv[a * 3 + 1])),
-                                s_rinv[a * 3 + 2]);
-      rd[p * 3 + a] = v;
+      rd[p * 3 + a] = d[a];
       ro[p * 3 + a] = s_org[a];
     }
   }
@@ -120,14 +72,6 @@ __global__ void __launch_bounds__(256) posenc_kernel(const float* __restrict__ x
 
 // ---------------------------------------------------------------- stratified depths
 // Reference: nerf/train_utils.py:104-133.
-__device__ __forceinline__ float coarse_depth(float near, float far, int Nc, int lindisp, int i) {
-  const float t = linspace_at(0.0f, 1.0f, Nc, i);
-  const float omt = __fsub_rn(1.0f, t);
-  if (!lindisp) return __fadd_rn(__fmul_rn(near, omt), __fmul_rn(far, t));
-  return __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(__fdiv_rn(1.0f, near), omt),
-                                   __fmul_rn(__fdiv_rn(1.0f, far), t)));
-}
-
 __global__ void __launch_bounds__(256) stratified_kernel(int64_t n, int Nc, float near_s, float far_s,
                                                          const float* __restrict__ near_a,
                                                          const float* __restrict__ far_a, int lindisp,
@@ -140,15 +84,7 @@ __global__ void __launch_bounds__(256) stratified_kernel(int64_t n, int Nc, floa
     const int i = (int)(e - r * Nc);
     const float near = near_a ? near_a[r] : near_s;
     const float far = far_a ? far_a[r] : far_s;
-    float v = coarse_depth(near, far, Nc, lindisp, i);
-    if (t_rand) {
-      const float prev = i > 0 ? coarse_depth(near, far, Nc, lindisp, i - 1) : v;
-      const float next = i < Nc - 1 ? coarse_depth(near, far, Nc, lindisp, i + 1) : v;
-      const float lower = i > 0 ? __fmul_rn(0.5f, __fadd_rn(v, prev)) : v;
-      const float upper = i < Nc - 1 ? __fmul_rn(0.5f, __fadd_rn(next, v)) : v;
-      v = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), t_rand[e]));
-    }
-    z[e] = v;
+    z[e] = stratified_depth(near, far, Nc, lindisp, i, t_rand != nullptr, t_rand ? t_rand[e] : 0.0f);
   }
 }
 

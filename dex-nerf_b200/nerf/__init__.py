@@ -13,8 +13,8 @@ from .models import (FlexibleNeRFModel, MultiHeadNeRFModel, PaperNeRFModel, Repl
 from .nerf_helpers import (cumprod_exclusive, gather_cdf_util, get_embedding_function, get_minibatches,
                            get_ray_bundle, img2mse, meshgrid_xy, mse2psnr, ndc_rays, positional_encoding,
                            sample_pdf_2)
-from .train_utils import (get_precision, predict_and_render_radiance, run_network, run_one_iter_of_nerf,
-                          sample_pdf, set_precision)
+from .train_utils import (get_precision, predict_and_render_radiance, render_camera, run_network,
+                          run_one_iter_of_nerf, sample_pdf, set_precision)
 from .sharding import allreduce_gradients, gather_rows, row_block
 from .training import Trainer, learning_rate, train_step
 from .datasets import load_blender_data, load_llff_data, load_messytable_data

@@ -33,6 +33,34 @@ class FlexibleSpec(C.Structure):
                 ("log_dir", C.c_int32), ("arch", C.c_int32)]
 
 
+class ModelRef(C.Structure):
+    _fields_ = [("prog", C.POINTER(Program)), ("params", C.c_void_p), ("spec", C.POINTER(FlexibleSpec)),
+                ("packed", C.c_void_p), ("packed_t", C.c_void_p)]
+
+
+class RenderParams(C.Structure):
+    """dexnerf_render_params (include/dexnerf.h): one ray chunk of the fused render driver."""
+    _fields_ = [("n", C.c_int64), ("ro", C.c_void_p), ("rd", C.c_void_p), ("T_w2c", C.c_void_p), ("K", C.c_void_p),
+                ("H", C.c_int32), ("W", C.c_int32), ("row0", C.c_int32), ("rows", C.c_int32),
+                ("use_viewdirs", C.c_int32), ("ndc", C.c_int32),
+                ("focal", C.c_float), ("near", C.c_float), ("far", C.c_float),
+                ("Nc", C.c_int32), ("Nf", C.c_int32), ("lindisp", C.c_int32), ("perturb", C.c_int32),
+                ("white_background", C.c_int32), ("noise_std", C.c_float),
+                ("thresholds", C.c_void_p), ("T", C.c_int32), ("pad0_", C.c_int32),
+                ("t_rand", C.c_void_p), ("u", C.c_void_p), ("noise_coarse", C.c_void_p), ("noise_fine", C.c_void_p),
+                ("seed", C.c_uint64), ("offset", C.c_uint64),
+                ("coarse", ModelRef), ("fine", ModelRef),
+                ("tape_coarse", C.c_void_p), ("tape_fine", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+                ("rgb_coarse", C.c_void_p), ("depth_coarse", C.c_void_p), ("acc_coarse", C.c_void_p),
+                ("rgb_fine", C.c_void_p), ("depth_fine", C.c_void_p), ("acc_fine", C.c_void_p),
+                ("dex_fine", C.c_void_p), ("dex_stride", C.c_int64),
+                ("events", C.POINTER(C.c_void_p))]
+
+
+RENDER_LAUNCHES = 7
+RENDER_WS_SLOTS = 16
+
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _SIGS = {
     "dexnerf_abi_version": (C.c_int, []),
@@ -48,14 +76,24 @@ _SIGS = {
     "dexnerf_mlp_forward": (C.c_int, [C.POINTER(Program), _P, _P, _L, _P, _P]),
     "dexnerf_mlp_query": (C.c_int, [C.POINTER(Program), _P, _P, _P, _P, _P, _L, _I, _P, _P]),
     "dexnerf_tc_packed_bytes": (C.c_int64, [C.POINTER(FlexibleSpec)]),
-    "dexnerf_tc_pack": (C.c_int, [C.POINTER(FlexibleSpec), C.POINTER(Program), _P, _P, _P, _P]),
+    "dexnerf_tc_pack": (C.c_int, [C.POINTER(FlexibleSpec), C.POINTER(Program), _P, _P, _P]),
     "dexnerf_tc_query": (C.c_int, [C.POINTER(FlexibleSpec), _P, _P, _P, _P, _P, _L, _I, _P, _P, _I, _I, _P]),
     "dexnerf_volume_render_backward": (C.c_int, [_P, _P, _P, _P, _L, _I, _I, _P, _P, _P, _P, _P]),
     "dexnerf_mse_loss_grad": (C.c_int, [_P, _P, _L, _L, _P, _P, _P]),
+    "dexnerf_mse_loss_pair": (C.c_int, [_P, _P, _P, _L, _L, _P, _P, _P, _P]),
+    "dexnerf_adam_step_zero_grad": (C.c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _L, _F, _P]),
     "dexnerf_pack_params": (C.c_int, [C.POINTER(Program), _P, _P, _P]),
     "dexnerf_adam_step": (C.c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _L, _F, _P]),
     "dexnerf_depth_error_metrics": (C.c_int, [_P, _P, _P, _L, _I, _P, _P, _P, _P]),
     "dexnerf_depth_error_image": (C.c_int, [_P, _P, _P, _I, _I, _F, _P, _P]),
+    "dexnerf_render_workspace_bytes": (C.c_int64, [_L, _I, _I]),
+    "dexnerf_render_workspace_layout": (C.c_int, [_L, _I, _I, C.POINTER(C.c_int64)]),
+    "dexnerf_ray_setup": (C.c_int, [C.POINTER(RenderParams), _P]),
+    "dexnerf_render_fused_fwd": (C.c_int, [C.POINTER(RenderParams), _P]),
+    "dexnerf_render_fused_bwd": (C.c_int, [C.POINTER(RenderParams), _P, _P, _P, _P, _P, _I, _P]),
+    "dexnerf_event_create": (C.c_void_p, []),
+    "dexnerf_event_destroy": (None, [_P]),
+    "dexnerf_event_elapsed_ms": (C.c_float, [_P, _P]),
     "dexnerf_tc_tape_bytes": (C.c_int64, [C.POINTER(FlexibleSpec), _L]),
     "dexnerf_tc_tape_layout": (C.c_int, [C.POINTER(FlexibleSpec), _L, C.POINTER(C.c_int64)]),
     "dexnerf_tc_query_train": (C.c_int, [C.POINTER(FlexibleSpec), _P, _P, _P, _P, _P, _L, _I, _P, _P, _P]),

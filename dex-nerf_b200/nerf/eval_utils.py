@@ -115,8 +115,8 @@ def dex_depth_error_metrics(depth_planes, depth_gt, mask=None):
     if not isinstance(depth_planes, torch.Tensor):
         depth_planes = torch.stack(list(depth_planes), 0)
     T = depth_planes.shape[0]
-    pred = L.dev_f32(depth_planes.reshape(T, -1), "depth_planes")
-    gt = L.dev_f32(depth_gt.reshape(-1), "depth_gt")
+    pred = L.dev_f32(_to_device(depth_planes.reshape(T, -1)), "depth_planes")
+    gt = L.dev_f32(_to_device(depth_gt.reshape(-1)), "depth_gt")
     n = gt.numel()
     if pred.shape[1] != n:
         raise ValueError("depth planes have %d pixels, ground truth %d" % (pred.shape[1], n))
@@ -134,8 +134,19 @@ def dex_depth_error_metrics(depth_planes, depth_gt, mask=None):
     return out, best
 
 
+def _to_device(t):
+    """The reference's validation block hands these helpers `.cpu()` tensors (train_dexnerf_rgb.py:391-415:
+    `depth_target.cpu()`, `...detach().cpu()`); the metrics run on the device, so host tensors are uploaded
+    to the current CUDA device here (the inputs are one depth map each - this is reporting, not the hot path)."""
+    t = t.detach()
+    if not t.is_cuda:
+        t = t.to(device=torch.device("cuda", torch.cuda.current_device()))
+    return t.to(torch.float32)
+
+
 def compute_err_metric(depth_gt, depth_pred, mask):
-    """train_utils.py:9-30, same signature and result dict (python floats)."""
+    """train_utils.py:9-30, same signature and result dict (python floats).  CPU tensors are accepted, as the
+    reference script passes them (train_dexnerf_rgb.py:391-404)."""
     out, _ = dex_depth_error_metrics(depth_pred.reshape(1, -1), depth_gt, mask)
     v = out[0].tolist()
     return {"depth_abs_err": v[0], "depth_err2": v[1], "depth_err4": v[2], "depth_err8": v[3]}
@@ -148,8 +159,8 @@ def depth_error_img(D_est_tensor, D_gt_tensor, mask, abs_thres=1.0, dilate_radiu
     (csrc/metrics.cu); `dilate_radius` is unused, as in the reference."""
     if D_est_tensor.dim() != 3 or D_gt_tensor.shape != D_est_tensor.shape or mask.shape != D_est_tensor.shape:
         raise ValueError("depth_error_img expects (B, H, W) depth maps and a (B, H, W) mask")
-    est = L.dev_f32(D_est_tensor.detach()[0], "D_est_tensor")
-    gt = L.dev_f32(D_gt_tensor.detach()[0].to(torch.float32), "D_gt_tensor")
+    est = L.dev_f32(_to_device(D_est_tensor[0]), "D_est_tensor")
+    gt = L.dev_f32(_to_device(D_gt_tensor[0]), "D_gt_tensor")
     m = mask.detach()[0].to(device=est.device, dtype=torch.uint8).contiguous()
     H, W = est.shape
     out = torch.empty((H, W, 3), dtype=torch.float32, device=est.device)

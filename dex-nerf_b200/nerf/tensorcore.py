@@ -51,8 +51,7 @@ def packed_weights(model, prog, spec):
         if nbytes <= 0:
             raise L.DexNerfError("tc_packed_bytes: " + L.lib().dexnerf_last_error().decode())
         blob = torch.empty(nbytes, dtype=torch.uint8, device=params.device)
-        ws = torch.empty(16384, dtype=torch.uint8, device=params.device)
-        L.check(L.lib().dexnerf_tc_pack(spec, prog, L.ptr(params), L.ptr(blob), L.ptr(ws), L.stream_ptr()), "tc_pack")
+        L.check(L.lib().dexnerf_tc_pack(spec, prog, L.ptr(params), L.ptr(blob), L.stream_ptr()), "tc_pack")
         cache = (key, blob)
         model.__dict__["_tc_cache"] = cache
     return cache[1]

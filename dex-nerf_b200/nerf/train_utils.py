@@ -44,17 +44,24 @@ def _trainable(model, embed_fn, embeddirs_fn):
             and tensorcore.trainable(model, model.program(embed_fn, embeddirs_fn if model.dim_dir else None)))
 
 
-_warned_no_grad = False
-
-
-def _warn_no_grad():
-    global _warned_no_grad
-    if not _warned_no_grad:
-        import warnings
-        warnings.warn("dexnerf: gradients are implemented on the tensor-core path only (FlexibleNeRFModel with "
-                      "view directions, hidden 128/256, get_embedding_function encoders, precision 'bf16'); "
-                      "this call returns outputs WITHOUT a grad_fn, so loss.backward() will raise")
-        _warned_no_grad = True
+def _no_grad_reason(model, embed_fn, embeddirs_fn):
+    """Why `model` cannot be trained through this package (None when it can)."""
+    from .models import FlexibleNeRFModel
+    if _precision != "bf16":
+        return "precision is %r (set_precision('bf16') / DEXNERF_PRECISION selects the tensor-core path)" % _precision
+    if not isinstance(model, FlexibleNeRFModel):
+        return "%s has no backward kernels (only FlexibleNeRFModel does)" % type(model).__name__
+    if not model.use_viewdirs:
+        return "FlexibleNeRFModel(use_viewdirs=False) has no backward kernels"
+    if model.hidden_size not in (128, 256):
+        return "hidden_size %d (the tensor-core kernels exist for 128 and 256)" % model.hidden_size
+    if not isinstance(embed_fn, _Embedder) or not isinstance(embeddirs_fn, _Embedder):
+        return "the encoders are not get_embedding_function objects (a custom encode fn cannot be fused)"
+    if model.dim_xyz > 64 or model.dim_dir > 32:
+        return "encoding widths %d / %d exceed the kernel's 64 / 32" % (model.dim_xyz, model.dim_dir)
+    if not _trainable(model, embed_fn, embeddirs_fn):
+        return "the model / encoder combination is not supported by the tensor-core training kernels"
+    return None
 
 
 kernel_event_log = None   # bench.py sets this to a list to collect (name, start_evt, end_evt, n, S)
@@ -154,10 +161,17 @@ def predict_and_render_radiance(ray_batch, model_coarse, model_fine, options, mo
     # Gradients are recorded in "train" mode only (the reference's scripts render validation frames
     # under torch.no_grad(), train_dexnerf_rgb.py:317; a full frame's tape would not fit anyway).
     with_grad = n > 0 and mode == "train" and training.wants_grad(model_coarse, model_fine)
-    if with_grad and not (_precision == "bf16" and _trainable(model_coarse, encode_position_fn, encode_direction_fn)
-                          and _trainable(model_fine, encode_position_fn, encode_direction_fn)):
-        _warn_no_grad()
-        with_grad = False
+    if with_grad:
+        # No silent outputs without a grad_fn (loss.backward() would fail later with an opaque autograd error):
+        # gradients exist on the tensor-core path only - say so here, naming the condition.
+        for m in (model_coarse, model_fine):
+            why = _no_grad_reason(m, encode_position_fn, encode_direction_fn)
+            if why is not None:
+                raise L.DexNerfError("run_one_iter_of_nerf(mode='train') with gradients enabled is not supported for "
+                                     "this configuration: " + why + ".  Gradients are implemented for "
+                                     "FlexibleNeRFModel with view directions, hidden 128/256, "
+                                     "get_embedding_function encoders, precision 'bf16'; wrap the call in "
+                                     "torch.no_grad() to render without gradients")
     noise = rng.get("noise_coarse")
     if noise is None and std > 0.0:
         noise = torch.randn((n, Nc), dtype=torch.float32, device=dev) * std
@@ -202,6 +216,66 @@ def predict_and_render_radiance(ray_batch, model_coarse, model_fine, options, mo
     return tuple([rgb_coarse, depth_coarse, acc_coarse, f["rgb"], f["depth"], f["acc"]] + dex)
 
 
+def _fused_ok(model_coarse, model_fine, mode, embed_fn, embeddirs_fn):
+    """The fused driver (csrc/render.cu) runs every call whose two models lower to layer programs with
+    get_embedding_function encoders, except a training call that has to record an autograd graph."""
+    from . import training
+    if model_coarse is None or model_fine is None:
+        return False
+    if not (_fusable(model_coarse, embed_fn, embeddirs_fn) and _fusable(model_fine, embed_fn, embeddirs_fn)):
+        return False
+    return not (mode == "train" and training.wants_grad(model_coarse, model_fine))
+
+
+def _run_fused(height, width, focal_length, model_coarse, model_fine, ro_in, rd_in, options, mode, embed_fn,
+               embeddirs_fn, m_thres_cand, rng, camera=None):
+    """run_one_iter_of_nerf as one C-ABI call per ray chunk (6 launches; no torch kernel)."""
+    from . import render
+    opt = getattr(options.nerf, mode)
+    dev = rd_in.device if rd_in is not None else camera[0].device
+    thr, T = _thresholds_tensor(m_thres_cand, dev)
+    if int(opt.num_fine) <= 0:
+        # the reference builds its return from depth_fine_dex, which only exists after the fine pass
+        raise NameError("name 'depth_fine_dex' is not defined")
+    if camera is None:
+        shape = tuple(rd_in.shape)
+        ro, rd = ro_in.reshape((-1, 3)), rd_in.reshape((-1, 3))
+    else:
+        shape = (int(camera[3]), int(width), 3)
+        ro = rd = None
+    if (camera is None and rd.shape[0] == 0) or (camera is not None and shape[0] * shape[1] == 0):
+        return ()      # no rays -> no ray chunks -> the reference's zip(*[]) is empty (train_utils.py:252-282)
+    outs = render.render_rays(height, width, focal_length, model_coarse, model_fine, ro, rd, options, mode, embed_fn,
+                              embeddirs_fn, thr, T, rng, _precision, camera=camera)
+    images = outs[:6] + [outs[6][t] for t in range(T)]
+    if mode == "validation":
+        shapes = [shape, shape[:-1], shape[:-1]] * 2 + [shape[:-1]] * T
+        images = [image.view(s) for image, s in zip(images, shapes)]
+    return tuple(images)
+
+
+def render_camera(height, width, tform_cam2world, intrinsic, model_coarse, model_fine, options, mode="validation",
+                  encode_position_fn=None, encode_direction_fn=None, m_thres_cand=None, row_start=0, row_count=None,
+                  rng=None):
+    """get_ray_bundle + run_one_iter_of_nerf for one camera in ONE fused call per chunk (extension): the rays of
+    image rows [row_start, row_start + row_count) are generated inside the setup launch from the world->cam
+    extrinsic and the intrinsic (same quirks as get_ray_bundle, nerf_helpers.py:67-112), so a frame is
+    6 launches.  Returns run_one_iter_of_nerf's tuple, shaped (rows, width[, 3]) in validation mode."""
+    from .nerf_helpers import _small_to_device
+    T = _small_to_device(tform_cam2world, "tform_cam2world", (4, 4))
+    K = _small_to_device(intrinsic, "intrinsic", (3, 3))
+    rows = int(height) - int(row_start) if row_count is None else int(row_count)
+    if not _fused_ok(model_coarse, model_fine, mode, encode_position_fn, encode_direction_fn):
+        from .nerf_helpers import get_ray_bundle
+        ro, rd = get_ray_bundle(height, width, None, T, K, row_start=row_start, row_count=rows)
+        return run_one_iter_of_nerf(height, width, K[0, 0], model_coarse, model_fine, ro, rd, options, mode=mode,
+                                    encode_position_fn=encode_position_fn, encode_direction_fn=encode_direction_fn,
+                                    m_thres_cand=m_thres_cand, rng=rng)
+    focal = float(K[0, 0]) if options.dataset.no_ndc is False else 0.0     # only ndc_rays reads it (a host sync)
+    return _run_fused(height, width, focal, model_coarse, model_fine, None, None, options, mode, encode_position_fn,
+                      encode_direction_fn, m_thres_cand, rng, camera=(T, K, int(row_start), rows))
+
+
 def run_one_iter_of_nerf(height, width, focal_length, model_coarse, model_fine, ray_origins, ray_directions,
                          options, mode="train", encode_position_fn=None, encode_direction_fn=None,
                          m_thres_cand=None, rng=None):
@@ -212,6 +286,9 @@ def run_one_iter_of_nerf(height, width, focal_length, model_coarse, model_fine, 
     run_network is unnecessary because no per-sample tensor but (r,g,b,sigma) exists."""
     rd_in = L.dev_f32(ray_directions, "ray_directions")
     ro_in = L.dev_f32(ray_origins, "ray_origins")
+    if _fused_ok(model_coarse, model_fine, mode, encode_position_fn, encode_direction_fn):
+        return _run_fused(height, width, focal_length, model_coarse, model_fine, ro_in, rd_in, options, mode,
+                          encode_position_fn, encode_direction_fn, m_thres_cand, rng)
     viewdirs = None
     if options.nerf.use_viewdirs:
         viewdirs = rd_in / rd_in.norm(p=2, dim=-1).unsqueeze(-1)

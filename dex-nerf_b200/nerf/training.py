@@ -228,7 +228,16 @@ class Trainer:
         self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
         self.lr_decay, self.lr_decay_factor = lr_decay, lr_decay_factor
         self.world, self.group = int(world_size), group
+        # `iteration` is the loop index of the NEXT step (the reference's `i`), `adam_steps` the number of Adam
+        # updates made so far and `_lr_now` the rate the optimizer currently holds.  They only differ after a
+        # resume: the reference re-runs loop index `iter` of its checkpoint (train_dexnerf_rgb.py:172-178) with
+        # the restored param_group rate while Adam's own step counter keeps counting.
         self.iteration = 0
+        self.adam_steps = 0
+        self._lr_now = self.lr
+        if not bool(getattr(options.nerf, "use_viewdirs", True)):
+            raise L.DexNerfError("Trainer: options.nerf.use_viewdirs is False, but the training kernels exist for "
+                                 "FlexibleNeRFModel WITH view directions only")
         self.progs, self.specs, self.sizes = [], [], []
         for m in self.models:
             prog = m.program(self.ex, self.ed)
@@ -252,6 +261,9 @@ class Trainer:
         self.exp_avg = torch.zeros_like(self.params)
         self.exp_avg_sq = torch.zeros_like(self.params)
         self.loss = torch.zeros(3, dtype=torch.float32, device=dev)     # total, coarse, fine
+        self._chunks = {}
+        self.keep_grads = False      # True: leave the step's gradients in `grads` (tests) instead of clearing them in Adam
+        self.timing = None           # bench.py: (render.Events of the forward call, render.Events of the backward)
         self.blobs, self.blobs_t = [], []
         for spec in self.specs:
             self.blobs.append(torch.empty(L.lib().dexnerf_tc_packed_bytes(spec), dtype=torch.uint8, device=dev))
@@ -267,7 +279,7 @@ class Trainer:
         """fp32 master parameters -> the bf16 operand images both directions stream (3 launches per net)."""
         for i, (spec, prog) in enumerate(zip(self.specs, self.progs)):
             p = self._flat(self.params, i)
-            L.check(L.lib().dexnerf_tc_pack(spec, prog, L.ptr(p), L.ptr(self.blobs[i]), None, L.stream_ptr()), "tc_pack")
+            L.check(L.lib().dexnerf_tc_pack(spec, prog, L.ptr(p), L.ptr(self.blobs[i]), L.stream_ptr()), "tc_pack")
             L.launch_count += 1
             L.check(L.lib().dexnerf_tc_pack_bwd(spec, prog, L.ptr(p), L.ptr(self.blobs_t[i]), L.stream_ptr()),
                     "tc_pack_bwd")
@@ -284,7 +296,8 @@ class Trainer:
                     lin.bias.copy_(flat[op.b_off:op.b_off + fout])
 
     def learning_rate(self):
-        return learning_rate(self.lr, self.iteration, self.lr_decay, self.lr_decay_factor)
+        """The rate the next step uses (what the reference's optimizer.param_groups[0]["lr"] holds)."""
+        return self._lr_now
 
     # -- checkpoints in the reference's format (train_dexnerf_rgb.py:442-457 / :167-174) --------
     def _param_slices(self):
@@ -304,7 +317,10 @@ class Trainer:
         """{iter, model_coarse_state_dict, model_fine_state_dict, optimizer_state_dict, loss, psnr} as the
         reference writes it: the state dicts have the reference's keys, and the optimizer entry is a
         torch.optim.Adam state_dict over coarse + fine parameters, so the reference's script (or
-        torch.optim.Adam.load_state_dict) resumes from it."""
+        torch.optim.Adam.load_state_dict) resumes from it.  Conventions of the reference's writer: "iter" is the
+        0-based loop index of the iteration just finished (k - 1 after k steps; :443), Adam's per-parameter
+        "step" is the number of updates made, and the param_group "lr" is the rate set after that iteration
+        (:283-289), i.e. the one the next iteration uses."""
         self.sync_to_modules()
         state, idx = {}, 0
         for w_off, b_off, lin in self._param_slices():
@@ -317,15 +333,15 @@ class Trainer:
                 ea, es = self.exp_avg[off:off + n].view(shape), self.exp_avg_sq[off:off + n].view(shape)
                 if is_w:
                     ea, es = ea.t(), es.t()
-                state[idx] = {"step": torch.tensor(float(self.iteration)), "exp_avg": ea.contiguous().clone(),
+                state[idx] = {"step": torch.tensor(float(self.adam_steps)), "exp_avg": ea.contiguous().clone(),
                               "exp_avg_sq": es.contiguous().clone()}
                 idx += 1
-        group = {"lr": self.learning_rate() if self.iteration else self.lr, "betas": self.betas, "eps": self.eps,
+        group = {"lr": self._lr_now, "betas": self.betas, "eps": self.eps,
                  "weight_decay": 0, "amsgrad": False, "maximize": False, "foreach": None, "capturable": False,
                  "differentiable": False, "fused": None, "decoupled_weight_decay": False, "params": list(range(idx))}
-        if self.iteration == 0:
+        if self.adam_steps == 0:
             state = {}
-        return {"iter": self.iteration, "model_coarse_state_dict": self.models[0].state_dict(),
+        return {"iter": max(self.iteration - 1, 0), "model_coarse_state_dict": self.models[0].state_dict(),
                 "model_fine_state_dict": self.models[1].state_dict(),
                 "optimizer_state_dict": {"state": state, "param_groups": [group]}, "loss": loss, "psnr": psnr}
 
@@ -356,117 +372,140 @@ class Trainer:
                     ea, es = ea.t().contiguous(), es.t().contiguous()
                 self.exp_avg[off_:off_ + n].copy_(ea.reshape(-1))
                 self.exp_avg_sq[off_:off_ + n].copy_(es.reshape(-1))
+        # resume as the reference script does (train_dexnerf_rgb.py:167-178): the loop restarts AT index `iter`,
+        # the optimizer keeps its own step counter and the rate of its restored param_group
         self.iteration = int(ckpt.get("iter", 0))
+        steps = [float(st["step"]) for st in state.values() if "step" in st]
+        self.adam_steps = int(max(steps)) if steps else 0
+        groups = (ckpt.get("optimizer_state_dict") or {}).get("param_groups") or []
+        self._lr_now = float(groups[0]["lr"]) if groups and "lr" in groups[0] else self.lr
         self._repack()
 
     # -- one iteration ------------------------------------------------------------------------
-    def _forward(self, i, ro, rd, vd, z, noise, white):
-        n, S = z.shape
-        spec = self.specs[i]
-        nbytes = L.lib().dexnerf_tc_tape_bytes(spec, n * S)
-        tape = torch.empty(nbytes, dtype=torch.uint8, device=z.device)
-        rf = torch.empty((n, S, 4), dtype=torch.float32, device=z.device)
-        with _timed("mlp_tc_train_fwd", n, S):
-            L.check(L.lib().dexnerf_tc_query_train(spec, L.ptr(self.blobs[i]), L.ptr(ro), L.ptr(rd), L.ptr(vd), L.ptr(z),
-                                                   n, S, L.ptr(rf), L.ptr(tape), L.stream_ptr()), "tc_query_train")
-        o = render_maps(rf, z, rd, noise, white, None, 0, want_weights=(i == 0))
-        return rf, tape, o
+    def _chunk_buffers(self, n):
+        """Device buffers of one ray chunk of `n` rays (cached per size; a training loop uses one size): the
+        workspace of the fused render call, the two tapes, the rgb predictions, their gradients and the
+        d(radiance field) scratch."""
+        from . import render
+        buf = self._chunks.get(n)
+        if buf is None:
+            opt = self.cfg.nerf.train
+            Nc, Nf = int(opt.num_coarse), int(opt.num_fine)
+            dev = self.params.device
+            self._chunks.clear()                      # a new size replaces the old buffers (tapes are GBs)
+            tapes = []
+            for spec, S in zip(self.specs, (Nc, Nc + Nf)):
+                nbytes = L.lib().dexnerf_tc_tape_bytes(spec, n * S)
+                if nbytes < 0:
+                    raise L.DexNerfError("tc_tape_bytes: " + L.lib().dexnerf_last_error().decode())
+                tapes.append(torch.empty(nbytes, dtype=torch.uint8, device=dev))
+            buf = dict(ws=torch.empty(render.workspace_bytes(n, Nc, Nf), dtype=torch.uint8, device=dev), tapes=tapes,
+                       rgb=torch.empty((2, n, 3), dtype=torch.float32, device=dev),
+                       g_rgb=torch.empty((2, n, 3), dtype=torch.float32, device=dev),
+                       d_rf=torch.empty((n, Nc + Nf, 4), dtype=torch.float32, device=dev))
+            self._chunks[n] = buf
+        return buf
 
-    def _backward(self, i, rf, tape, z, rd, noise, white, g_rgb):
-        n, S = z.shape
-        d_rf = volume_render_backward(rf, z, rd, noise, white, g_rgb, None, None)
-        g = self._flat(self.grads, i)
-        for bit, name in ((1, "mlp_tc_bwd_dx"), (2, "mlp_tc_bwd_dw")):
-            with _timed(name, n, S):
-                L.check(L.lib().dexnerf_tc_backward(self.specs[i], self.progs[i], L.ptr(self.blobs[i]),
-                                                    L.ptr(self.blobs_t[i]), L.ptr(tape), L.ptr(d_rf), n, S, L.ptr(g),
-                                                    bit, 0, L.stream_ptr()), "tc_backward")
-
-    def step(self, ray_origins, ray_directions, target, rng=None):
-        """One iteration on pre-selected rays (n,3) / targets (n,3).  Returns the loss tensor
-        [total, coarse, fine] (device, overwritten by the next step).  `rng` replays the four draws.
-        Batches larger than `cfg.nerf.train.chunksize` rays are processed in chunks (the tape of a chunk
-        is 10 KB per sample) whose gradients accumulate in the flat buffer before the single Adam step."""
-        rng = rng or {}
+    def _render_params(self, n, buf, ro, rd, rng, height, width, focal_length):
+        from . import render
         opt = self.cfg.nerf.train
+        p = L.RenderParams()
+        render.fill_common(p, opt, self.cfg, True, height, width, focal_length, None, 0)
+        p.n = n
+        p.ro, p.rd = ro.data_ptr(), rd.data_ptr()
+        keep = []
+        for i, m in enumerate(self.models):
+            ref, k = render.model_ref(m, self.ex, self.ed, "bf16",
+                                      blobs=(self.blobs[i], self.blobs_t[i], self._flat(self.params, i)))
+            keep.append(k)
+            if i == 0:
+                p.coarse = ref
+            else:
+                p.fine = ref
+        p.t_rand, p.u = L.ptr(rng.get("t_rand")).value, L.ptr(rng.get("u")).value
+        p.noise_coarse, p.noise_fine = L.ptr(rng.get("noise_coarse")).value, L.ptr(rng.get("noise_fine")).value
+        p.offset = render.next_philox_offset()
+        p.tape_coarse, p.tape_fine = buf["tapes"][0].data_ptr(), buf["tapes"][1].data_ptr()
+        p.workspace, p.workspace_bytes = buf["ws"].data_ptr(), buf["ws"].numel()
+        p.rgb_coarse, p.rgb_fine = buf["rgb"][0].data_ptr(), buf["rgb"][1].data_ptr()
+        return p, keep
+
+    def step(self, ray_origins, ray_directions, target, rng=None, height=None, width=None, focal_length=None):
+        """One iteration on pre-selected rays (n,3) / targets (n,3).  Returns the loss tensor
+        [total, coarse, fine] (device, overwritten by the next step).  `rng` replays the four draws; without it
+        they come from the Philox generator of the setup launch.
+        Batches larger than `cfg.nerf.train.chunksize` rays are processed in chunks (the tape of a chunk
+        is 10 KB per sample) whose gradients accumulate in the flat buffer before the single Adam step.
+        With `cfg.dataset.no_ndc: False` (the LLFF configs) the rays are warped by ndc_rays exactly as
+        run_one_iter_of_nerf does (train_utils.py:238-242), which needs `height`, `width` and `focal_length`."""
+        rng = {k: L.dev_f32(v, k) for k, v in (rng or {}).items() if v is not None}
+        opt = self.cfg.nerf.train
+        if self.cfg.dataset.no_ndc is False and (height is None or width is None or focal_length is None):
+            raise L.DexNerfError("Trainer.step: cfg.dataset.no_ndc is False - pass height, width and focal_length "
+                                 "(ndc_rays needs them, train_utils.py:238-242)")
         ro = L.dev_f32(ray_origins.reshape(-1, 3), "ray_origins")
         rd = L.dev_f32(ray_directions.reshape(-1, 3), "ray_directions")
         tgt = L.dev_f32(target[..., :3].reshape(-1, 3), "target")
         n_total = ro.shape[0]
         chunk = int(getattr(opt, "chunksize", n_total) or n_total)
         self.loss.zero_()
-        self.grads.zero_()
+        if self.keep_grads:
+            self.grads.zero_()        # otherwise the previous Adam launch has already cleared them
         starts = list(range(0, n_total, chunk))
         pending = []
         for start in starts:
             sl = slice(start, min(start + chunk, n_total))
-            sub = {k: v[sl] for k, v in rng.items() if v is not None}
+            sub = {k: v[sl] for k, v in rng.items()}
             # the fine network's backward runs first: on the last chunk its gradients are final as soon as its
             # weight-gradient GEMM is enqueued, so their all-reduce overlaps the coarse network's backward
             after_fine = None
             if self.world > 1 and start == starts[-1]:
                 after_fine = lambda: pending.append(self._allreduce_async(self._flat(self.grads, 1)))
-            self._accumulate(ro[sl], rd[sl], tgt[sl], sub, n_total, after_fine)
+            self._accumulate(ro[sl], rd[sl], tgt[sl], sub, n_total, after_fine, height, width, focal_length)
         if self.world > 1:
             pending.append(self._allreduce_async(self._flat(self.grads, 0)))
             for work in pending:
                 work.wait()              # stream-level wait: the Adam launch below is ordered after both
         # Adam with the script's schedule: iteration i steps with the rate set after iteration i-1 (:283-289)
-        lr = learning_rate(self.lr, self.iteration - 1, self.lr_decay, self.lr_decay_factor) if self.iteration else self.lr
+        lr = self._lr_now
+        self.adam_steps += 1
+        adam = L.lib().dexnerf_adam_step if self.keep_grads else L.lib().dexnerf_adam_step_zero_grad
+        L.check(adam(L.ptr(self.params), L.ptr(self.grads), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq),
+                     self.params.numel(), lr, self.betas[0], self.betas[1], self.eps, self.adam_steps, 1.0 / self.world,
+                     L.stream_ptr()), "adam_step")
+        self._lr_now = learning_rate(self.lr, self.iteration, self.lr_decay, self.lr_decay_factor)
         self.iteration += 1
-        L.check(L.lib().dexnerf_adam_step(L.ptr(self.params), L.ptr(self.grads), L.ptr(self.exp_avg),
-                                          L.ptr(self.exp_avg_sq), self.params.numel(), lr, self.betas[0], self.betas[1],
-                                          self.eps, self.iteration, 1.0 / self.world, L.stream_ptr()), "adam_step")
         self._repack()
-        self.loss[0:1] = self.loss[1:2] + self.loss[2:3]
         return self.loss
 
     def _allreduce_async(self, buf):
         import torch.distributed as dist
         return dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
-    def _accumulate(self, ro, rd, tgt, rng, n_total, after_fine=None):
-        """Forward + backward of one ray chunk; loss terms and gradients accumulate."""
-        opt = self.cfg.nerf.train
+    def _accumulate(self, ro, rd, tgt, rng, n_total, after_fine=None, height=None, width=None, focal_length=None):
+        """Forward + backward of one ray chunk: ONE fused forward call (6 launches: setup incl. the Philox draws,
+        two queries with tape, two compositings, resampling), one loss launch, the backward chains of the fine
+        and then the coarse network (3 launches each); loss terms and gradients accumulate."""
+        from . import render
         ro, rd, tgt = ro.contiguous(), rd.contiguous(), tgt.contiguous()
-        n, dev = ro.shape[0], ro.device
-        Nc, Nf = int(opt.num_coarse), int(opt.num_fine)
-        std, white = float(opt.radiance_field_noise_std), bool(opt.white_background)
-        vd = rd / rd.norm(p=2, dim=-1, keepdim=True)
-        near = torch.full((n,), float(self.cfg.dataset.near), dtype=torch.float32, device=dev)
-        far = torch.full((n,), float(self.cfg.dataset.far), dtype=torch.float32, device=dev)
-        t_rand = None
-        if opt.perturb:
-            t_rand = rng.get("t_rand")
-            if t_rand is None:
-                t_rand = torch.rand((n, Nc), dtype=torch.float32, device=dev)
-            t_rand = L.dev_f32(t_rand, "t_rand")
-        z = torch.empty((n, Nc), dtype=torch.float32, device=dev)
-        L.check(L.lib().dexnerf_stratified_z(n, Nc, 0.0, 0.0, L.ptr(near), L.ptr(far), int(bool(opt.lindisp)),
-                                             L.ptr(t_rand), L.ptr(z), L.stream_ptr()), "stratified_z")
-        noise_c = rng.get("noise_coarse")
-        if noise_c is None and std > 0.0:
-            noise_c = torch.randn((n, Nc), dtype=torch.float32, device=dev) * std
-        noise_c = L.dev_f32(noise_c, "noise_coarse", allow_none=True)
-        rf_c, tape_c, oc = self._forward(0, ro, rd, vd, z, noise_c, white)
-        u = rng.get("u")
-        if u is None and opt.perturb != 0.0:
-            u = torch.rand((n, Nf), dtype=torch.float32, device=dev)
-        u = L.dev_f32(u, "u", allow_none=True)
-        z_fine = torch.empty((n, Nc + Nf), dtype=torch.float32, device=dev)
-        L.check(L.lib().dexnerf_resample_merge(L.ptr(z), L.ptr(oc["weights"]), n, Nc, Nf, L.ptr(u), L.ptr(z_fine),
-                                               L.stream_ptr()), "resample_merge")
-        noise_f = rng.get("noise_fine")
-        if noise_f is None and std > 0.0:
-            noise_f = torch.randn((n, Nc + Nf), dtype=torch.float32, device=dev) * std
-        noise_f = L.dev_f32(noise_f, "noise_fine", allow_none=True)
-        rf_f, tape_f, of = self._forward(1, ro, rd, vd, z_fine, noise_f, white)
+        n = ro.shape[0]
+        buf = self._chunk_buffers(n)
+        p, keep = self._render_params(n, buf, ro, rd, rng, height, width, focal_length)
+        lib, stream = L.lib(), L.stream_ptr()
+        ev = self.timing
+        p.events = ev[0].pointer() if ev else None
+        L.check(lib.dexnerf_render_fused_fwd(C.byref(p), stream), "render_fused_fwd")
+        L.launch_count += 5 + p.ndc
         # loss = mse(rgb_coarse, target) + mse(rgb_fine, target)  (train_dexnerf_rgb.py:264-277)
-        g_c, g_f = torch.empty_like(oc["rgb"]), torch.empty_like(of["rgb"])
-        for pred, g, slot in ((oc["rgb"], g_c, 1), (of["rgb"], g_f, 2)):
-            L.check(L.lib().dexnerf_mse_loss_grad(L.ptr(pred), L.ptr(tgt), pred.numel(), 3 * n_total, L.ptr(g),
-                                                  L.ptr(self.loss[slot:slot + 1]), L.stream_ptr()), "mse_loss_grad")
-        self._backward(1, rf_f, tape_f, z_fine, rd, noise_f, white, g_f)
-        if after_fine is not None:
-            after_fine()
-        self._backward(0, rf_c, tape_c, z, rd, noise_c, white, g_c)
+        g = buf["g_rgb"]
+        L.check(lib.dexnerf_mse_loss_pair(L.ptr(buf["rgb"][0]), L.ptr(buf["rgb"][1]), L.ptr(tgt), 3 * n, 3 * n_total,
+                                          L.ptr(g[0]), L.ptr(g[1]), L.ptr(self.loss), stream), "mse_loss_pair")
+        p.events = ev[1].pointer() if ev else None
+        gc, gf = self._flat(self.grads, 0), self._flat(self.grads, 1)
+        for which in (1, 2):
+            L.check(lib.dexnerf_render_fused_bwd(C.byref(p), L.ptr(g[0]), L.ptr(g[1]), L.ptr(buf["d_rf"]), L.ptr(gc),
+                                                 L.ptr(gf), which, stream), "render_fused_bwd")
+            L.launch_count += 2
+            if which == 1 and after_fine is not None:
+                after_fine()
+        del keep

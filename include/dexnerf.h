@@ -28,7 +28,7 @@ extern "C" {
 #define DEXNERF_API
 #endif
 
-#define DEXNERF_ABI_VERSION 1
+#define DEXNERF_ABI_VERSION 2
 #define DEXNERF_E_INVALID (-1) /* bad argument (null pointer, unsupported size) */
 #define DEXNERF_E_CUDA (-2)    /* a CUDA runtime call or launch failed */
 #define DEXNERF_E_UNSUPPORTED (-3)
@@ -131,13 +131,12 @@ typedef struct {
 } dexnerf_flexible_spec;
 /* size in bytes of the packed weight blob for `spec` (negative on error) */
 DEXNERF_API int64_t dexnerf_tc_packed_bytes(const dexnerf_flexible_spec* spec /*host*/);
-#define DEXNERF_TC_PACK_WORKSPACE_BYTES 16384
 /* params: the fp32 program-layout buffer of the same model (as for dexnerf_mlp_query);
- * prog: the program it was built from.  packed: device blob of dexnerf_tc_packed_bytes();
- * workspace: unused since ABI revision 1.1 (may be NULL); packing is stream-ordered like every other
- * entry point (the layout tables travel as kernel parameters). */
+ * prog: the program it was built from.  packed: device blob of dexnerf_tc_packed_bytes().  Packing is
+ * stream-ordered like every other entry point (the layout tables travel as kernel parameters; ABI 2 dropped the
+ * unused workspace argument of ABI 1). */
 DEXNERF_API int dexnerf_tc_pack(const dexnerf_flexible_spec* spec, const dexnerf_mlp_program* prog,
-                    const float* params, void* packed, void* workspace, void* stream);
+                    const float* params, void* packed, void* stream);
 /* run_network on tensor cores: ro, rd, viewdirs (n,3), z (n,S) -> rf (n,S,4).
  * dbg (optional, may be NULL): raw fp32 accumulator of (dbg_layer, dbg_pass), [n*S rounded up to
  * 128][128] floats - used by the kernel's own tests. */
@@ -179,6 +178,86 @@ DEXNERF_API int dexnerf_tc_backward(const dexnerf_flexible_spec* spec, const dex
                         const void* packed, const void* packed_t, void* tape, const float* d_rf,
                         int64_t n, int S, float* grads, int what, int variant, void* stream);
 
+/* ---- a-9  the render driver as ONE call per ray chunk (nerf/train_utils.py:92-202 predict_and_render_radiance
+ * driven by :205-288 run_one_iter_of_nerf).  The reference runs ~200 eager kernels per chunk; here the host side
+ * of the library sequences the kernels of this header on `stream` with no torch glue in between:
+ *
+ *   ray setup (one launch: optional ray generation from a camera, view directions rd/|rd| (:222-226), the
+ *     stratified depths (:111-133) and - in train mode - the Philox draws t_rand / u / sigma noise)
+ *   [ndc_rays first when `ndc` is set (:238-242; near is 1.0 as in the reference)]
+ *   -> coarse MLP query -> coarse compositing -> resample + merge -> fine MLP query -> fine compositing (+ Dex depth)
+ *
+ * Rays: explicit arrays ro, rd (n,3) - or ro == NULL and a camera (T_w2c, K, H, W, row0, rows; n = rows * W), in
+ * which case get_ray_bundle (a-1) is part of the setup launch and a frame is 6 launches in total.
+ * RNG: t_rand (n,Nc), u (n,Nf), noise_coarse (n,Nc), noise_fine (n,Nc+Nf) replay given draws (parity tests; the
+ * noises are pre-scaled by the std); a NULL pointer means "draw in the setup kernel" with Philox4x32-10
+ * keyed by (seed, offset) when perturb / noise_std ask for it (perturb: jittered depths AND random u,
+ * train_utils.py:126-133,169).
+ * Models: `spec`/`packed` select the tensor-core path (bf16 operands), spec == NULL the fp32 CUDA-core path
+ * (`prog`/`params`).  tape_coarse / tape_fine (dexnerf_tc_tape_bytes each; tensor-core path only) make the two
+ * queries record the training tape; NULL = inference.
+ * Workspace: dexnerf_render_workspace_bytes(n, Nc, Nf) bytes, 256-byte aligned; dexnerf_render_workspace_layout
+ * describes where the intermediates (rays, view directions, depths, radiance fields, weights, noises) live, for
+ * dexnerf_render_fused_bwd and for tests.
+ * Outputs (device, any may be NULL): rgb (n,3), depth (n) [the EXPECTED depth, train_utils.py:201], acc (n) of both
+ * passes; dex_fine: T planes, plane t at dex_fine + t * dex_stride (dex_stride >= n lets a chunk write its columns
+ * of a (T, n_total) tensor). */
+typedef struct {
+  const dexnerf_mlp_program* prog;   /* host */
+  const float* params;               /* device: fp32 program-layout buffer (fp32 path; also the source of `packed`) */
+  const dexnerf_flexible_spec* spec; /* host; NULL = fp32 CUDA-core path */
+  const void* packed;                /* device: dexnerf_tc_pack blob (tensor-core path) */
+  const void* packed_t;              /* device: dexnerf_tc_pack_bwd blob (dexnerf_render_fused_bwd only) */
+} dexnerf_model_ref;
+
+typedef struct {
+  int64_t n;
+  const float* ro; const float* rd;          /* (n,3) each, or NULL with a camera */
+  const float* T_w2c; const float* K;        /* device 4x4 / 3x3, camera form */
+  int32_t H, W, row0, rows;
+  int32_t use_viewdirs, ndc;
+  float focal, near, far;
+  int32_t Nc, Nf, lindisp, perturb, white_background;
+  float noise_std;
+  const float* thresholds; int32_t T; int32_t pad0_;
+  const float* t_rand; const float* u; const float* noise_coarse; const float* noise_fine;
+  uint64_t seed, offset;
+  dexnerf_model_ref coarse, fine;
+  void* tape_coarse; void* tape_fine;
+  void* workspace; int64_t workspace_bytes;
+  float* rgb_coarse; float* depth_coarse; float* acc_coarse;
+  float* rgb_fine; float* depth_fine; float* acc_fine;
+  float* dex_fine; int64_t dex_stride;
+  /* optional per-launch timing (benchmarks): host array of 2 * DEXNERF_RENDER_LAUNCHES events made by
+   * dexnerf_event_create; events[2k] / events[2k+1] are recorded before / after launch k (order: setup, ndc,
+   * coarse query, coarse compositing, resample, fine query, fine compositing).  NULL = no events. */
+  void** events;
+} dexnerf_render_params;
+#define DEXNERF_RENDER_LAUNCHES 7
+DEXNERF_API void* dexnerf_event_create(void);                 /* cudaEvent_t with timing, NULL on failure */
+DEXNERF_API void dexnerf_event_destroy(void* ev);
+DEXNERF_API float dexnerf_event_elapsed_ms(void* start, void* end); /* < 0 when not complete / never recorded */
+
+/* byte offsets into the workspace: [0] total, [1] ro, [2] rd, [3] viewdirs, [4] z_coarse, [5] rf_coarse,
+ * [6] weights_coarse, [7] z_fine, [8] rf_fine, [9] t_rand, [10] u, [11] noise_coarse, [12] noise_fine,
+ * [13] ro_raw, [14] rd_raw (the camera's rays before ndc_rays) */
+#define DEXNERF_RENDER_WS_SLOTS 16
+DEXNERF_API int64_t dexnerf_render_workspace_bytes(int64_t n, int Nc, int Nf);
+DEXNERF_API int dexnerf_render_workspace_layout(int64_t n, int Nc, int Nf, int64_t* out /*host, 16*/);
+/* the setup launch alone (what the training paths of nerf/training.py share with the fused call): fills the
+ * workspace slots ro / rd / viewdirs / z_coarse / t_rand / u / noise_* according to `p` */
+DEXNERF_API int dexnerf_ray_setup(const dexnerf_render_params* p /*host*/, void* stream);
+DEXNERF_API int dexnerf_render_fused_fwd(const dexnerf_render_params* p /*host*/, void* stream);
+/* backward of a dexnerf_render_fused_fwd call that recorded tapes (train_dexnerf_rgb.py:278 loss.backward()):
+ * g_rgb_coarse, g_rgb_fine (n,3) = dL/d(rgb maps) -> grads_coarse / grads_fine, fp32 buffers in the program layout,
+ * ACCUMULATED into.  d_rf_scratch: (n, Nc+Nf, 4) floats.  which: bit 0 = the fine network's chain, bit 1 = the
+ * coarse network's (3 = both, fine first: its gradient buffer is complete first, so a data-parallel caller can
+ * issue the two halves separately and start reducing the fine gradients while the coarse chain runs).
+ * 3 launches per network: compositing backward, activation-gradient chain, weight-gradient GEMM. */
+DEXNERF_API int dexnerf_render_fused_bwd(const dexnerf_render_params* p /*host*/, const float* g_rgb_coarse,
+                                         const float* g_rgb_fine, float* d_rf_scratch, float* grads_coarse,
+                                         float* grads_fine, int which, void* stream);
+
 /* ---- validation depth metrics (nerf/train_utils.py:9-30 compute_err_metric, looped over the
  * threshold candidates at train_dexnerf_rgb.py:391-404).  pred (T,n) threshold depth planes, gt (n),
  * mask (n) uint8 or NULL (= the reference's (gt > 0) & (gt < 1.25)).  out (T,4) =
@@ -201,6 +280,11 @@ DEXNERF_API int dexnerf_depth_error_image(const float* est, const float* gt, con
  * `step` counts from 1; grads are multiplied by grad_scale first (1 / world for data parallel). */
 DEXNERF_API int dexnerf_mse_loss_grad(const float* pred, const float* target, int64_t count, int64_t total_count,
                           float* grad, float* loss_accum, void* stream);
+/* both loss terms of train_dexnerf_rgb.py:264-277 in one launch: loss3 = [total, coarse, fine] ACCUMULATES
+ * sum((pred - target)^2) / total_count of each prediction (total = coarse + fine); grads as above. */
+DEXNERF_API int dexnerf_mse_loss_pair(const float* pred_coarse, const float* pred_fine, const float* target,
+                          int64_t count, int64_t total_count, float* grad_coarse, float* grad_fine, float* loss3,
+                          void* stream);
 /* nn.Linear tensors -> the flat program-layout buffer in one launch.  ptr_table: DEVICE array of 2*n_ops
  * pointers (weight (out,in) row-major, bias) in op order; flat: the buffer dexnerf_mlp_query / tc_pack read. */
 DEXNERF_API int dexnerf_pack_params(const dexnerf_mlp_program* prog /*host*/, const void* ptr_table, float* flat,
@@ -208,6 +292,12 @@ DEXNERF_API int dexnerf_pack_params(const dexnerf_mlp_program* prog /*host*/, co
 DEXNERF_API int dexnerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                       float lr, float beta1, float beta2, float eps, int64_t step, float grad_scale,
                       void* stream);
+
+/* dexnerf_adam_step that also clears `grads` as it consumes them (the weight-gradient GEMMs accumulate, so the
+ * next iteration needs no memset launch) */
+DEXNERF_API int dexnerf_adam_step_zero_grad(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                float lr, float beta1, float beta2, float eps, int64_t step, float grad_scale,
+                                void* stream);
 
 #ifdef __cplusplus
 }

@@ -377,6 +377,39 @@ def gen_lego():
     print("lego_lowres.npz")
 
 
+def gen_lego_frame():
+    """The same trained lego-lowres checkpoint on a 40x48 view (1 920 rays x 20 thresholds): enough rays for the
+    Dex-depth flip-rate table of the bf16 tensor-core path.  Weights are NOT stored again
+    (lego_lowres.npz holds them); outputs only."""
+    ck = torch.load(os.path.join(REF, "pretrained/lego-lowres/checkpoint199999.ckpt"),
+                    map_location="cpu", weights_only=False)
+    mc = ref.models.FlexibleNeRFModel(num_encoding_fn_xyz=10, num_encoding_fn_dir=4)
+    mf = ref.models.FlexibleNeRFModel(num_encoding_fn_xyz=10, num_encoding_fn_dir=4)
+    mc.load_state_dict(ck["model_coarse_state_dict"])
+    mf.load_state_dict(ck["model_fine_state_dict"])
+    H, W = 40, 48
+    sys.path.insert(0, os.path.join(HERE, "..", ".."))
+    from oracle.nerf_oracle import pose_spherical_world2cam
+    T = pose_spherical_world2cam(30.0, -30.0, 4.0)
+    K = torch.tensor([[56.0, 0, 24.0], [0, 56.0, 20.0], [0, 0, 1]])
+    ro, rd = ref.get_ray_bundle(H, W, None, T, K)
+    thr = [float(m) for m in np.arange(5, 105, 5)]
+    cfg = make_cfg(64, 64, 2.0, 6.0, False, 0.0, True, False)
+    with torch.no_grad():
+        res = ref.run_one_iter_of_nerf(H, W, 56.0, mc, mf, ro, rd, cfg, mode="validation",
+                                       encode_position_fn=ref.get_embedding_function(10, True, True),
+                                       encode_direction_fn=ref.get_embedding_function(4, True, True),
+                                       m_thres_cand=thr)
+    out = dict(T=npy(T), K=npy(K), HW=np.array([H, W]), thr=np.array(thr, dtype=np.float32))
+    for nme, v in zip(["rgb_c", "depth_c", "acc_c", "rgb_f", "depth_f", "acc_f"], res[:6]):
+        out[nme] = npy(v)
+    out["dex"] = np.stack([npy(v) for v in res[6:]], 0)
+    print("lego frame acc_f mean", float(res[5].mean()), "dex>near frac",
+          float((res[6] > 2.0 + 1e-6).float().mean()), float((res[-1] > 2.0 + 1e-6).float().mean()))
+    np.savez_compressed(os.path.join(HERE, "lego_frame.npz"), **out)
+    print("lego_frame.npz")
+
+
 def gen_tiny():
     """BASELINE config 1 shrunk to 20x20: tiny_nerf.py functions with a 5-arg get_ray_bundle."""
     H = W = 20
@@ -545,6 +578,7 @@ if __name__ == "__main__":
     gen_models()
     gen_pipeline()
     gen_lego()
+    gen_lego_frame()
     gen_tiny()
     gen_train_grads()
     gen_next_rows()

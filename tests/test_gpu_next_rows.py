@@ -25,6 +25,13 @@ def test_depth_error_metrics_golden(golden):
                                g["metric_errs"][3], rtol=2e-5, atol=1e-7)
     idx, err, tab = nerf.select_dex_threshold(planes, gt)
     assert idx == int(g["metric_best"]) and abs(err["depth_abs_err"] - g["metric_errs"][idx, 0]) < 1e-4
+    # exactly as the reference script calls it (train_dexnerf_rgb.py:391-404): gt_depth_torch = depth_target.cpu(),
+    # pred_depth_torch = depth_fine_dex[cand].detach().cpu(), a CPU bool mask
+    gt_cpu, mask_cpu = gt.cpu(), ((gt > 0) & (gt < 1.25)).cpu()
+    for cand in (0, 3):
+        e_cpu = nerf.compute_err_metric(gt_cpu, planes[cand].detach().cpu(), mask_cpu)
+        np.testing.assert_allclose([e_cpu[k] for k in ("depth_abs_err", "depth_err2", "depth_err4", "depth_err8")],
+                                   g["metric_errs"][cand], rtol=2e-5, atol=1e-7)
 
 
 def test_depth_error_metrics_full_frame_vs_oracle():

@@ -89,19 +89,23 @@ def test_small_scene_train_replayed_rng(golden):
     ex, ed = nerf.get_embedding_function(6, True, True), nerf.get_embedding_function(4, True, True)
     rng = dict(t_rand=t(g["train_t_rand"]).cuda(), u=t(g["train_u"]).cuda(),
                noise_coarse=t(g["train_noise_c"]).cuda(), noise_fine=t(g["train_noise_f"]).cuda())
-    res = nerf.run_one_iter_of_nerf(H, W, 9.0, mc, mf, t(g["ro"]).reshape(-1, 3).cuda(),
-                                    t(g["rd"]).reshape(-1, 3).cuda(),
-                                    make_cfg(16, 24, 2.0, 6.0, perturb=True, noise_std=0.2), mode="train",
-                                    encode_position_fn=ex, encode_direction_fn=ed, m_thres_cand=g["thr"].tolist(),
-                                    rng=rng)
-    assert res[0].shape == (H * W, 3)                       # train mode stays flat
-    check(res, g, "train")
-    # without replay it must still run (Philox draws on the device) and give finite outputs
-    res = nerf.run_one_iter_of_nerf(H, W, 9.0, mc, mf, t(g["ro"]).reshape(-1, 3).cuda(),
-                                    t(g["rd"]).reshape(-1, 3).cuda(),
-                                    make_cfg(16, 24, 2.0, 6.0, perturb=True, noise_std=0.2), mode="train",
-                                    encode_position_fn=ex, encode_direction_fn=ed, m_thres_cand=g["thr"].tolist())
+    args = (H, W, 9.0, mc, mf, t(g["ro"]).reshape(-1, 3).cuda(), t(g["rd"]).reshape(-1, 3).cuda(),
+            make_cfg(16, 24, 2.0, 6.0, perturb=True, noise_std=0.2))
+    kw = dict(mode="train", encode_position_fn=ex, encode_direction_fn=ed, m_thres_cand=g["thr"].tolist())
+    with torch.no_grad():
+        res = nerf.run_one_iter_of_nerf(*args, rng=rng, **kw)
+        assert res[0].shape == (H * W, 3)                       # train mode stays flat
+        check(res, g, "train")
+        # without replay it must still run (Philox draws in the setup launch), give finite outputs, and draw
+        # fresh numbers on every call
+        res = nerf.run_one_iter_of_nerf(*args, **kw)
+        res2 = nerf.run_one_iter_of_nerf(*args, **kw)
     assert all(torch.isfinite(v).all() for v in res)
+    assert not torch.equal(res[3], res2[3])
+    # gradients for this configuration (fp32 precision, hidden 32) do not exist: the call must say so instead of
+    # returning outputs without a grad_fn
+    with pytest.raises(nerf.DexNerfError, match="not supported"):
+        nerf.run_one_iter_of_nerf(*args, rng=rng, **kw)
 
 
 def test_small_scene_ndc_no_viewdirs(golden):

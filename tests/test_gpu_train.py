@@ -485,6 +485,7 @@ def test_trainer_chunked_batch_equals_single_pass():
     cfg_a, cfg_b = make_cfg(nc, nf, 2.0, 6.0, True), make_cfg(nc, nf, 2.0, 6.0, True)
     cfg_b.nerf.train.chunksize = 40                     # 96 rays -> chunks of 40, 40, 16
     ta, tb = nerf.Trainer(mc, mf, cfg_a, ex, ed), nerf.Trainer(mc2, mf2, cfg_b, ex, ed)
+    ta.keep_grads = tb.keep_grads = True                # leave the gradients in place for the comparison below
     la, lb = ta.step(ro, rd, target, rng=rng).clone(), tb.step(ro, rd, target, rng=rng).clone()
     assert float((la - lb).abs().max()) < 1e-6
     assert rel_err(tb.grads, ta.grads) < 1e-5
@@ -520,7 +521,11 @@ def test_trainer_checkpoint_round_trip_with_torch_adam(tmp_path):
     torch.save(trainer.checkpoint_dict(loss=float(loss[0]), psnr=float(nerf.mse2psnr(float(loss[0])))), path)
     ckpt = torch.load(path, weights_only=False)
     assert set(ckpt) == {"iter", "model_coarse_state_dict", "model_fine_state_dict", "optimizer_state_dict", "loss", "psnr"}
-    assert ckpt["iter"] == 3 and set(ckpt["model_coarse_state_dict"]) == set(mk().state_dict())
+    # the reference's conventions: "iter" = 0-based index of the iteration just finished, Adam's "step" = updates made,
+    # param_group lr = the rate set after that iteration (train_dexnerf_rgb.py:283-289, 443)
+    assert ckpt["iter"] == 2 and set(ckpt["model_coarse_state_dict"]) == set(mk().state_dict())
+    assert float(ckpt["optimizer_state_dict"]["state"][0]["step"]) == 3.0
+    assert abs(ckpt["optimizer_state_dict"]["param_groups"][0]["lr"] - nerf.learning_rate(5e-3, 2, 250, 0.1)) < 1e-12
     # (a) the reference's resume path: modules + torch.optim.Adam
     mc2, mf2 = mk(), mk()
     mc2.load_state_dict(ckpt["model_coarse_state_dict"])
@@ -531,7 +536,8 @@ def test_trainer_checkpoint_round_trip_with_torch_adam(tmp_path):
     mc3, mf3 = mk(), mk()
     t3 = nerf.Trainer(mc3, mf3, cfg, ex, ed, lr=5e-3)
     t3.load_checkpoint_dict(ckpt)
-    assert t3.iteration == 3
+    # resumed as the reference script resumes: loop index = ckpt["iter"], Adam step and rate from the optimizer state
+    assert t3.iteration == 2 and t3.adam_steps == 3 and t3.learning_rate() == trainer.learning_rate()
     rng = draws()
     la = nerf.train_step(mc2, mf2, opt, ro, rd, target, cfg, ex, ed, m_thres_cand=[], rng=rng, height=8, width=8, focal=1.0)[0]
     lb = trainer.step(ro, rd, target, rng=rng)[0].clone()

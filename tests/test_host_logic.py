@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(handle, name), name
     assert sorted(L._SIGS) == declared          # the ctypes table binds exactly the header
-    assert L.lib().dexnerf_abi_version() == 1
+    assert L.lib().dexnerf_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
