@@ -11,8 +11,9 @@ A "step" renders one frame.  With N GPUs the image rows are block-partitioned ov
 bracketed by barrier + synchronize; the JSON line carries the device-timed throughput (`value`),
 the end-to-end throughput through the public `nerf` API with host buffers (`e2e`), the roofline
 of the dominant kernel (the fine-pass MLP query) and the CPU oracle timed on this box.
-`--impl reference` times the reference's CPU algorithm (the oracle port; the Python reference
-itself cannot travel to the GPU box) on a bounded sample of the same workload.
+`--impl reference` times the UNMODIFIED reference on the host cores (oracle/_ref, staged by
+oracle/make_ref.py and shipped to the GPU box; the oracle port only if that copy is absent) on a
+bounded sample of the same workload.
 """
 import argparse
 import json
@@ -35,7 +36,7 @@ FX = 1111.1
 THRESHOLDS = [float(m) for m in range(5, 105, 5)]
 FLOP_PER_EVAL = 2 * 593408                        # SURVEY.md section 8(d), unpadded
 FLOP_PER_RAY = (NC + NC + NF) * FLOP_PER_EVAL     # 303 824 896
-CPU_SAMPLE_RAYS = 16384
+CPU_SAMPLE_RAYS = 4096
 MODEL_ARGS = (8, 256, 4, 10, 4)                   # FlexibleNeRFModel(num_layers, hidden, skip, Lx, Ld)
 METRIC = "rays/sec render (64+128 samples, 8x256 MLP)"
 WORKLOAD = ("C2: full-paper NeRF render 800x800, 64 coarse + 128 fine samples, two 8x256 skip-4 "
@@ -180,8 +181,8 @@ class ClockSampler:
 
 
 def cpu_oracle_rays_per_s(n_rays=CPU_SAMPLE_RAYS, reps=1):
-    """The oracle (CPU port of the reference's algorithm) on a bounded sample of the C2 workload:
-    `n_rays` rays from the centre rows of the 800x800 camera, all host threads."""
+    """Fallback CPU leg when oracle/_ref is absent: the oracle (CPU port of the reference's algorithm) on a bounded
+    sample of the workload: `n_rays` rays from the centre rows of the camera, all host threads."""
     from oracle import nerf_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     T, K = camera()
@@ -191,7 +192,7 @@ def cpu_oracle_rays_per_s(n_rays=CPU_SAMPLE_RAYS, reps=1):
     mc, mf = state_dicts()
     sdc = {k: v.detach() for k, v in mc.state_dict().items()}
     sdf = {k: v.detach() for k, v in mf.state_dict().items()}
-    opts = O.RenderOptions(near=NEAR, far=FAR, num_coarse=NC, num_fine=NF, Lx=10, Ld=4, chunksize=65536)
+    opts = O.RenderOptions(near=NEAR, far=FAR, num_coarse=NC, num_fine=NF, Lx=10, Ld=4, chunksize=REF_CHUNK)
     fc = lambda x: O.flexible_forward(sdc, x, skip_connect_every=MODEL_ARGS[2])   # noqa: E731
     ff = lambda x: O.flexible_forward(sdf, x, skip_connect_every=MODEL_ARGS[2])   # noqa: E731
     with torch.no_grad():
@@ -201,29 +202,82 @@ def cpu_oracle_rays_per_s(n_rays=CPU_SAMPLE_RAYS, reps=1):
             t0 = time.perf_counter()
             O.render_rays(ro[start:start + n_rays], rd[start:start + n_rays], fc, ff, opts, THRESHOLDS)
             times.append(time.perf_counter() - t0)
-    return n_rays / statistics.median(times), torch.get_num_threads()
+    return n_rays / statistics.median(times), torch.get_num_threads(), [1e3 * x for x in times]
+
+
+REF_RAYS = 4096        # >= 4096 rays x 3 repetitions after one warm-up, chunksize 4096
+REF_CHUNK = 4096
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def reference_available():
+    return os.path.exists(os.path.join(REF_DIR, "MANIFEST.json"))
+
+
+def run_ref_runner(device, rays, reps, warmup, chunksize):
+    """The staged UNMODIFIED reference (oracle/_ref, recipe oracle/make_ref.py) in its own process - its package is
+    called `nerf` like this repository's.  Returns the runner's JSON dict or None."""
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_runner.py"), "--device", device, "--rays", str(rays),
+           "--reps", str(reps), "--warmup", str(warmup), "--scene", SCENE, "--chunksize", str(chunksize)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=1500)
+        if r.returncode != 0:
+            sys.stderr.write("ref_runner failed: %s\n" % r.stderr[-2000:])
+            return None
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:          # noqa: BLE001
+        sys.stderr.write("ref_runner failed: %r\n" % (e,))
+        return None
+
+
+def cpu_baseline(reps=3, warmup=1):
+    """The reference's CPU path on this box's host cores on a bounded sample (REF_RAYS rays of the centre rows, the
+    full coarse -> fine pipeline): the staged reference itself when oracle/_ref travelled here ("reference"), else
+    the oracle port ("port")."""
+    d = run_ref_runner("cpu", REF_RAYS, reps, warmup, REF_CHUNK) if reference_available() else None
+    if d is not None:
+        return {"value": d["rays_per_s"], "unit": "rays/s", "cores": d["cores"], "kind": "reference",
+                "sample": "%d rays of the same %s frame (centre rows), chunksize %d, median of %d repetitions after %d "
+                          "warm-up; the unmodified reference (oracle/_ref, sha256 manifest %s) with the repaired 8-layer "
+                          "forward" % (d["rays"], SCENE.upper(), REF_CHUNK, reps, warmup, "ok" if d["sha_ok"] else "MISMATCH"),
+                "ms": d["ms"]}
+    v, cores, ms = cpu_oracle_rays_per_s(REF_RAYS, reps=reps)
+    return {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
+            "sample": "%d rays of the same %s frame (centre rows), chunksize %d, median of %d repetitions after a 128-ray "
+                      "warm-up; oracle port (oracle/_ref not present)" % (REF_RAYS, SCENE.upper(), REF_CHUNK, reps), "ms": ms}
+
+
+def gpu_eager_baseline():
+    """The same unmodified reference code with device="cuda": a stream of eager ATen kernels on this B200 (the
+    reference has no GPU-specific code of its own).  ~A sixth of a frame per repetition, the YAMLs' chunksize."""
+    if not reference_available():
+        return None
+    d = run_ref_runner("cuda", 131072, 3, 1, 131072)
+    if d is None:
+        return None
+    return {"value": d["rays_per_s"], "unit": "rays/s", "kind": "reference code, torch eager on cuda:0",
+            "sample": "%d rays of the same %s frame (centre rows), chunksize 131072 (config/lego.yml:136), median of 3 "
+                      "repetitions after 1 warm-up" % (d["rays"], SCENE.upper()), "ms": d["ms"]}
 
 
 def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path, all host threads, each step a bounded
+    sample (REF_RAYS rays) of the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    T = []
-    cores = os.cpu_count() or 1
-    for i in range(args.warmup + args.steps):
-        v, cores = cpu_oracle_rays_per_s(CPU_SAMPLE_RAYS, reps=1)
-        if i >= args.warmup:
-            T.append(CPU_SAMPLE_RAYS / v)
-    ms = 1e3 * sum(T) / len(T)
-    value = CPU_SAMPLE_RAYS / (ms / 1e3)
-    sample = "%d rays of the %dx%d %s frame (centre rows) per step, full %d+%d pipeline" % (
-        CPU_SAMPLE_RAYS, W, H, SCENE.upper(), NC, NF)
+    base = cpu_baseline(reps=args.steps, warmup=args.warmup)
+    ms = sum(base["ms"]) / len(base["ms"])                                   # mean step, like the GPU arm
+    rays = int(round(base["value"] * statistics.median(base["ms"]) * 1e-3))  # rays per step (whole image rows)
+    value = rays / (ms / 1e3)
+    base = dict(base, value=value)
+    base.pop("ms", None)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value,
         "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": base,
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
@@ -297,6 +351,9 @@ def run_train(args, dist, rank, world, dev, quiet=False):
     if rank == 0:
         sampler.start()
     TR.event_log = []
+    from nerf import render as RD
+    if api == "trainer":
+        trainer.timing = (RD.Events(), RD.Events())      # per-launch events recorded by the library (last step is read)
     launches0 = L.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -312,6 +369,29 @@ def run_train(args, dist, rank, world, dev, quiet=False):
     for name, a, b, n, S in log:
         parts.setdefault("%s_S%d" % (name, S), []).append(a.elapsed_time(b))
     parts = {k: sum(v) / len(v) for k, v in parts.items()}
+    small = {}
+    if api == "trainer":
+        fw, bw = trainer.timing[0].elapsed_ms(), trainer.timing[1].elapsed_ms(RD.BWD_LAUNCH_NAMES)
+        trainer.timing = None
+        parts = {"mlp_tc_train_fwd_S%d" % NC: fw["mlp_coarse"], "mlp_tc_train_fwd_S%d" % (NC + NF): fw["mlp_fine"],
+                 "mlp_tc_bwd_dx_S%d" % NC: bw["mlp_bwd_dx_coarse"], "mlp_tc_bwd_dx_S%d" % (NC + NF): bw["mlp_bwd_dx_fine"],
+                 "mlp_tc_bwd_dw_S%d" % NC: bw["mlp_bwd_dw_coarse"], "mlp_tc_bwd_dw_S%d" % (NC + NF): bw["mlp_bwd_dw_fine"]}
+        small = {k: v for k, v in list(fw.items()) + list(bw.items()) if not k.startswith("mlp_")}
+    # multi-GPU correctness on record: after the same number of steps every rank must hold the same parameters
+    param_check = None
+    if api == "trainer":
+        cs = torch.stack((trainer.params.double().sum(), (trainer.params.double() ** 2).sum(),
+                          trainer.params.view(torch.int32).to(torch.int64).sum().double()))
+        if dist is not None:
+            allcs = [torch.empty_like(cs) for _ in range(world)]
+            dist.all_gather(allcs, cs)
+            same = all(torch.equal(allcs[0], c) for c in allcs)
+            param_check = {"ranks": world, "identical_across_ranks": bool(same), "sum": float(cs[0]), "sumsq": float(cs[1]),
+                           "int_view_sum": float(cs[2])}
+            assert same, "data-parallel ranks diverged: parameter checksums differ"
+        else:
+            param_check = {"ranks": 1, "identical_across_ranks": True, "sum": float(cs[0]), "sumsq": float(cs[1]),
+                           "int_view_sum": float(cs[2])}
     # end to end: ray indices + targets come from pinned host memory, the loss goes back to the host
     loss_pin = torch.empty((), dtype=torch.float32).pin_memory()
 
@@ -361,6 +441,9 @@ def run_train(args, dist, rank, world, dev, quiet=False):
                      "tensor_tflops": 3 * flop_fine / ((fw_ms + dx_ms + dw_ms) * 1e-3) / 1e12 if (fw_ms and dx_ms and dw_ms) else None,
                      "tensor_frac_of_sustained_peak": None},
         "clocks": clocks,
+        "param_checksum": param_check,
+        "non_mlp_ms": ms_dev - mlp_ms,
+        "small_kernel_ms": {k: round(v, 4) for k, v in sorted(small.items())},
     }
     if fw_ms and dx_ms and dw_ms:
         tape_bytes = TRAIN_RAYS * (NC + NF) / 128.0 * (666.0 + 646.0 + 1424.0) * 1024.0
@@ -422,7 +505,6 @@ def main():
 
     import nerf
     from nerf import _lib as L
-    from nerf import train_utils as TU
     if args.precision:
         nerf.set_precision(args.precision)
 
@@ -454,12 +536,14 @@ def main():
     T_pin, K_pin = T_cpu.pin_memory(), K_cpu.pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
+    from nerf import render as RD
+
     def step(T_, K_):
-        ro, rd = nerf.get_ray_bundle(H, W, None, T_, K_, row_start=row0, row_count=rows)
+        # the public API: nerf.render_camera = get_ray_bundle + run_one_iter_of_nerf for one camera, rays generated
+        # inside the setup launch (6 launches per frame, all of them this library's kernels)
         with torch.no_grad():
-            return nerf.run_one_iter_of_nerf(H, W, FX, mc, mf, ro, rd, cfg, mode="validation",
-                                             encode_position_fn=ex, encode_direction_fn=ed,
-                                             m_thres_cand=THRESHOLDS)
+            return nerf.render_camera(H, W, T_, K_, mc, mf, cfg, mode="validation", encode_position_fn=ex,
+                                      encode_direction_fn=ed, m_thres_cand=THRESHOLDS, row_start=row0, row_count=rows)
 
     def barrier():
         if dist is not None:
@@ -481,8 +565,15 @@ def main():
     barrier()
     if rank == 0:
         sampler.start()
-    TU.kernel_event_log = []
-    L.event_log = []
+    # per-launch CUDA events recorded by the library on the launching stream inside the timed region
+    ev_pool = [RD.Events() for _ in range(args.steps)]
+    ev_used = []
+
+    def hook(n):
+        e = ev_pool[len(ev_used) % len(ev_pool)]
+        ev_used.append((e, n))
+        return e
+    RD.event_hook = hook
     launches0 = L.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -491,15 +582,27 @@ def main():
         flush.zero_()
     e1.record()
     barrier()
-    hbm_log, L.event_log = L.event_log, None
+    RD.event_hook = None
     launches = L.launch_count - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms_dev = reduce_max(e0.elapsed_time(e1) / args.steps)
-    log, TU.kernel_event_log = TU.kernel_event_log, None
-    fine = [(a.elapsed_time(b), n, S, nm) for nm, a, b, n, S in log if S == NC + NF]
-    kern_ms = sum(x[0] for x in fine) / len(fine)
-    kern_name = fine[0][3]
-    all_mlp_ms = sum(a.elapsed_time(b) for _, a, b, _, _ in log) / args.steps
+    per_launch = {}
+    for e, n_ in ev_used:
+        for name, ms in e.elapsed_ms().items():
+            per_launch.setdefault(name, []).append(ms)
+    per_launch = {k: sum(v) / len(v) for k, v in per_launch.items()}
+    n_rays_rank = rows * W
+    kern_ms = per_launch["mlp_fine"]
+    kern_name = "mlp_tc" if nerf.get_precision() == "bf16" else "mlp_simt"
+    all_mlp_ms = per_launch["mlp_fine"] + per_launch["mlp_coarse"]
+    fine = [(kern_ms, n_rays_rank, NC + NF, kern_name)]
+    # algorithmic HBM bytes of the small kernels: compositing 24 S + 36 + 4 T per ray in its
+    # full form (coarse: weights out, no Dex planes; fine: Dex planes, no weights), resampling 8 Nc + 4 (Nc + Nf)
+    hbm_bytes = {"composite_coarse": n_rays_rank * (NC * (16 + 4 + 4) + 12 + 24),
+                 "composite_fine": n_rays_rank * ((NC + NF) * (16 + 4) + 12 + 24 + 4 * len(THRESHOLDS)),
+                 "resample_merge": n_rays_rank * (8 * NC + 4 * (NC + NF)),
+                 "ray_setup": n_rays_rank * (36 + 4 * NC)}
+    hbm_log = [(k, per_launch[k], hbm_bytes[k]) for k in hbm_bytes if k in per_launch]
 
     # ------------------------------------------------------------------ end to end (host buffers)
     out_pin = None
@@ -521,6 +624,36 @@ def main():
     ms_e2e = reduce_max(e0.elapsed_time(e1) / args.steps)
     d2h = sum(o.numel() * o.element_size() for o in out_pin)
     h2d = (T_pin.numel() + K_pin.numel()) * 4
+
+    # ... and with the frame ASSEMBLED in one process (N > 1): every rank's row block is all-gathered over
+    # NVLink (nerf.gather_rows: rgb + the T Dex planes + expected depth + acc of the fine pass, what a consumer
+    # of the frame reads) and rank 0 copies the full planes to pinned host memory
+    ms_gathered, gathered_bytes = None, None
+    if dist is not None:
+        from nerf.sharding import gather_rows
+        full_pin = None
+
+        def gathered_step():
+            nonlocal full_pin
+            res = step(T_pin.to(dev, non_blocking=True), K_pin.to(dev, non_blocking=True))
+            planes = torch.cat([res[3]] + [r.unsqueeze(-1) for r in res[4:]], dim=-1)     # (rows, W, 3 + 2 + T)
+            full = gather_rows(planes, H)
+            if rank == 0:
+                if full_pin is None:
+                    full_pin = torch.empty(full.shape, dtype=full.dtype).pin_memory()
+                full_pin.copy_(full, non_blocking=True)
+            return full
+        for _ in range(2):
+            gathered_step()
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            full = gathered_step()
+        e1.record()
+        barrier()
+        ms_gathered = reduce_max(e0.elapsed_time(e1) / args.steps)
+        gathered_bytes = full.numel() * 4
+        assert full.shape[0] == H
 
     # BASELINE config 4 rides along (a few training iterations; reported under "train_c4")
     train_line = None
@@ -555,24 +688,29 @@ def main():
             "clocks": clocks,
         }
         # the HBM-bound kernels of the step: achieved GB/s of algorithmic bytes against the measured copy peak
-        hbm = {}
-        for name, a, b, n_, S_, nbytes in hbm_log:
-            hbm.setdefault("%s_S%d" % (name, S_), []).append((a.elapsed_time(b), nbytes))
         line["hbm_kernels"] = {
-            k: {"ms": sum(x[0] for x in v) / len(v), "bytes": v[0][1],
-                "achieved_gbs": v[0][1] / (sum(x[0] for x in v) / len(v) * 1e-3) / 1e9,
-                "frac_of_hbm_peak": v[0][1] / (sum(x[0] for x in v) / len(v) * 1e-3) / 1e9 / pk["hbm"]}
-            for k, v in sorted(hbm.items())}
+            k: {"ms": ms, "bytes": nbytes, "achieved_gbs": nbytes / (ms * 1e-3) / 1e9,
+                "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / pk["hbm"]} for k, ms, nbytes in hbm_log}
+        line["kernel_ms_per_launch"] = {k: round(v, 4) for k, v in sorted(per_launch.items())}
+        if ms_gathered is not None:
+            line["e2e_gathered"] = {"value": rays / (ms_gathered * 1e-3), "unit": "rays/s", "ms_per_step": ms_gathered,
+                                    "gathered_bytes_per_step": gathered_bytes,
+                                    "what": "fine rgb + expected depth + acc + T Dex planes all-gathered to every rank "
+                                            "(NCCL), rank 0 copies the assembled frame to pinned host memory"}
         if train_line is not None:
-            line["train_c4"] = {k: train_line[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e")}
+            line["train_c4"] = {k: train_line[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "gpu_launches",
+                                                           "param_checksum", "non_mlp_ms", "small_kernel_ms")}
             line["train_c4"]["kernel_ms"] = train_line["roofline"]["kernel_ms"]
             line["train_c4"]["hbm_frac_of_peak"] = train_line["roofline"].get("frac")
             line["train_c4"]["tensor_frac_of_sustained_peak"] = train_line["roofline"].get("tensor_frac_of_sustained_peak")
         if not args.no_cpu_baseline:
-            v, cores = cpu_oracle_rays_per_s()
-            line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
-                                    "sample": "%d rays of the same %s frame (centre rows), 1 repetition after "
-                                              "a 128-ray warm-up" % (CPU_SAMPLE_RAYS, SCENE.upper())}
+            base = cpu_baseline(reps=3, warmup=1)
+            base.pop("ms", None)
+            line["cpu_baseline"] = base
+            if n_gpus == 1:
+                # the informative competitor: the same reference code as eager torch kernels on this GPU
+                torch.cuda.empty_cache()
+                line["ref_gpu_eager"] = gpu_eager_baseline()
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()

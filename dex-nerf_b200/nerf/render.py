@@ -15,6 +15,8 @@ _philox_offset = [0]   # advances once per fused call that draws random numbers 
 
 LAUNCH_NAMES = ("ray_setup", "ndc_rays", "mlp_coarse", "composite_coarse", "resample_merge", "mlp_fine",
                 "composite_fine")
+BWD_LAUNCH_NAMES = ("composite_bwd_fine", "mlp_bwd_dx_fine", "mlp_bwd_dw_fine", "composite_bwd_coarse",
+                    "mlp_bwd_dx_coarse", "mlp_bwd_dw_coarse")      # dexnerf_render_fused_bwd's event slots
 
 
 def workspace_bytes(n, Nc, Nf):
@@ -102,10 +104,10 @@ class Events:
     def pointer(self):
         return C.cast(self.arr, C.POINTER(C.c_void_p))
 
-    def elapsed_ms(self):
+    def elapsed_ms(self, names=LAUNCH_NAMES):
         """{launch name: ms} for the launches that ran in the last call (after a synchronize)."""
         lib, out = L.lib(), {}
-        for k, name in enumerate(LAUNCH_NAMES):
+        for k, name in enumerate(names):
             ms = lib.dexnerf_event_elapsed_ms(self.arr[2 * k], self.arr[2 * k + 1])
             if ms >= 0.0:
                 out[name] = float(ms)

@@ -32,6 +32,28 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(L.FlexibleSpec) == 48
 
 
+def test_render_params_layout_matches_a_c_compiler(tmp_path):
+    """dexnerf_render_params / dexnerf_model_ref as gcc lays them out from include/dexnerf.h against the ctypes
+    mirror in nerf/_lib.py (size and the offset of every field)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    fields = [n for n, _ in L.RenderParams._fields_]
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "dexnerf.h"', 'int main(void) {',
+           'printf("%zu %zu\\n", sizeof(dexnerf_render_params), sizeof(dexnerf_model_ref));']
+    src += ['printf("%%zu\\n", offsetof(dexnerf_render_params, %s));' % f for f in fields]
+    src += ['return 0; }']
+    c = tmp_path / "layout.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert int(out[0]) == ctypes.sizeof(L.RenderParams) and int(out[1]) == ctypes.sizeof(L.ModelRef)
+    for f, off in zip(fields, out[2:]):
+        assert getattr(L.RenderParams, f).offset == int(off), f
+
+
 def test_namespace_matches_reference():
     # names the reference scripts import (train_dexnerf_rgb.py:15-19, tiny_nerf.py:9)
     for name in ["CfgNode", "get_embedding_function", "get_ray_bundle", "img2mse", "meshgrid_xy", "models",
@@ -143,6 +165,55 @@ def test_cfgnode_schema():
     import yaml
     assert yaml.safe_load(cfg.dump())["nerf"]["train"]["num_coarse"] == 64
     assert getattr(nerf.models, cfg.models.coarse.type) is nerf.FlexibleNeRFModel
+
+
+def test_shipped_yaml_configs_load():
+    """Every YAML the reference ships (config/*.yml and pretrained/*/config.yml, copied verbatim to
+    tests/golden/configs as data fixtures) goes through CfgNode the way the scripts read it
+    (train_dexnerf_rgb.py:39-41 and the key list of SURVEY.md section 5): attribute access for every key a script
+    consumes, hasattr gates, getattr(cfg.nerf, mode), models constructible by name, dump() round trip."""
+    import glob
+    import yaml
+    files = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "configs", "*.yml")))
+    assert len(files) == 14
+    for path in files:
+        with open(path, "r") as f:
+            cfg = nerf.CfgNode(yaml.load(f, Loader=yaml.FullLoader))
+        assert isinstance(cfg.experiment.id, str) and cfg.experiment.train_iters > 0, path
+        if os.path.basename(path) == "config_default.yml":
+            # an older schema (num_encoding_functions, no dataset.type): the scripts fail on it with the
+            # AttributeError of cfgnode.py:115-119 - and so does the drop-in
+            assert getattr(nerf.models, cfg.models.coarse.type) is nerf.FlexibleNeRFModel
+            with pytest.raises(AttributeError):
+                cfg.models.coarse.num_encoding_fn_xyz
+            continue
+        for key in ("validate_every", "save_every", "print_every", "randomseed", "logdir"):
+            getattr(cfg.experiment, key)
+        if hasattr(cfg.dataset, "type"):          # config/default.yml predates the dataset.type / near / far keys
+            assert cfg.dataset.type in ("blender", "llff", "messytable"), path
+            assert isinstance(cfg.dataset.no_ndc, bool) and cfg.dataset.far > cfg.dataset.near >= 0, path
+        assert hasattr(cfg.models, "fine") and hasattr(cfg.models, "coarse"), path
+        for net in (cfg.models.coarse, cfg.models.fine):
+            cls = getattr(nerf.models, net.type)                       # train_dexnerf_rgb.py:122
+            m = cls(num_encoding_fn_xyz=net.num_encoding_fn_xyz, num_encoding_fn_dir=net.num_encoding_fn_dir,
+                    include_input_xyz=net.include_input_xyz, include_input_dir=net.include_input_dir,
+                    use_viewdirs=net.use_viewdirs)                     # the five kwargs of :122-128
+            assert m.dim_xyz == (3 if net.include_input_xyz else 0) + 6 * net.num_encoding_fn_xyz
+        assert cfg.optimizer.type == "Adam" and cfg.optimizer.lr > 0
+        assert cfg.scheduler.lr_decay > 0 and 0 < cfg.scheduler.lr_decay_factor <= 1
+        assert isinstance(cfg.nerf.use_viewdirs, bool)
+        for mode in ("train", "validation"):
+            opt = getattr(cfg.nerf, mode)                              # train_utils.py:114
+            assert opt.chunksize > 0 and opt.num_coarse > 0 and opt.num_fine > 0, path
+            for key in ("perturb", "white_background", "radiance_field_noise_std", "lindisp"):
+                getattr(opt, key)
+        assert cfg.nerf.train.num_random_rays > 0
+        if "messytable" in os.path.basename(path):
+            assert cfg.nerf.validation.m_thres > 0          # (two of them say dataset.type: blender)
+        with pytest.raises(AttributeError):
+            cfg.dataset.no_such_key                                   # cfgnode.py:115-119
+        back = yaml.safe_load(cfg.dump())
+        assert back["nerf"]["train"]["num_coarse"] == cfg.nerf.train.num_coarse and back["experiment"]["id"] == cfg.experiment.id
 
 
 def test_linspace_formula_matches_torch():

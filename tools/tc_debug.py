@@ -1,6 +1,6 @@
 """Bring-up aid for the tcgen05 MLP kernel: dumps the raw fp32 accumulator of every (layer, pass)
 through the kernel's debug tap and prints its error against a bf16-operand emulation in torch.
-Run on the GPU box:  python tests/tc_debug.py [hidden] [n_rays] [S]"""
+Run on the GPU box:  python tools/tc_debug.py [hidden] [n_rays] [S]"""
 import os
 import sys
 

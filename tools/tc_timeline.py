@@ -1,6 +1,6 @@
 """Pipeline timeline of the tcgen05 MLP kernel (block 0, first tile pair): SM-clock stamps of each
 MMA pass issue window and each epilogue pass, dumped through the kernel's timing tap
-(dbg_layer = -2).  Run on the GPU box:  python tests/tc_timeline.py [n_rays] [S]"""
+(dbg_layer = -2).  Run on the GPU box:  python tools/tc_timeline.py [n_rays] [S]"""
 import os
 import sys
 
