@@ -50,7 +50,7 @@ def world2cam_from_blender_pose(c2w):
     if c2w.shape[0] == 3:
         c2w = torch.cat((c2w, torch.tensor([[0.0, 0.0, 0.0, 1.0]], dtype=torch.float64)), 0)
     cv = c2w @ torch.diag(torch.tensor([1.0, -1.0, -1.0, 1.0], dtype=torch.float64))
-    return torch.linalg.inv(cv).to(torch.float32)
+    return torch.linalg.inv(cv).to(torch.float32).contiguous()      # (LAPACK hands back column-major strides)
 
 
 def render_poses_spherical(n_frames=40, phi=-30.0, radius=4.0):

@@ -37,7 +37,7 @@ def pair(layers, hidden, skip, seed=3, boost=300.0):
 def camera(H, W, f):
     T = O.pose_spherical_world2cam(25.0, -35.0, 4.0)
     K = torch.tensor([[f, 0, W / 2.0], [0, f, H / 2.0], [0, 0, 1]])
-    return T.cuda(), K.cuda()
+    return T.contiguous().cuda(), K.cuda()        # (torch.linalg.inv returns column-major strides)
 
 
 @pytest.mark.parametrize("precision", ["bf16", "fp32"])

@@ -116,15 +116,18 @@ def test_lego_checkpoint_on_the_tensor_core_path(golden, fixture):
     for name in ("rgb_c", "rgb_f", "acc_c", "acc_f"):
         assert s_ref[name]["mean"] < 2e-3, (name, s_ref[name])            # north-star figure holds for the MEAN
         assert s_ref[name]["max"] < 0.30, (name, s_ref[name])
-    assert s_ref["rgb_f"]["p99"] < 2.5e-2 and s_ref["acc_f"]["p99"] < 1e-2
+    if H * W >= 1000:       # percentiles need rays: the 120-ray fixture's 99th percentile IS its second-worst ray
+        assert s_ref["rgb_f"]["p99"] < 2.5e-2 and s_ref["acc_f"]["p99"] < 1e-2
     assert s_ref["depth_f"]["mean"] < 0.5 * spacing                        # expected depth: within a sample spacing on average
     assert s_ref["dex_within_one_spacing"] > 0.995                          # Dex depth: same or neighbouring sample
     assert max(s_ref["dex_off_by_more_than_one_spacing_per_threshold"]) < 0.02
     # ---- bars against the oracle under the same contract: accumulation order only; the same tipping-point rays
     # amplify it, so the maps are held to the mean / p99 and the Dex depths to the sample spacing
+    # (measured: 10x12 view max 7.7e-4; 40x48 view max 5.8e-3 on one ray, p99 3.3e-4, mean 2e-5, 99.3 % of the Dex
+    # depths the very same value)
     for name in ("rgb_c", "rgb_f", "acc_c", "acc_f"):
-        assert s_orc[name]["mean"] < 1e-3, (name, s_orc[name])
-    assert s_orc["dex_within_one_spacing"] > 0.997
+        assert s_orc[name]["mean"] < 1e-4 and s_orc[name]["p99"] < 2e-3 and s_orc[name]["max"] < 1.5e-2, (name, s_orc[name])
+    assert s_orc["dex_within_one_spacing"] > 0.999 and s_orc["dex_same_sample"] > 0.97
 
 
 def test_c5_128_256_on_the_tensor_core_path():
