@@ -373,9 +373,12 @@ def run_train(args, dist, rank, world, dev, quiet=False):
     if api == "trainer":
         fw, bw = trainer.timing[0].elapsed_ms(), trainer.timing[1].elapsed_ms(RD.BWD_LAUNCH_NAMES)
         trainer.timing = None
-        parts = {"mlp_tc_train_fwd_S%d" % NC: fw["mlp_coarse"], "mlp_tc_train_fwd_S%d" % (NC + NF): fw["mlp_fine"],
-                 "mlp_tc_bwd_dx_S%d" % NC: bw["mlp_bwd_dx_coarse"], "mlp_tc_bwd_dx_S%d" % (NC + NF): bw["mlp_bwd_dx_fine"],
-                 "mlp_tc_bwd_dw_S%d" % NC: bw["mlp_bwd_dw_coarse"], "mlp_tc_bwd_dw_S%d" % (NC + NF): bw["mlp_bwd_dw_fine"]}
+        parts = {"mlp_tc_train_fwd_S%d" % NC: fw["mlp_coarse"], "mlp_tc_train_fwd_S%d" % (NC + NF): fw["mlp_fine"]}
+        if "mlp_bwd_dw_fine" in bw:      # DEXNERF_BWD=split: the two stand-alone backward kernels
+            parts.update({"mlp_tc_bwd_dx_S%d" % NC: bw["mlp_bwd_coarse"], "mlp_tc_bwd_dx_S%d" % (NC + NF): bw["mlp_bwd_fine"],
+                          "mlp_tc_bwd_dw_S%d" % NC: bw["mlp_bwd_dw_coarse"], "mlp_tc_bwd_dw_S%d" % (NC + NF): bw["mlp_bwd_dw_fine"]})
+        else:                            # the fused backward launch (chain + weight-gradient GEMM)
+            parts.update({"mlp_tc_bwd_fused_S%d" % NC: bw["mlp_bwd_coarse"], "mlp_tc_bwd_fused_S%d" % (NC + NF): bw["mlp_bwd_fine"]})
         small = {k: v for k, v in list(fw.items()) + list(bw.items()) if not k.startswith("mlp_")}
     # multi-GPU correctness on record: after the same number of steps every rank must hold the same parameters
     param_check = None
@@ -427,7 +430,7 @@ def run_train(args, dist, rank, world, dev, quiet=False):
                    "rays_per_step": rays, "parallelism": "dp%d" % world,
                    "api": "nerf.Trainer (flat buffers, fused Adam)" if api == "trainer"
                           else "run_one_iter_of_nerf(mode='train') autograd + torch.optim.Adam",
-                   "l2": "the per-step tape (10 KB/sample, 10.7 GB per step) exceeds the 126 MB L2"},
+                   "l2": "the per-step forward tape (5.3 KB/sample, 5.6 GB per step) exceeds the 126 MB L2"},
         "e2e": {"value": rays / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": TRAIN_RAYS * (8 + 12), "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
@@ -445,6 +448,34 @@ def run_train(args, dist, rank, world, dev, quiet=False):
         "non_mlp_ms": ms_dev - mlp_ms,
         "small_kernel_ms": {k: round(v, 4) for k, v in sorted(small.items())},
     }
+    bw_ms = parts.get("mlp_tc_bwd_fused_S%d" % (NC + NF))
+    if fw_ms and bw_ms:
+        # Fused backward: the gradient images go from the chain CTAs to the weight-gradient
+        # CTAs through L2, so the step's HBM traffic is the forward tape only (written once: 666 KB per 128-sample
+        # tile; read once by the GEMM, the two head operands twice: ~766 KB) and the bound is the tensor pipe:
+        # forward + activation-gradient chain + weight-gradient GEMM = 1 + 0.896 + 1 forward-equivalents.
+        f_dx = TRAIN_RAYS * (NC + NF) * 2.0 * (128 * 256 + 8 * 256 * 256)
+        flop3 = 2 * flop_fine + f_dx
+        r = line["roofline"]
+        r.update({"bound": "tensor", "kernel": "mlp_tc train fwd + fused backward (fine pass, 192 samples/ray)",
+                  "achieved": flop3 / ((fw_ms + bw_ms) * 1e-3) / 1e12, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                  "peak_source": pk["source"] + " bf16 sustained", "flop_per_launch": flop3})
+        r["frac"] = r["achieved"] / pk["tf_sustained"]
+        r["tensor_tflops"] = r["achieved"]
+        r["tensor_frac_of_sustained_peak"] = r["frac"]
+        tiles_ = TRAIN_RAYS * (NC + NF) / 128.0
+        r["hbm_bytes_algorithmic"] = tiles_ * (666.0 + 766.0) * 1024.0
+        r["hbm_gbs"] = r["hbm_bytes_algorithmic"] / ((fw_ms + bw_ms) * 1e-3) / 1e9
+        r["hbm_frac_of_peak"] = r["hbm_gbs"] / pk["hbm"]
+        r["kernels"] = {
+            "mlp_tc_train_fwd": {"ms": fw_ms, "tflops": flop_fine / (fw_ms * 1e-3) / 1e12,
+                                 "hbm_write_gbs": tiles_ * 666.0 * 1024.0 / (fw_ms * 1e-3) / 1e9},
+            "mlp_tc_bwd_fused": {"ms": bw_ms, "tflops": (flop_fine + f_dx) / (bw_ms * 1e-3) / 1e12,
+                                 "tensor_frac_of_sustained_peak": (flop_fine + f_dx) / (bw_ms * 1e-3) / 1e12 / pk["tf_sustained"],
+                                 "hbm_read_gbs": tiles_ * 766.0 * 1024.0 / (bw_ms * 1e-3) / 1e9}}
+        if not quiet:
+            print(json.dumps(line))
+        return line
     if fw_ms and dx_ms and dw_ms:
         tape_bytes = TRAIN_RAYS * (NC + NF) / 128.0 * (666.0 + 646.0 + 1424.0) * 1024.0
         r = line["roofline"]

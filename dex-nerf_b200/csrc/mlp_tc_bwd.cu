@@ -18,6 +18,14 @@
 //       of a layer in proportion to its bytes and reduce with red.global.add.f32.  Bias gradients
 //       are column sums of G taken from the shared-memory image by the otherwise idle warps.
 //
+//   mlp_tc_bwd_fused_kernel   BOTH of the above in ONE launch (the training path): the first n_chain CTAs run the
+//       activation-gradient chain, the others the weight-gradient GEMM, and the G images never visit HBM: a chain
+//       CTA releases a per-(layer, tile) flag in global memory when an image is complete (dirty in the 126 MB L2),
+//       the GEMM CTA of that (layer, tile) acquires it, bulk-copies the image out of L2 and then DISCARDS its lines
+//       (discard.global.L2: dropped without write-back).  The chain never waits for the GEMM (no back-pressure, so
+//       no deadlock); a GEMM CTA that falls behind only lets lines spill to HBM.  The tile split of the GEMM CTAs is
+//       interleaved (tile = split + k * n_cta) so that they consume in the order the chain produces.
+//
 // Arithmetic contract: bf16-rounded G and activations as tensor-core operands, fp32 accumulation;
 // fc_alpha / fc_rgb gradients use the same bf16 images.  oracle.train_step(bf16=True) is the
 // statement of this contract; the fp32 reference gradients are matched to bf16 tolerance.
@@ -47,13 +55,43 @@ struct BwdParams {
   int64_t grad_off[kMaxLayers];
   int64_t ghead_off;
   int relu[kMaxLayers];       // forward ReLU flag of each layer (its G needs the mask)
+  uint32_t* ready;            // fused launch: [kMaxLayers + 1][n_tiles] completion counters of the G images (else NULL)
+  int64_t n_tiles_pad;        // tiles the tape is laid out for (an even count)
 };
+
+// ---- cross-CTA hand-off of a finished G image (fused launch).  Producer: the warp's stores are ordered before
+// lane 0's gpu-scope release by __syncwarp + the fence (cumulativity); the image is read by the consumer's bulk copy
+// (async proxy), hence the proxy fence on both sides.
+__device__ __forceinline__ void signal_image(uint32_t* flag, int lane) {
+  __syncwarp();
+  if (lane == 0) {
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(flag) : "memory");
+  }
+}
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+static __device__ __noinline__ void flag_timeout(int who) {
+  printf("dexnerf fused backward: flag wait timeout (site %d, block %d, thread %d)\n", who, blockIdx.x, threadIdx.x);
+  __trap();
+}
+__device__ __forceinline__ void wait_image(const uint32_t* flag, uint32_t expected, int who) {
+  uint32_t spins = 0;
+  while (ld_acquire_u32(flag) < expected) {
+    __nanosleep(64);
+    if (++spins > (1u << 22)) flag_timeout(who);     // seconds: a protocol bug must trap, not hang the GPU
+  }
+}
 
 struct BSmem {
   static constexpr int w_slots = 0;
   static constexpr int consts = w_slots + kBSlots * kBSlotBytes;
   static constexpr int bars = consts + kMaxConstFloats * 4;
-  static constexpr int n_bars = 2 * kBSlots + 6;
+  static constexpr int n_bars = 2 * kBSlots + 8;
   static constexpr int tmem_ptr = bars + n_bars * 8;
   static constexpr int total = tmem_ptr + 16;
 };
@@ -62,6 +100,7 @@ __device__ __forceinline__ int BB_wempty(int s) { return kBSlots + s; }
 __device__ __forceinline__ int BB_aready(int t) { return 2 * kBSlots + t; }
 __device__ __forceinline__ int BB_dfull(int t) { return 2 * kBSlots + 2 + t; }
 __device__ __forceinline__ int BB_dfree(int t) { return 2 * kBSlots + 4 + t; }
+__device__ __forceinline__ int BB_img(int t) { return 2 * kBSlots + 6 + t; }     // fused: "this pass's G rows are stored"
 
 // One backward epilogue pass of one warp over its 64 accumulator columns: optional rank-1 term
 // d_sigma * w_alpha, optional ReLU mask, bf16 pack, A-operand store (held / parked / direct) and
@@ -114,10 +153,9 @@ __device__ __forceinline__ void bwd_epilogue_pass(uint32_t d_tmem, uint32_t a_pa
   }
 }
 
-template <int H>
-__global__ void __launch_bounds__(kBThreads, 1) mlp_tc_bwd_dx_kernel(const __grid_constant__ BwdParams P) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+// cta / n_cta: this CTA's index among the chain CTAs (the whole grid in the stand-alone kernel)
+template <int H, bool kFused>
+__device__ __forceinline__ void chain_body(const BwdParams& P, uint8_t* smem, const int cta, const int n_cta) {
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bars = sbase + BSmem::bars;
   auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
@@ -133,6 +171,7 @@ __global__ void __launch_bounds__(kBThreads, 1) mlp_tc_bwd_dx_kernel(const __gri
       mbar_init(bar(BB_aready(t)), kBEpiThreads);
       mbar_init(bar(BB_dfull(t)), 1);
       mbar_init(bar(BB_dfree(t)), kBEpiThreads);
+      mbar_init(bar(BB_img(t)), kBEpiThreads);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -154,7 +193,7 @@ __global__ void __launch_bounds__(kBThreads, 1) mlp_tc_bwd_dx_kernel(const __gri
     const bool leader = elect_one();
     uint32_t cnt = 0;
 #pragma unroll 1
-    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+    for (int64_t pair = cta; pair < n_pairs; pair += n_cta) {
       const uint8_t* src = P.weights_t;
 #pragma unroll 1
       for (int j = 0; j < n_steps; ++j) {
@@ -182,7 +221,7 @@ __global__ void __launch_bounds__(kBThreads, 1) mlp_tc_bwd_dx_kernel(const __gri
     const uint32_t idesc = instr_desc(128);
     constexpr uint32_t b_lbo16 = 128;      // LBO = 128 rows * 16 B, in 16-byte units
 #pragma unroll 1
-    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+    for (int64_t pair = cta; pair < n_pairs; pair += n_cta) {
 #pragma unroll 1
       for (int j = 0; j < n_steps; ++j) {
         const int nc = (j == 0 ? H / 2 : H) / 64;
@@ -236,7 +275,7 @@ __global__ void __launch_bounds__(kBThreads, 1) mlp_tc_bwd_dx_kernel(const __gri
     uint32_t held[32];
     const int half = row >> 6, r64 = row & 63;
 #pragma unroll 1
-    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+    for (int64_t pair = cta; pair < n_pairs; pair += n_cta) {
       const int64_t tile = pair * 2 + t;
       const int64_t g = tile * kTileM + row;
       const float4 d = (g < P.m_total) ? P.d_rf[g] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -271,6 +310,7 @@ __global__ void __launch_bounds__(kBThreads, 1) mlp_tc_bwd_dx_kernel(const __gri
           *reinterpret_cast<uint4*>(hrow) = make_uint4(pack_bf16(d.x, d.y, false), pack_bf16(d.z, d.w, false), 0u, 0u);
           *reinterpret_cast<uint4*>(hrow + 1024) = make_uint4(0u, 0u, 0u, 0u);
         }
+        if (kFused) mbar_arrive(bar(BB_img(t)));      // G of the dir layer (+ the head operand) is stored
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(bar(BB_aready(t)));
@@ -311,7 +351,32 @@ __global__ void __launch_bounds__(kBThreads, 1) mlp_tc_bwd_dx_kernel(const __gri
             tc_fence_before();
             mbar_arrive(bar(BB_aready(t)));
           }
+          if (kFused) mbar_arrive(bar(BB_img(t)));    // this pass's rows of G[dst] are stored
         }
+      }
+    }
+  } else if (kFused) {
+    // =============================== signallers (fused launch; warp 2: tile 0, warp 3: tile 1) ===============
+    // The epilogue threads only arrive on a shared-memory barrier after their stores (release.cta); THIS warp pays
+    // the gpu-scope fence (~1 us) and publishes the image to the weight-gradient CTAs, off the
+    // MMA -> epilogue -> MMA chain.  By cumulativity the fence orders the 256 threads' stores it has synchronised
+    // with before the flag.
+    const int t = warp - 2;
+    uint32_t ph = 0;
+#pragma unroll 1
+    for (int64_t pair = cta; pair < n_pairs; pair += n_cta) {
+      const int64_t tile = pair * 2 + t;
+      mbar_wait(bar(BB_img(t)), ph, 15);
+      ph ^= 1;
+      signal_image(P.ready + (int64_t)(P.nl - 1) * P.n_tiles_pad + tile, lane);
+      signal_image(P.ready + (int64_t)kMaxLayers * P.n_tiles_pad + tile, lane);
+#pragma unroll 1
+      for (int j = 0; j < n_steps; ++j) {
+        for (int p = 0; p < kPass; ++p) {
+          mbar_wait(bar(BB_img(t)), ph, 15);
+          ph ^= 1;
+        }
+        signal_image(P.ready + (int64_t)(P.nl - 2 - j) * P.n_tiles_pad + tile, lane);
       }
     }
   }
@@ -321,6 +386,13 @@ __global__ void __launch_bounds__(kBThreads, 1) mlp_tc_bwd_dx_kernel(const __gri
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
+}
+
+template <int H>
+__global__ void __launch_bounds__(kBThreads, 1) mlp_tc_bwd_dx_kernel(const __grid_constant__ BwdParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  chain_body<H, false>(P, smem, (int)blockIdx.x, (int)gridDim.x);
 }
 
 // ---- transposed weight images for the dX chain (one 16 KB chunk = 128 in-features x 64 out-features)
@@ -347,7 +419,7 @@ constexpr int kWStageA = 32768;     // up to 2 M-blocks x 16 feature groups x 64
 constexpr int kWStageG = 32768;     // up to 32 feature groups (N = 256)
 constexpr int kWStages = 3;
 constexpr int kWThreads = 256;      // producer, MMA issuer, TMEM allocator, (idle), 4 reducer warps
-constexpr int kMaxDwItems = 40;
+constexpr int kMaxDwItems = 24;     // <= 16 layers + 2 encoding parts + 2 heads
 
 struct DwItem {
   int64_t a_off;     // tape offset of the A image array
@@ -363,6 +435,8 @@ struct DwItem {
   int col0, n_cols;  // output columns flushed: D[:, col0 : col0 + n_cols] -> dWt[:, 0 : n_cols]
   int ld;            // row stride of dWt (out features of the layer)
   int cta0, n_cta;   // CTAs [cta0, cta0 + n_cta) split this item's tiles
+  int flag_row;      // fused launch: row of the `ready` table that announces this item's G image
+  int n_consumers;   // ... and how many items read that image (the last reader discards it from L2)
 };
 
 struct DwParams {
@@ -371,6 +445,8 @@ struct DwParams {
   int64_t n_tiles;
   int n_items;
   int variant;       // bring-up knob: bit 0 swaps the LBO / SBO fields of the MN-major descriptors
+  const uint32_t* ready;   // fused launch: [kMaxLayers + 1][n_tiles] image-complete counters written by the chain CTAs
+  uint32_t* consumed;      // fused launch: [kMaxLayers + 1][n_tiles][2] readers done with a half image
   DwItem items[kMaxDwItems];
 };
 
@@ -390,9 +466,15 @@ __device__ __forceinline__ void red_add_f32x4(float* p, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-__global__ void __launch_bounds__(kWThreads, 1) mlp_tc_bwd_dw_kernel(const __grid_constant__ DwParams P) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+// drop 128-byte lines from L2 without writing them back (the data is dead: every reader has its copy)
+__device__ __forceinline__ void discard_l2(const uint8_t* p) {
+  asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
+}
+
+// cta: this CTA's index among the weight-gradient CTAs.  kFused: the G images come from chain CTAs of the same launch
+// (wait for their flags, interleaved tile split, discard after use); all blockDim threads call this, warps >= 8 idle.
+template <bool kFused>
+__device__ __forceinline__ void dw_body(const DwParams& P, uint8_t* smem, const int cta) {
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bars = sbase + WSmem::bars;
   auto full = [&](int s) { return bars + 8u * (uint32_t)s; };
@@ -402,11 +484,15 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_tc_bwd_dw_kernel(const __gri
 
   // which item / which slice of its tiles
   int it = 0;
-  while (it + 1 < P.n_items && (int)blockIdx.x >= P.items[it].cta0 + P.items[it].n_cta) ++it;
+  while (it + 1 < P.n_items && cta >= P.items[it].cta0 + P.items[it].n_cta) ++it;
   const DwItem& I = P.items[it];
-  const int split = (int)blockIdx.x - I.cta0;
-  const int64_t tile_begin = P.n_tiles * split / I.n_cta, tile_end = P.n_tiles * (split + 1) / I.n_cta;
-  const int64_t n_stage_total = (tile_end - tile_begin) * 2;     // half-tiles
+  const int split = cta - I.cta0;
+  // stand-alone: a contiguous range of tiles; fused: every n_cta-th tile, in the order the chain produces them
+  const int64_t tile_begin = kFused ? split : P.n_tiles * split / I.n_cta;
+  const int64_t tile_end = kFused ? P.n_tiles : P.n_tiles * (split + 1) / I.n_cta;
+  const int64_t tile_step = kFused ? I.n_cta : 1;
+  const int64_t n_my_tiles = tile_end > tile_begin ? (tile_end - tile_begin + tile_step - 1) / tile_step : 0;
+  const int64_t n_stage_total = n_my_tiles * 2;     // half-tiles
   const uint32_t a_bytes = (uint32_t)I.a_fgs * 1024u, g_bytes = (uint32_t)I.g_fg * 1024u;
 
   if (threadIdx.x == 0) {
@@ -419,7 +505,7 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_tc_bwd_dw_kernel(const __gri
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   // the MMA reads 16 feature groups per M block even when the image has fewer: keep the tail finite
-  for (int i = threadIdx.x; i < kWStages * kWStageA / 16; i += kWThreads)
+  for (int i = threadIdx.x; i < kWStages * kWStageA / 16; i += (int)blockDim.x)
     reinterpret_cast<uint4*>(smem + WSmem::a)[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async();
   tc_fence_before();
@@ -430,20 +516,49 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_tc_bwd_dw_kernel(const __gri
   if (warp == 0) {
     // =============================== producer ===============================
     const bool leader = elect_one();
+    auto g_image = [&](int64_t s) {
+      const int64_t tile = tile_begin + (s >> 1) * tile_step;
+      return P.tape + I.g_off + tile * (int64_t)(I.g_fg * 2048) + (int64_t)(s & 1) * (I.g_fg * 1024);
+    };
+    // fused: kWStages extra rounds drain the ring so that the last images are discarded too
 #pragma unroll 1
-    for (int64_t s = 0; s < n_stage_total; ++s) {
+    for (int64_t s = 0; s < n_stage_total + (kFused ? kWStages : 0); ++s) {
       const int st = (int)(s % kWStages);
       const uint32_t ph = (uint32_t)((s / kWStages) & 1);
       mbar_wait(empty(st), ph ^ 1, 20);
-      if (leader) {
-        const int64_t tile = tile_begin + (s >> 1);
-        const int half = (int)(s & 1);
-        const uint8_t* a_src = P.tape + I.a_off + tile * (int64_t)(I.a_fg * 2048) + (int64_t)half * (I.a_fg * 1024) +
-                               (int64_t)I.a_fg0 * 1024;
-        const uint8_t* g_src = P.tape + I.g_off + tile * (int64_t)(I.g_fg * 2048) + (int64_t)half * (I.g_fg * 1024);
-        mbar_arrive_expect_tx(full(st), a_bytes + g_bytes);
-        bulk_g2s(sbase + WSmem::a + st * kWStageA, a_src, a_bytes, full(st));
-        bulk_g2s(sbase + WSmem::g + st * kWStageG, g_src, g_bytes, full(st));
+      if (kFused && s >= kWStages) {
+        // the half image that occupied this stage has been read by the MMAs and the column sums of THIS item; the
+        // last of its readers drops its lines from L2 (they are dirty there and would be written back otherwise)
+        const int64_t sp = s - kWStages;
+        const int64_t tile = tile_begin + (sp >> 1) * tile_step;
+        uint32_t last = 1;
+        if (I.n_consumers > 1) {
+          uint32_t old = 0;
+          if (lane == 0)
+            old = atomicAdd(P.consumed + ((int64_t)I.flag_row * P.n_tiles + tile) * 2 + (sp & 1), 1u);
+          last = (__shfl_sync(0xffffffffu, old, 0) + 1 == (uint32_t)I.n_consumers) ? 1u : 0u;
+        }
+        if (last) {
+          const uint8_t* g = g_image(sp);
+          for (uint32_t off = (uint32_t)lane * 128u; off < g_bytes; off += 32u * 128u) discard_l2(g + off);
+        }
+      }
+      if (s < n_stage_total) {
+        if (kFused && (s & 1) == 0) {
+          const int64_t tile = tile_begin + (s >> 1) * tile_step;
+          if (lane == 0) wait_image(P.ready + (int64_t)I.flag_row * P.n_tiles + tile, 1u, 24);
+          __syncwarp();
+          asm volatile("fence.proxy.async.global;" ::: "memory");   // the image is read by the async proxy next
+        }
+        if (leader) {
+          const int64_t tile = tile_begin + (s >> 1) * tile_step;
+          const int half = (int)(s & 1);
+          const uint8_t* a_src = P.tape + I.a_off + tile * (int64_t)(I.a_fg * 2048) + (int64_t)half * (I.a_fg * 1024) +
+                                 (int64_t)I.a_fg0 * 1024;
+          mbar_arrive_expect_tx(full(st), a_bytes + g_bytes);
+          bulk_g2s(sbase + WSmem::a + st * kWStageA, a_src, a_bytes, full(st));
+          bulk_g2s(sbase + WSmem::g + st * kWStageG, g_image(s), g_bytes, full(st));
+        }
       }
       __syncwarp();
     }
@@ -481,7 +596,7 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_tc_bwd_dw_kernel(const __gri
     }
     if (leader) tc_commit(acc_bar);
     __syncwarp();
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 8) {
     // =============================== bias column sums + final reduction ===============================
     // thread j owns feature group j / 4 of G (8 features) and every 4th sample of the half-tile:
     // one 16-byte shared-memory load per sample row, rows rotated by the feature group so that the
@@ -562,6 +677,23 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_tc_bwd_dw_kernel(const __gri
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
+}
+
+__global__ void __launch_bounds__(kWThreads, 1) mlp_tc_bwd_dw_kernel(const __grid_constant__ DwParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  dw_body<false>(P, smem, (int)blockIdx.x);
+}
+
+// The training path: chain CTAs [0, n_chain) and weight-gradient CTAs [n_chain, gridDim.x) in ONE launch
+// (see the file header).  Chain CTAs carry the low block indices so that they are scheduled first.
+template <int H>
+__global__ void __launch_bounds__(kBThreads, 1)
+mlp_tc_bwd_fused_kernel(const __grid_constant__ BwdParams B, const __grid_constant__ DwParams W, const int n_chain) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  if ((int)blockIdx.x < n_chain) chain_body<H, true>(B, smem, (int)blockIdx.x, n_chain);
+  else dw_body<true>(W, smem, (int)blockIdx.x - n_chain);
 }
 
 }  // namespace tc
@@ -650,8 +782,10 @@ extern "C" DEXNERF_API int dexnerf_tc_backward(const dexnerf_flexible_spec* spec
   make_tape_layout(plan, n_pairs * 2, &T);
   cudaStream_t st = (cudaStream_t)stream;
 
-  if (what & 1) {
-    BwdParams P{};
+  const bool fused = (what & 4) != 0;
+  DN_REQUIRE(!fused || what == 4, "tc_backward: what = 4 (the fused launch) excludes the other bits");
+  BwdParams P{};
+  if ((what & 1) || fused) {
     P.weights_t = reinterpret_cast<const uint8_t*>(packed_t);
     P.consts = reinterpret_cast<const float*>(packed);
     P.d_rf = reinterpret_cast<const float4*>(d_rf);
@@ -662,6 +796,10 @@ extern "C" DEXNERF_API int dexnerf_tc_backward(const dexnerf_flexible_spec* spec
       P.mask_off[l] = T.mask[l]; P.grad_off[l] = T.grad[l]; P.relu[l] = plan.layers[l].tc.relu;
     }
     P.ghead_off = T.ghead;
+    P.n_tiles_pad = n_pairs * 2;
+    P.ready = fused ? reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(tape) + T.flags) : nullptr;
+  }
+  if (what & 1) {
     const int grid = (int)(n_pairs < kNumSMs ? n_pairs : kNumSMs);
     const size_t smem = BSmem::total + 1024;
     auto launch = [&](auto kernel) -> int {
@@ -674,7 +812,7 @@ extern "C" DEXNERF_API int dexnerf_tc_backward(const dexnerf_flexible_spec* spec
     DN_CHECK_LAUNCH("mlp_tc_bwd_dx");
   }
 
-  if (what & 2) {
+  if ((what & 2) || fused) {
     DwParams W{};
     W.tape = reinterpret_cast<const uint8_t*>(tape);
     W.grads = grads;
@@ -682,12 +820,16 @@ extern "C" DEXNERF_API int dexnerf_tc_backward(const dexnerf_flexible_spec* spec
     W.variant = variant;
     double cost[kMaxDwItems];
     auto add = [&](int64_t a_off, int a_fg, int a_fg0, int a_fgs, int a_rows, int64_t g_off, int g_fg, int64_t w_out,
-                   int64_t b_out, int col0, int n_cols, int ld) {
+                   int64_t b_out, int col0, int n_cols, int ld, int flag_row) {
       DwItem& I = W.items[W.n_items];
+      I.flag_row = flag_row; I.n_consumers = 1;
       I.a_off = a_off; I.a_fg = a_fg; I.a_fg0 = a_fg0; I.a_fgs = a_fgs; I.n_mblk = (a_fgs + 15) / 16;
       I.a_rows = a_rows; I.g_off = g_off; I.g_fg = g_fg; I.w_out = w_out; I.b_out = b_out;
       I.col0 = col0; I.n_cols = n_cols; I.ld = ld;
-      cost[W.n_items] = (double)(a_fgs + g_fg);
+      // stand-alone kernel: bytes streamed per tile (HBM-bound); fused launch: tensor-pipe cycles per tile
+      // (n_mblk M blocks x 8 K steps, an N-wide MMA takes ~max(N, 64) / 2 cycles) - the G half comes out of L2
+      cost[W.n_items] = fused ? (double)(I.n_mblk * 8 * ((g_fg * 8 > 64 ? g_fg * 8 : 64) / 2)) + 200.0
+                              : (double)(a_fgs + g_fg);
       ++W.n_items;
     };
     const int hfg = H / 8;
@@ -698,26 +840,44 @@ extern "C" DEXNERF_API int dexnerf_tc_backward(const dexnerf_flexible_spec* spec
       int64_t w_row = op.w_off;
       bool bias_done = false;
       if (L.k_main) {      // hidden-input part: rows [0, H) of Wt
-        add(T.act[l - 1], hfg, 0, hfg, H, T.grad[l], gfg, w_row, op.b_off, 0, L.n_out, L.n_out);
+        add(T.act[l - 1], hfg, 0, hfg, H, T.grad[l], gfg, w_row, op.b_off, 0, L.n_out, L.n_out, l);
         bias_done = true;
         w_row += (int64_t)H * L.n_out;
       }
       if (L.smem_src == 1)
-        add(T.xyz, 8, 0, 8, spec->dim_xyz, T.grad[l], gfg, w_row, bias_done ? -1 : op.b_off, 0, L.n_out, L.n_out);
+        add(T.xyz, 8, 0, 8, spec->dim_xyz, T.grad[l], gfg, w_row, bias_done ? -1 : op.b_off, 0, L.n_out, L.n_out, l);
       else if (L.smem_src == 2)
-        add(T.dir, 4, 0, 4, spec->dim_dir, T.grad[l], gfg, w_row, bias_done ? -1 : op.b_off, 0, L.n_out, L.n_out);
+        add(T.dir, 4, 0, 4, spec->dim_dir, T.grad[l], gfg, w_row, bias_done ? -1 : op.b_off, 0, L.n_out, L.n_out, l);
     }
     {   // heads: fc_alpha reads the last trunk output, fc_rgb the dir-layer output; G = [d rgb, d sigma, 0..]
       const dexnerf_op& oa = prog->ops[plan.op_alpha];
       const dexnerf_op& orgb = prog->ops[plan.op_rgb];
-      add(T.act[nl - 3], hfg, 0, hfg, H, T.ghead, 2, oa.w_off, oa.b_off, 3, 1, 1);
-      add(T.act[nl - 1], hfg / 2, 0, hfg / 2, H / 2, T.ghead, 2, orgb.w_off, orgb.b_off, 0, 3, 3);
+      add(T.act[nl - 3], hfg, 0, hfg, H, T.ghead, 2, oa.w_off, oa.b_off, 3, 1, 1, kMaxLayers);
+      add(T.act[nl - 1], hfg / 2, 0, hfg / 2, H / 2, T.ghead, 2, orgb.w_off, orgb.b_off, 0, 3, 3, kMaxLayers);
     }
     DN_REQUIRE(W.n_items <= kMaxDwItems, "tc_backward: too many weight-gradient items");
+    for (int i = 0; i < W.n_items; ++i) {
+      int readers = 0;
+      for (int k = 0; k < W.n_items; ++k) readers += W.items[k].flag_row == W.items[i].flag_row;
+      W.items[i].n_consumers = readers;
+    }
     // ONE wave of CTAs (one per SM).  Every CTA of item i streams cost[i] * n_tiles / share[i] bytes;
     // the kernel ends with the slowest CTA, so shares are chosen greedily to minimise that maximum:
     // start with one CTA per item and keep giving a CTA to the currently most loaded item.
-    int64_t budget = kNumSMs;
+    // Fused launch: the SMs are first divided between the chain and the GEMM in proportion to their tensor-pipe
+    // cycles per tile (variant >> 8 overrides the chain's share for experiments).
+    int n_chain = 0;
+    if (fused) {
+      double chain_cost = 0.0, dw_cost = 0.0;
+      for (int j = 0; j < nl - 1; ++j) chain_cost += (double)(H / 128) * ((j == 0 ? H / 2 : H) / 64) * 4 * 64 + 150.0 * (H / 128);
+      for (int i = 0; i < W.n_items; ++i) dw_cost += cost[i];
+      n_chain = (int)(kNumSMs * chain_cost / (chain_cost + dw_cost) + 0.5);
+      if ((variant >> 8) > 0) n_chain = variant >> 8;
+      if (n_chain > kNumSMs - W.n_items) n_chain = kNumSMs - W.n_items;
+      if (n_chain > n_pairs) n_chain = (int)n_pairs;
+      if (n_chain < 1) n_chain = 1;
+    }
+    int64_t budget = kNumSMs - n_chain;
     if (budget < W.n_items) budget = W.n_items;
     int share[kMaxDwItems];
     for (int i = 0; i < W.n_items; ++i) share[i] = 1;
@@ -734,6 +894,23 @@ extern "C" DEXNERF_API int dexnerf_tc_backward(const dexnerf_flexible_spec* spec
       if (k > W.n_tiles) k = W.n_tiles;
       W.items[i].cta0 = cta; W.items[i].n_cta = (int)k;
       cta += (int)k;
+    }
+    if (fused) {
+      uint8_t* flags = reinterpret_cast<uint8_t*>(tape) + T.flags;
+      W.ready = reinterpret_cast<const uint32_t*>(flags);
+      W.consumed = reinterpret_cast<uint32_t*>(flags) + (int64_t)(kMaxLayers + 1) * W.n_tiles;
+      W.variant = variant & 0xFF;
+      DN_CUDA(cudaMemsetAsync(flags, 0, (size_t)T.flag_bytes, st));
+      const size_t smem = (WSmem::total > BSmem::total ? WSmem::total : BSmem::total) + 1024;
+      auto launch = [&](auto kernel) -> int {
+        DN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kernel<<<n_chain + cta, kBThreads, smem, st>>>(P, W, n_chain);
+        return 0;
+      };
+      const int rc = (H == 256) ? launch(mlp_tc_bwd_fused_kernel<256>) : launch(mlp_tc_bwd_fused_kernel<128>);
+      if (rc) return rc;
+      DN_CHECK_LAUNCH("mlp_tc_bwd_fused");
+      return 0;
     }
     const size_t smem = WSmem::total + 1024;
     DN_CUDA(cudaFuncSetAttribute(mlp_tc_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -13,6 +13,8 @@
 //
 // i.e. 6 launches per chunk, no per-ray near / far / ones arrays, no (n, 11) ray matrix, no torch glue.
 // Intermediates live in a caller-provided workspace (dexnerf_render_workspace_layout).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dexnerf {
@@ -230,6 +232,11 @@ static void resolve_only(const dexnerf_render_params* p, Resolved* r) {
   r->rf_c = f(L.rf_c); r->w_c = f(L.w_c); r->z_f = f(L.z_f); r->rf_f = f(L.rf_f);
 }
 
+static bool split_backward() {
+  static const bool v = [] { const char* e = getenv("DEXNERF_BWD"); return e && e[0] == 's'; }();
+  return v;
+}
+
 static int query(const dexnerf_model_ref& m, const Resolved& r, const float* z, int64_t n, int S, float* rf,
                  void* tape, cudaStream_t st) {
   DN_REQUIRE(m.prog, "render: model program is null");
@@ -332,7 +339,8 @@ extern "C" DEXNERF_API int dexnerf_render_fused_bwd(const dexnerf_render_params*
   Resolved r;
   resolve_only(p, &r);
   cudaStream_t st = (cudaStream_t)stream;
-  // events (optional): 0 compositing bwd fine, 1 dX fine, 2 dW fine, 3 compositing bwd coarse, 4 dX coarse, 5 dW coarse
+  // events (optional): 0 compositing bwd fine, 1 MLP backward fine (dX when split), 2 (dW when split), 3 compositing bwd
+  // coarse, 4 MLP backward coarse (dX when split), 5 (dW when split)
   auto chain = [&](const dexnerf_model_ref& m, void* tape, const float* rf, const float* z, const float* noise, int S,
                    const float* g_rgb, float* grads, int ev0) -> int {
     DN_REQUIRE(g_rgb && grads, "render_fused_bwd: null gradient pointer");
@@ -341,12 +349,17 @@ extern "C" DEXNERF_API int dexnerf_render_fused_bwd(const dexnerf_render_params*
       if (int rc = dexnerf_volume_render_backward(rf, z, r.rd, noise, n, S, p->white_background, g_rgb, nullptr,
                                                   nullptr, d_rf_scratch, stream)) return rc;
     }
-    for (int bit = 1; bit <= 2; ++bit) {
-      Bracket b(p->events, ev0 + bit, st);
-      if (int rc = dexnerf_tc_backward(m.spec, m.prog, m.packed, m.packed_t, tape, d_rf_scratch, n, S, grads, bit, 0,
-                                       stream)) return rc;
+    if (split_backward()) {     // DEXNERF_BWD=split: the two stand-alone kernels (G through HBM), for comparison
+      for (int bit = 1; bit <= 2; ++bit) {
+        Bracket b(p->events, ev0 + bit, st);
+        if (int rc = dexnerf_tc_backward(m.spec, m.prog, m.packed, m.packed_t, tape, d_rf_scratch, n, S, grads, bit, 0,
+                                         stream)) return rc;
+      }
+      return 0;
     }
-    return 0;
+    // one launch: activation-gradient chain and weight-gradient GEMM on disjoint SMs, G handed over through L2
+    Bracket b(p->events, ev0 + 1, st);
+    return dexnerf_tc_backward(m.spec, m.prog, m.packed, m.packed_t, tape, d_rf_scratch, n, S, grads, 4, 0, stream);
   };
   if (which & 1)
     if (int rc = chain(p->fine, p->tape_fine, r.rf_f, r.z_f, r.noise_f, Sf, g_rgb_fine, grads_fine, 0)) return rc;

@@ -120,6 +120,8 @@ struct TapeLayout {
   int64_t mask[kMaxLayers] = {};       // its ReLU bits
   int64_t grad[kMaxLayers] = {};       // dL/d(pre-activation) of layer l (written by the backward)
   int64_t ghead = 0;                   // [d rgb (3), d sigma, 0 x 12]: 16 features
+  int64_t flags = 0;                   // fused backward: uint32 ready[kMaxLayers + 1][n_tiles], consumed[..][n_tiles][2]
+  int64_t flag_bytes = 0;
   int64_t total = 0;
 };
 
@@ -137,6 +139,9 @@ inline void make_tape_layout(const Plan& plan, int64_t n_tiles, TapeLayout* out)
     T.grad[l] = take((int64_t)L.n_out * 256);
   }
   T.ghead = take(16 * 256);
+  T.flag_bytes = (int64_t)(kMaxLayers + 1) * n_tiles * 3 * 4;
+  T.flags = off;
+  off += (T.flag_bytes + 127) / 128 * 128;
   T.total = off;
 }
 

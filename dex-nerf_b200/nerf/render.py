@@ -15,8 +15,10 @@ _philox_offset = [0]   # advances once per fused call that draws random numbers 
 
 LAUNCH_NAMES = ("ray_setup", "ndc_rays", "mlp_coarse", "composite_coarse", "resample_merge", "mlp_fine",
                 "composite_fine")
-BWD_LAUNCH_NAMES = ("composite_bwd_fine", "mlp_bwd_dx_fine", "mlp_bwd_dw_fine", "composite_bwd_coarse",
-                    "mlp_bwd_dx_coarse", "mlp_bwd_dw_coarse")      # dexnerf_render_fused_bwd's event slots
+# dexnerf_render_fused_bwd's event slots: slot 1 / 4 is the ONE fused MLP backward launch (the activation-gradient
+# chain alone under DEXNERF_BWD=split, which also fills slots 2 / 5 with the weight-gradient GEMM)
+BWD_LAUNCH_NAMES = ("composite_bwd_fine", "mlp_bwd_fine", "mlp_bwd_dw_fine", "composite_bwd_coarse",
+                    "mlp_bwd_coarse", "mlp_bwd_dw_coarse")
 
 
 def workspace_bytes(n, Nc, Nf):

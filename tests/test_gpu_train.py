@@ -273,6 +273,43 @@ def test_weight_gradient_gemm(hidden, layers, skip, Lx):
     assert errs[0] < 1e-4, errs
 
 
+@pytest.mark.parametrize("hidden,layers,skip,n,S", [(256, 8, 4, 1, 100), (256, 8, 4, 37, 64), (128, 8, 3, 300, 192),
+                                                    (128, 4, 4, 640, 128), (256, 8, 4, 1500, 192)])
+def test_fused_backward_launch_equals_the_two_kernels(hidden, layers, skip, n, S):
+    """dexnerf_tc_backward(what = 4) - chain CTAs and weight-gradient CTAs in ONE launch, gradient images handed over
+    through L2 with release / acquire flags and discarded after use - against what = 3 (the stand-alone chain kernel,
+    then the stand-alone GEMM, images through HBM) on the same tape: the same bf16 images enter the same MMAs, only
+    the split-K partition (hence the order of the fp32 red.adds) differs.  Sizes: a single padded tile, an odd tile
+    count, more tiles than SMs, and 2 250 tiles (15 pairs per chain CTA)."""
+    torch.manual_seed(hidden + n)
+    model = nerf.FlexibleNeRFModel(layers, hidden, skip, 10, 4).cuda()
+    ex, ed = nerf.get_embedding_function(10, True, True), nerf.get_embedding_function(4, True, True)
+    prog = model.program(ex, ed)
+    spec = tensorcore.spec_for(model, prog)
+    g = torch.Generator().manual_seed(S)
+    ro, rd = (torch.randn(n, 3, generator=g) * 0.3).cuda(), torch.randn(n, 3, generator=g).cuda()
+    vd = rd / rd.norm(dim=-1, keepdim=True)
+    z = torch.sort(2 + 4 * torch.rand(n, S, generator=g), dim=-1).values.cuda()
+    d_rf = (torch.randn(n, S, 4, generator=g) * 0.05).cuda()
+    rf, tape = training.query_train(model, prog, spec, ro, rd, vd, z)
+    tape2 = tape.clone()
+    want = training.mlp_backward(model, prog, spec, tape, d_rf, n, S, what=3)
+    got = training.mlp_backward(model, prog, spec, tape2, d_rf, n, S, what=4)
+    torch.cuda.synchronize()
+    assert torch.isfinite(got).all() and float(want.abs().max()) > 0
+    assert rel_err(got, want) < 2e-5, rel_err(got, want)
+    for i, (lin, *_r) in enumerate(model._layers()):
+        op = prog.ops[i]
+        for sl in (slice(op.w_off, op.w_off + lin.in_features * lin.out_features), slice(op.b_off, op.b_off + lin.out_features)):
+            if float(want[sl].norm()) > 1e-12:
+                assert rel_err(got[sl], want[sl]) < 1e-4, (i, rel_err(got[sl], want[sl]))
+    # the gradient images the chain left in the tape are the stand-alone chain's, bit for bit, wherever a reader did
+    # not discard them... which it did: the fused launch drops them from L2, so only the split path's tape holds them.
+    # A second fused launch on the same tape must give the same result again (flags are re-armed per launch).
+    again = training.mlp_backward(model, prog, spec, tape2, d_rf, n, S, what=4)
+    assert rel_err(again, want) < 2e-5
+
+
 # ------------------------------------------------------------------ whole training iteration
 def make_cfg(nc, nf, near, far, white, noise_std=0.2, perturb=True):
     mode = dict(chunksize=1 << 20, perturb=perturb, num_coarse=nc, num_fine=nf, white_background=white,
