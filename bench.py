@@ -374,10 +374,10 @@ def run_train(args, dist, rank, world, dev, quiet=False):
         fw, bw = trainer.timing[0].elapsed_ms(), trainer.timing[1].elapsed_ms(RD.BWD_LAUNCH_NAMES)
         trainer.timing = None
         parts = {"mlp_tc_train_fwd_S%d" % NC: fw["mlp_coarse"], "mlp_tc_train_fwd_S%d" % (NC + NF): fw["mlp_fine"]}
-        if "mlp_bwd_dw_fine" in bw:      # DEXNERF_BWD=split: the two stand-alone backward kernels
+        if "mlp_bwd_dw_fine" in bw:      # the two backward kernels (default)
             parts.update({"mlp_tc_bwd_dx_S%d" % NC: bw["mlp_bwd_coarse"], "mlp_tc_bwd_dx_S%d" % (NC + NF): bw["mlp_bwd_fine"],
                           "mlp_tc_bwd_dw_S%d" % NC: bw["mlp_bwd_dw_coarse"], "mlp_tc_bwd_dw_S%d" % (NC + NF): bw["mlp_bwd_dw_fine"]})
-        else:                            # the fused backward launch (chain + weight-gradient GEMM)
+        else:                            # DEXNERF_BWD=fused / shared: ONE backward launch (chain + weight-gradient GEMM)
             parts.update({"mlp_tc_bwd_fused_S%d" % NC: bw["mlp_bwd_coarse"], "mlp_tc_bwd_fused_S%d" % (NC + NF): bw["mlp_bwd_fine"]})
         small = {k: v for k, v in list(fw.items()) + list(bw.items()) if not k.startswith("mlp_")}
     # multi-GPU correctness on record: after the same number of steps every rank must hold the same parameters

@@ -232,6 +232,88 @@ __device__ __forceinline__ void epilogue_pass(uint32_t d_tmem, uint32_t a_park, 
   if (kTape && kRelu) *tape_mask = make_uint2(mbits[0], mbits[1]);
 }
 
+// The same pass for hidden = 128 kernels (one pass per layer, nothing held).  tcgen05.wait::ld waits for EVERY
+// outstanding load of the thread, so the 16-column double buffering above is a chain of four ~200-cycle round trips
+// (850 - 1 100 cycles per pass, longer than the 8-MMA pass of the other tile, which made the MMA -> epilogue -> MMA
+// chain of a tile the limiter at hidden 128).  Here the warp's 64 columns are requested with
+// fewer, deeper round trips - the hidden-128 kernels have the registers (no held[] array):
+//   DEXNERF_WIDE_EPI == 1: both 32-column halves at once, ONE round trip, accumulator released before the arithmetic;
+//   DEXNERF_WIDE_EPI == 2: three 16-column buffers, two loads in flight while a third slice is processed.
+// The sigma head accumulates in four independent partial sums (a 64-deep dependent FMA chain otherwise).
+#ifndef DEXNERF_WIDE_EPI
+#define DEXNERF_WIDE_EPI 1
+#endif
+template <bool kRelu, bool kSig, bool kDbg, bool kTape>
+__device__ __forceinline__ void epilogue_pass_wide(uint32_t d_tmem, uint32_t a_store, uint32_t bias, uint32_t wa,
+                                                   float& sigma, uint32_t dfree_bar, float* dbg_dst,
+                                                   uint8_t* tape_row, uint2* tape_mask) {
+  uint32_t mbits[2] = {0u, 0u};
+  float sg[4] = {0.f, 0.f, 0.f, 0.f};
+  // 16 columns [c0, c0 + 16) of this warp's 64: + bias, head, ReLU, pack -> pk[0..8)
+  auto slice16 = [&](const uint32_t* v, int c0, uint32_t* pk) {
+    if (kDbg && dbg_dst) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) dbg_dst[c0 + i] = __uint_as_float(v[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      const float4 b4 = lds128(bias + (uint32_t)((c0 + i) * 4));
+      float x0, x1, x2, x3;
+      add_f32x2(v[i], v[i + 1], b4.x, b4.y, x0, x1);
+      add_f32x2(v[i + 2], v[i + 3], b4.z, b4.w, x2, x3);
+      if (kSig) {
+        const float4 w4 = lds128(wa + (uint32_t)((c0 + i) * 4));
+        sg[0] = fmaf(kRelu ? fmaxf(x0, 0.0f) : x0, w4.x, sg[0]);
+        sg[1] = fmaf(kRelu ? fmaxf(x1, 0.0f) : x1, w4.y, sg[1]);
+        sg[2] = fmaf(kRelu ? fmaxf(x2, 0.0f) : x2, w4.z, sg[2]);
+        sg[3] = fmaf(kRelu ? fmaxf(x3, 0.0f) : x3, w4.w, sg[3]);
+      }
+      pk[i / 2] = pack_bf16(x0, x1, kRelu);
+      pk[i / 2 + 1] = pack_bf16(x2, x3, kRelu);
+    }
+    tmem_st8(a_store + (uint32_t)(c0 / 2), pk);
+    if (kTape) {
+      stg128(tape_row + (c0 / 8) * 1024, pk[0], pk[1], pk[2], pk[3]);
+      stg128(tape_row + (c0 / 8 + 1) * 1024, pk[4], pk[5], pk[6], pk[7]);
+      if (kRelu) mbits[c0 >> 5] |= relu_bits16(pk) << (c0 & 16);
+    }
+  };
+#if DEXNERF_WIDE_EPI == 1
+  uint32_t v[2][32];
+  tmem_ld32_issue(d_tmem, v[0]);
+  tmem_ld32_issue(d_tmem + 32, v[1]);
+  tmem_ld32_wait(v[0]);
+  tmem_ld32_tie(v[1]);
+  tc_fence_before();
+  mbar_arrive(dfree_bar);                 // all 64 columns are in registers
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint32_t pk[8];
+    slice16(&v[h][0], h * 32, pk);
+    slice16(&v[h][16], h * 32 + 16, pk);
+  }
+#else
+  uint32_t v[3][16];
+  tmem_ld16_issue(d_tmem, v[0]);
+  tmem_ld16_issue(d_tmem + 16, v[1]);
+  tmem_ld16_wait(v[0]);
+  tmem_ld16_tie(v[1]);
+  tmem_ld16_issue(d_tmem + 32, v[2]);
+  uint32_t pk[8];
+  slice16(v[0], 0, pk);
+  tmem_ld16_issue_tied(d_tmem + 48, v[0], v[1]);
+  slice16(v[1], 16, pk);
+  tmem_ld16_wait(v[2]);
+  tmem_ld16_tie(v[0]);
+  tc_fence_before();
+  mbar_arrive(dfree_bar);
+  slice16(v[2], 32, pk);
+  slice16(v[0], 48, pk);
+#endif
+  if (kSig) sigma += (sg[0] + sg[1]) + (sg[2] + sg[3]);
+  if (kTape && kRelu) *tape_mask = make_uint2(mbits[0], mbits[1]);
+}
+
 // ------------------------------------------------------------------ the kernel
 // kPaper: PaperNeRFModel's layer table (tc_plan.cuh) - layers narrower than H (128 -> 128 in an H = 256 kernel),
 // a sigma head on an unrectified layer; a separate instantiation so that the Flexible kernels stay as they are.
@@ -660,6 +742,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
               // single-pass layer (dir branch of the Paper model): nothing held, nothing to park
               if (kind == 0) epilogue_pass<false, false, false, false, kDbg, kTape>(d_tmem, a_park, a_store, bp, wp, sigma, held, dfree, dbg_dst, stamps, tape_row, tape_mask);
               else epilogue_pass<true, false, false, false, kDbg, kTape>(d_tmem, a_park, a_store, bp, wp, sigma, held, dfree, dbg_dst, stamps, tape_row, tape_mask);
+              tmem_wait_st();
+              tc_fence_before();
+              mbar_arrive(bar(B_aready(t)));
+            } else if (H == 128 && DEXNERF_WIDE_EPI != 0) {
+              // hidden 128: one pass per layer; the accumulator is fetched with deeper round trips (see above)
+              if (kind == 0) epilogue_pass_wide<false, false, kDbg, kTape>(d_tmem, a_store, bp, wp, sigma, dfree, dbg_dst, tape_row, tape_mask);
+              else if (kind == 1) epilogue_pass_wide<true, false, kDbg, kTape>(d_tmem, a_store, bp, wp, sigma, dfree, dbg_dst, tape_row, tape_mask);
+              else if (kPaper && kind == 3) epilogue_pass_wide<false, true, kDbg, kTape>(d_tmem, a_store, bp, wp, sigma, dfree, dbg_dst, tape_row, tape_mask);
+              else epilogue_pass_wide<true, true, kDbg, kTape>(d_tmem, a_store, bp, wp, sigma, dfree, dbg_dst, tape_row, tape_mask);
               tmem_wait_st();
               tc_fence_before();
               mbar_arrive(bar(B_aready(t)));

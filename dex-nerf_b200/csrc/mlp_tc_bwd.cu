@@ -57,6 +57,11 @@ struct BwdParams {
   int relu[kMaxLayers];       // forward ReLU flag of each layer (its G needs the mask)
   uint32_t* ready;            // fused launch: [kMaxLayers + 1][n_tiles] completion counters of the G images (else NULL)
   int64_t n_tiles_pad;        // tiles the tape is laid out for (an even count)
+  // back-pressure (shared-SM kernel): a chain may start tile t only when the weight-gradient side has finished
+  // throttle_items * (t - throttle_window + 1) (item, tile) units, so that the gradient images in flight stay
+  // L2-resident; NULL = no throttle
+  const uint32_t* consumed_total;
+  int throttle_items, throttle_window;
 };
 
 // ---- cross-CTA hand-off of a finished G image (fused launch).  Producer: the warp's stores are ordered before
@@ -79,28 +84,50 @@ static __device__ __noinline__ void flag_timeout(int who) {
   printf("dexnerf fused backward: flag wait timeout (site %d, block %d, thread %d)\n", who, blockIdx.x, threadIdx.x);
   __trap();
 }
-__device__ __forceinline__ void wait_image(const uint32_t* flag, uint32_t expected, int who) {
+// soft (bring-up, variant bit 6): give up after a short while and carry on with whatever the tape holds
+__device__ __forceinline__ void wait_image(const uint32_t* flag, uint32_t expected, int who, bool soft) {
   uint32_t spins = 0;
   while (ld_acquire_u32(flag) < expected) {
     __nanosleep(64);
-    if (++spins > (1u << 22)) flag_timeout(who);     // seconds: a protocol bug must trap, not hang the GPU
+    ++spins;
+    if (soft && spins > (1u << 14)) return;
+    if (spins > (1u << 22)) flag_timeout(who);     // seconds: a protocol bug must trap, not hang the GPU
   }
 }
 
-struct BSmem {
+// The backward reads only the head weights of the const block, [off_walpha, n_const) = H + 4 + 3 H / 2 + 4 floats; the
+// shared-SM kernel keeps just those (kCompact) and spends the shared memory on weight slots instead.
+constexpr int kCompactConstFloats = 1024;
+template <int kSlots, bool kCompact = false>
+struct BSmemT {
   static constexpr int w_slots = 0;
-  static constexpr int consts = w_slots + kBSlots * kBSlotBytes;
-  static constexpr int bars = consts + kMaxConstFloats * 4;
-  static constexpr int n_bars = 2 * kBSlots + 8;
+  static constexpr int consts = w_slots + kSlots * kBSlotBytes;
+  static constexpr int bars = consts + (kCompact ? kCompactConstFloats : kMaxConstFloats) * 4;
+  static constexpr int n_bars = 2 * kSlots + 6;
   static constexpr int tmem_ptr = bars + n_bars * 8;
-  static constexpr int total = tmem_ptr + 16;
+  static constexpr int img_cnt = tmem_ptr + 16;      // fused: uint32[2], epilogue warps that have stored their pass
+  static constexpr int total = (img_cnt + 16 + 127) / 128 * 128;
 };
-__device__ __forceinline__ int BB_wfull(int s) { return s; }
-__device__ __forceinline__ int BB_wempty(int s) { return kBSlots + s; }
-__device__ __forceinline__ int BB_aready(int t) { return 2 * kBSlots + t; }
-__device__ __forceinline__ int BB_dfull(int t) { return 2 * kBSlots + 2 + t; }
-__device__ __forceinline__ int BB_dfree(int t) { return 2 * kBSlots + 4 + t; }
-__device__ __forceinline__ int BB_img(int t) { return 2 * kBSlots + 6 + t; }     // fused: "this pass's G rows are stored"
+using BSmem = BSmemT<kBSlots>;
+constexpr int kBSlotsShared = 7;      // weight ring of the chain when it shares the SM with the weight-gradient GEMM
+// whole-CTA barrier with an explicit thread count: the role groups of the shared-SM kernel reach it from different
+// call sites
+__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
+// fused launch: epilogue warp -> signaller hand-off through a MONOTONIC shared-memory counter (an mbarrier's
+// parity wait cannot tell phase k from phase k + 2, and the signaller, which pays a gpu-scope fence per image, may
+// lag the epilogue by several passes)
+__device__ __forceinline__ void img_stored(uint32_t cnt_addr, int lane) {
+  __syncwarp();
+  if (lane == 0) asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(cnt_addr) : "memory");
+}
+__device__ __forceinline__ void img_wait(uint32_t cnt_addr, uint32_t need, int who) {
+  uint32_t v, spins = 0;
+  while (true) {
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(cnt_addr) : "memory");
+    if (v >= need) break;
+    if (++spins > kSpinLimit) barrier_timeout(who);
+  }
+}
 
 // One backward epilogue pass of one warp over its 64 accumulator columns: optional rank-1 term
 // d_sigma * w_alpha, optional ReLU mask, bf16 pack, A-operand store (held / parked / direct) and
@@ -153,38 +180,54 @@ __device__ __forceinline__ void bwd_epilogue_pass(uint32_t d_tmem, uint32_t a_pa
   }
 }
 
-// cta / n_cta: this CTA's index among the chain CTAs (the whole grid in the stand-alone kernel)
-template <int H, bool kFused>
+// cta / n_cta: this CTA's index among the chain CTAs (the whole grid in the stand-alone kernel).
+// kTiles: 128-sample tiles in flight per CTA - 2 (a pair: one tile's MMA pass hides the other's epilogue; all 512
+// TMEM columns) or 1 (256 columns: the shared-SM kernel, where the weight-gradient GEMM of the same CTA keeps the
+// tensor pipe busy during the epilogue).  kSlots: weight ring depth.  Threads of warps >= 4 + 8 * kTiles belong to
+// somebody else and only take part in the two CTA-wide barriers.
+template <int H, bool kFused, int kTiles, int kSlots>
 __device__ __forceinline__ void chain_body(const BwdParams& P, uint8_t* smem, const int cta, const int n_cta) {
+  constexpr bool kCompact = kSlots != kBSlots;       // (the shared-SM instantiation)
+  using BSmem = BSmemT<kSlots, kCompact>;
+  const int c_base = kCompact ? P.off_walpha : 0;    // first float of the const block that is kept in shared memory
+  auto BB_wfull = [](int s) { return s; };
+  auto BB_wempty = [](int s) { return kSlots + s; };
+  auto BB_aready = [](int t) { return 2 * kSlots + t; };
+  auto BB_dfull = [](int t) { return 2 * kSlots + 2 + t; };
+  auto BB_dfree = [](int t) { return 2 * kSlots + 4 + t; };
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bars = sbase + BSmem::bars;
   auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t n_tiles = (P.m_total + kTileM - 1) / kTileM;
-  const int64_t n_pairs = (n_tiles + 1) / 2;
+  // fused launches walk every tile the tape is laid out for (an even count): the weight-gradient side waits for
+  // the flags of the padding tile too (its gradients are zero)
+  const int64_t n_tiles = kFused ? P.n_tiles_pad : (P.m_total + kTileM - 1) / kTileM;
+  const int64_t n_pairs = (n_tiles + kTiles - 1) / kTiles;     // work units: tile pairs, or single tiles
   constexpr int kPass = H / 128;          // N = 128 passes of a layer
   const int n_steps = P.nl - 1;           // MMA layers: step j consumes G[nl-1-j], produces G[nl-2-j]
+  constexpr int kChainThreads = (4 + 8 * kTiles) * 32;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kBSlots; ++s) { mbar_init(bar(BB_wfull(s)), 1); mbar_init(bar(BB_wempty(s)), 2); }
-    for (int t = 0; t < 2; ++t) {
+    for (int s = 0; s < kSlots; ++s) { mbar_init(bar(BB_wfull(s)), 1); mbar_init(bar(BB_wempty(s)), kTiles); }
+    for (int t = 0; t < kTiles; ++t) {
       mbar_init(bar(BB_aready(t)), kBEpiThreads);
       mbar_init(bar(BB_dfull(t)), 1);
       mbar_init(bar(BB_dfree(t)), kBEpiThreads);
-      mbar_init(bar(BB_img(t)), kBEpiThreads);
     }
+    reinterpret_cast<volatile uint32_t*>(smem + BSmem::img_cnt)[0] = 0u;
+    reinterpret_cast<volatile uint32_t*>(smem + BSmem::img_cnt)[1] = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + BSmem::tmem_ptr), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  {
+  if (threadIdx.x < kChainThreads) {
     float* c = reinterpret_cast<float*>(smem + BSmem::consts);
-    for (int i = threadIdx.x; i < P.n_const; i += kBThreads) c[i] = P.consts[i];
+    for (int i = c_base + threadIdx.x; i < P.n_const; i += kChainThreads) c[i - c_base] = P.consts[i];
   }
   tc_fence_before();
-  __syncthreads();
+  cta_sync();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + BSmem::tmem_ptr);
 
@@ -195,12 +238,25 @@ __device__ __forceinline__ void chain_body(const BwdParams& P, uint8_t* smem, co
 #pragma unroll 1
     for (int64_t pair = cta; pair < n_pairs; pair += n_cta) {
       const uint8_t* src = P.weights_t;
+      if (kFused && P.consumed_total) {
+        // back-pressure: the first weight chunk of a tile is not requested (so the issuer does not start it) until
+        // the weight-gradient side is within `throttle_window` tiles of it
+        const int64_t need = (int64_t)P.throttle_items * (pair * kTiles - P.throttle_window + 1);
+        if (need > 0 && lane == 0) {
+          uint32_t spins = 0;
+          while ((int64_t)ld_acquire_u32(P.consumed_total) < need) {
+            __nanosleep(256);
+            if (++spins > (1u << 22)) flag_timeout(25);
+          }
+        }
+        __syncwarp();
+      }
 #pragma unroll 1
       for (int j = 0; j < n_steps; ++j) {
         const int nc = (j == 0 ? H / 2 : H) / 64;
 #pragma unroll 1
         for (int pc = 0; pc < kPass * nc; ++pc, ++cnt) {
-          const uint32_t slot = cnt % kBSlots, ph = (cnt / kBSlots) & 1;
+          const uint32_t slot = cnt % kSlots, ph = (cnt / kSlots) & 1;
           mbar_wait(bar(BB_wempty(slot)), ph ^ 1, 10);
           if (leader) {
             mbar_arrive_expect_tx(bar(BB_wfull(slot)), kBSlotBytes);
@@ -229,7 +285,7 @@ __device__ __forceinline__ void chain_body(const BwdParams& P, uint8_t* smem, co
         for (int p = 0; p < kPass; ++p) {
           const uint32_t slot_p = w_slot, phase_p = w_phase;
 #pragma unroll
-          for (int t = 0; t < 2; ++t) {
+          for (int t = 0; t < kTiles; ++t) {
             const uint32_t a_tmem = tmem_base + (uint32_t)(t * 256);
             const uint32_t d_tmem = a_tmem + 128;
             if (p == 0) {
@@ -253,16 +309,16 @@ __device__ __forceinline__ void chain_body(const BwdParams& P, uint8_t* smem, co
                 tc_commit(bar(BB_wempty(slot)));
               }
               __syncwarp();
-              if (++slot == kBSlots) { slot = 0; phase ^= 1; }
+              if (++slot == kSlots) { slot = 0; phase ^= 1; }
             }
             if (leader) tc_commit(bar(BB_dfull(t)));
             __syncwarp();
-            if (t == 1) { w_slot = slot; w_phase = phase; }
+            if (t == kTiles - 1) { w_slot = slot; w_phase = phase; }
           }
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 4 + 8 * kTiles) {
     // =============================== epilogue ===============================
     const int e = warp - 4;
     const int t = e >> 3, hs = (e >> 2) & 1, q = warp & 3;
@@ -276,7 +332,7 @@ __device__ __forceinline__ void chain_body(const BwdParams& P, uint8_t* smem, co
     const int half = row >> 6, r64 = row & 63;
 #pragma unroll 1
     for (int64_t pair = cta; pair < n_pairs; pair += n_cta) {
-      const int64_t tile = pair * 2 + t;
+      const int64_t tile = pair * kTiles + t;
       const int64_t g = tile * kTileM + row;
       const float4 d = (g < P.m_total) ? P.d_rf[g] : make_float4(0.f, 0.f, 0.f, 0.f);
       // ---- G of layers_dir[0]: (W_rgb^T d_rgb) masked by y > 0, on the CUDA cores
@@ -285,7 +341,7 @@ __device__ __forceinline__ void chain_body(const BwdParams& P, uint8_t* smem, co
         const int col0 = hs * mine;
         const int ld = P.nl - 1;
         const uint2 ym = reinterpret_cast<const uint2*>(P.tape + P.mask_off[ld] + tile * 2048 + hs * 1024)[row];
-        const float* wr = s_const + P.off_wrgb + col0;
+        const float* wr = s_const + (P.off_wrgb - c_base) + col0;
         uint8_t* trow = P.tape + P.grad_off[ld] + tile * (int64_t)(hw * 256) + half * (hw * 128) +
                         (col0 / 8) * 1024 + r64 * 16;
 #pragma unroll
@@ -310,7 +366,7 @@ __device__ __forceinline__ void chain_body(const BwdParams& P, uint8_t* smem, co
           *reinterpret_cast<uint4*>(hrow) = make_uint4(pack_bf16(d.x, d.y, false), pack_bf16(d.z, d.w, false), 0u, 0u);
           *reinterpret_cast<uint4*>(hrow + 1024) = make_uint4(0u, 0u, 0u, 0u);
         }
-        if (kFused) mbar_arrive(bar(BB_img(t)));      // G of the dir layer (+ the head operand) is stored
+        if (kFused) img_stored(sbase + BSmem::img_cnt + 4u * (uint32_t)t, lane);   // G of the dir layer (+ the head operand) is stored
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(bar(BB_aready(t)));
@@ -331,7 +387,7 @@ __device__ __forceinline__ void chain_body(const BwdParams& P, uint8_t* smem, co
                                                   (p * 2 + hs) * 1024)[row];
           uint8_t* trow = P.tape + P.grad_off[dst] + tile * (int64_t)(H * 256) + half * (H * 128) +
                           (p * 16 + hs * 8) * 1024 + r64 * 16;
-          const uint32_t wa = sbase + BSmem::consts + (uint32_t)(P.off_walpha + p * 128 + hs * 64) * 4;
+          const uint32_t wa = sbase + BSmem::consts + (uint32_t)(P.off_walpha - c_base + p * 128 + hs * 64) * 4;
           const uint32_t a_park = a_tmem + (uint32_t)(hs * 32);
           const uint32_t a_store = a_tmem + (uint32_t)(p * 64 + hs * 32);
           const uint32_t dfree = bar(BB_dfree(t));
@@ -351,38 +407,37 @@ __device__ __forceinline__ void chain_body(const BwdParams& P, uint8_t* smem, co
             tc_fence_before();
             mbar_arrive(bar(BB_aready(t)));
           }
-          if (kFused) mbar_arrive(bar(BB_img(t)));    // this pass's rows of G[dst] are stored
+          if (kFused) img_stored(sbase + BSmem::img_cnt + 4u * (uint32_t)t, lane);   // this pass's rows of G[dst] are stored
         }
       }
     }
-  } else if (kFused) {
+  } else if (kFused && warp >= 2 && warp < 2 + kTiles) {
     // =============================== signallers (fused launch; warp 2: tile 0, warp 3: tile 1) ===============
-    // The epilogue threads only arrive on a shared-memory barrier after their stores (release.cta); THIS warp pays
-    // the gpu-scope fence (~1 us) and publishes the image to the weight-gradient CTAs, off the
-    // MMA -> epilogue -> MMA chain.  By cumulativity the fence orders the 256 threads' stores it has synchronised
-    // with before the flag.
+    // The 8 epilogue warps of a tile only bump a shared-memory counter after their stores (release.cta); THIS warp
+    // pays the gpu-scope fence (~1 us) and publishes the image to the weight-gradient CTAs, off the
+    // MMA -> epilogue -> MMA chain.  By cumulativity the fence orders the stores it has synchronised with before
+    // the flag.
     const int t = warp - 2;
-    uint32_t ph = 0;
+    const uint32_t cnt = sbase + BSmem::img_cnt + 4u * (uint32_t)t;
+    uint32_t need = 0;            // epilogue-warp arrivals so far: 8 per pass
 #pragma unroll 1
     for (int64_t pair = cta; pair < n_pairs; pair += n_cta) {
-      const int64_t tile = pair * 2 + t;
-      mbar_wait(bar(BB_img(t)), ph, 15);
-      ph ^= 1;
+      const int64_t tile = pair * kTiles + t;
+      need += 8;
+      img_wait(cnt, need, 15);
       signal_image(P.ready + (int64_t)(P.nl - 1) * P.n_tiles_pad + tile, lane);
       signal_image(P.ready + (int64_t)kMaxLayers * P.n_tiles_pad + tile, lane);
 #pragma unroll 1
       for (int j = 0; j < n_steps; ++j) {
-        for (int p = 0; p < kPass; ++p) {
-          mbar_wait(bar(BB_img(t)), ph, 15);
-          ph ^= 1;
-        }
+        need += 8 * kPass;
+        img_wait(cnt, need, 15);
         signal_image(P.ready + (int64_t)(P.nl - 2 - j) * P.n_tiles_pad + tile, lane);
       }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  cta_sync();
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
@@ -392,7 +447,7 @@ template <int H>
 __global__ void __launch_bounds__(kBThreads, 1) mlp_tc_bwd_dx_kernel(const __grid_constant__ BwdParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  chain_body<H, false>(P, smem, (int)blockIdx.x, (int)gridDim.x);
+  chain_body<H, false, 2, kBSlots>(P, smem, (int)blockIdx.x, (int)gridDim.x);
 }
 
 // ---- transposed weight images for the dX chain (one 16 KB chunk = 128 in-features x 64 out-features)
@@ -419,7 +474,7 @@ constexpr int kWStageA = 32768;     // up to 2 M-blocks x 16 feature groups x 64
 constexpr int kWStageG = 32768;     // up to 32 feature groups (N = 256)
 constexpr int kWStages = 3;
 constexpr int kWThreads = 256;      // producer, MMA issuer, TMEM allocator, (idle), 4 reducer warps
-constexpr int kMaxDwItems = 24;     // <= 16 layers + 2 encoding parts + 2 heads
+constexpr int kMaxDwItems = 40;     // <= 16 layers (x 2 M blocks in the shared-SM kernel) + encoding parts + heads
 
 struct DwItem {
   int64_t a_off;     // tape offset of the A image array
@@ -445,19 +500,28 @@ struct DwParams {
   int64_t n_tiles;
   int n_items;
   int variant;       // bring-up knob: bit 0 swaps the LBO / SBO fields of the MN-major descriptors
+  int n_cta_total;         // CTAs that own an item (the shared-SM kernel launches one CTA per SM regardless)
   const uint32_t* ready;   // fused launch: [kMaxLayers + 1][n_tiles] image-complete counters written by the chain CTAs
   uint32_t* consumed;      // fused launch: [kMaxLayers + 1][n_tiles][2] readers done with a half image
+  uint32_t* consumed_total;   // shared-SM kernel: (item, tile) units finished - the chains' back-pressure signal
   DwItem items[kMaxDwItems];
 };
 
-struct WSmem {
+template <int kStages, int kStageA, int kStageG>
+struct WSmemT {
   static constexpr int a = 0;
-  static constexpr int g = a + kWStages * kWStageA;
-  static constexpr int bars = g + kWStages * kWStageG;
-  static constexpr int n_bars = 2 * kWStages + 1;
+  static constexpr int g = a + kStages * kStageA;
+  static constexpr int bars = g + kStages * kStageG;
+  static constexpr int n_bars = 2 * kStages + 1;
   static constexpr int tmem_ptr = bars + n_bars * 8;
   static constexpr int total = tmem_ptr + 16;
 };
+using WSmem = WSmemT<kWStages, kWStageA, kWStageG>;
+// the weight-gradient GEMM when it shares the SM with the chain: ONE M block per item (256 TMEM columns), so a stage
+// is 16 KB of A (16 feature groups x 64 samples) + 32 KB of G, two stages
+constexpr int kWStagesShared = 2;
+constexpr int kWStageAShared = 16384;
+using WSmemShared = WSmemT<kWStagesShared, kWStageAShared, kWStageG>;
 
 __device__ __forceinline__ void red_add_f32(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
@@ -472,15 +536,24 @@ __device__ __forceinline__ void discard_l2(const uint8_t* p) {
 }
 
 // cta: this CTA's index among the weight-gradient CTAs.  kFused: the G images come from chain CTAs of the same launch
-// (wait for their flags, interleaved tile split, discard after use); all blockDim threads call this, warps >= 8 idle.
-template <bool kFused>
-__device__ __forceinline__ void dw_body(const DwParams& P, uint8_t* smem, const int cta) {
+// (wait for their flags, interleaved tile split, discard after use).
+// kWarp0 = 0: the CTA is all ours (8 working warps: producer, issuer, TMEM allocator, -, 4 reducers; further warps
+// idle).  kWarp0 > 0 (shared-SM kernel): our 8 warps start at warp kWarp0, the TMEM allocation belongs to the chain
+// group (*shared_tmem holds its base) and we use the columns from kCol0 on; the other warps of the CTA only meet us
+// at the two CTA-wide barriers.
+template <bool kFused, int kWarp0, int kCol0, typename WS, int kStages, int kStageA>
+__device__ __forceinline__ void dw_body(const DwParams& P, uint8_t* smem, const int cta, const uint8_t* shared_tmem) {
+  using WSmem = WS;
+  constexpr int kWStages = kStages;
+  constexpr int kWStageA = kStageA;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bars = sbase + WSmem::bars;
   auto full = [&](int s) { return bars + 8u * (uint32_t)s; };
   auto empty = [&](int s) { return bars + 8u * (uint32_t)(kWStages + s); };
   const uint32_t acc_bar = bars + 8u * (uint32_t)(2 * kWStages);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (int)(threadIdx.x >> 5) - kWarp0, lane = threadIdx.x & 31;
+  const int tid = (int)threadIdx.x - kWarp0 * 32;                 // thread index within the group
+  const int n_group = kWarp0 ? 256 : (int)blockDim.x;
 
   // which item / which slice of its tiles
   int it = 0;
@@ -491,27 +564,29 @@ __device__ __forceinline__ void dw_body(const DwParams& P, uint8_t* smem, const 
   const int64_t tile_begin = kFused ? split : P.n_tiles * split / I.n_cta;
   const int64_t tile_end = kFused ? P.n_tiles : P.n_tiles * (split + 1) / I.n_cta;
   const int64_t tile_step = kFused ? I.n_cta : 1;
-  const int64_t n_my_tiles = tile_end > tile_begin ? (tile_end - tile_begin + tile_step - 1) / tile_step : 0;
+  const bool has_item = !kWarp0 || cta < P.n_cta_total;
+  const int64_t n_my_tiles = (has_item && tile_end > tile_begin) ? (tile_end - tile_begin + tile_step - 1) / tile_step : 0;
   const int64_t n_stage_total = n_my_tiles * 2;     // half-tiles
   const uint32_t a_bytes = (uint32_t)I.a_fgs * 1024u, g_bytes = (uint32_t)I.g_fg * 1024u;
 
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     for (int s = 0; s < kWStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1 + 128); }
     mbar_init(acc_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {
+  if (kWarp0 == 0 && warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + WSmem::tmem_ptr), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   // the MMA reads 16 feature groups per M block even when the image has fewer: keep the tail finite
-  for (int i = threadIdx.x; i < kWStages * kWStageA / 16; i += (int)blockDim.x)
+  for (int i = tid; i < kWStages * kWStageA / 16; i += n_group)
     reinterpret_cast<uint4*>(smem + WSmem::a)[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async();
   tc_fence_before();
-  __syncthreads();
+  cta_sync();
   tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + WSmem::tmem_ptr);
+  const uint32_t tmem_base = *reinterpret_cast<const volatile uint32_t*>(kWarp0 ? shared_tmem : smem + WSmem::tmem_ptr) +
+                             (uint32_t)kCol0;
 
   if (warp == 0) {
     // =============================== producer ===============================
@@ -520,48 +595,48 @@ __device__ __forceinline__ void dw_body(const DwParams& P, uint8_t* smem, const 
       const int64_t tile = tile_begin + (s >> 1) * tile_step;
       return P.tape + I.g_off + tile * (int64_t)(I.g_fg * 2048) + (int64_t)(s & 1) * (I.g_fg * 1024);
     };
+    // The producer's critical path per stage is: slot free -> issue the two bulk copies.  Everything else of the
+    // fused hand-off is done AFTER the issue: dropping the previous occupant's lines from L2 and - one tile ahead -
+    // the acquire of the next tile's flag (a ~1 us global round trip even when the flag is long set).
+    auto acquire_tile = [&](int64_t s) {
+      const int64_t tile = tile_begin + (s >> 1) * tile_step;
+      if (lane == 0 && !(P.variant & 16))
+        wait_image(P.ready + (int64_t)I.flag_row * P.n_tiles + tile, 1u, 24, (P.variant & 64) != 0);
+      __syncwarp();
+    };
+    const bool prof = (P.variant & 128) != 0;          // bring-up: where does the producer's time go?
+    long long t_empty = 0, t_flag = 0, t_disc = 0, t_all = prof ? clock64() : 0;
+    if (kFused && n_stage_total > 0) acquire_tile(0);
     // fused: kWStages extra rounds drain the ring so that the last images are discarded too
 #pragma unroll 1
     for (int64_t s = 0; s < n_stage_total + (kFused ? kWStages : 0); ++s) {
       const int st = (int)(s % kWStages);
       const uint32_t ph = (uint32_t)((s / kWStages) & 1);
+      long long c0 = prof ? clock64() : 0;
       mbar_wait(empty(st), ph ^ 1, 20);
-      if (kFused && s >= kWStages) {
-        // the half image that occupied this stage has been read by the MMAs and the column sums of THIS item; the
-        // last of its readers drops its lines from L2 (they are dirty there and would be written back otherwise)
-        const int64_t sp = s - kWStages;
-        const int64_t tile = tile_begin + (sp >> 1) * tile_step;
-        uint32_t last = 1;
-        if (I.n_consumers > 1) {
-          uint32_t old = 0;
-          if (lane == 0)
-            old = atomicAdd(P.consumed + ((int64_t)I.flag_row * P.n_tiles + tile) * 2 + (sp & 1), 1u);
-          last = (__shfl_sync(0xffffffffu, old, 0) + 1 == (uint32_t)I.n_consumers) ? 1u : 0u;
-        }
-        if (last) {
-          const uint8_t* g = g_image(sp);
-          for (uint32_t off = (uint32_t)lane * 128u; off < g_bytes; off += 32u * 128u) discard_l2(g + off);
-        }
-      }
-      if (s < n_stage_total) {
-        if (kFused && (s & 1) == 0) {
-          const int64_t tile = tile_begin + (s >> 1) * tile_step;
-          if (lane == 0) wait_image(P.ready + (int64_t)I.flag_row * P.n_tiles + tile, 1u, 24);
-          __syncwarp();
-          asm volatile("fence.proxy.async.global;" ::: "memory");   // the image is read by the async proxy next
-        }
-        if (leader) {
-          const int64_t tile = tile_begin + (s >> 1) * tile_step;
-          const int half = (int)(s & 1);
-          const uint8_t* a_src = P.tape + I.a_off + tile * (int64_t)(I.a_fg * 2048) + (int64_t)half * (I.a_fg * 1024) +
-                                 (int64_t)I.a_fg0 * 1024;
-          mbar_arrive_expect_tx(full(st), a_bytes + g_bytes);
-          bulk_g2s(sbase + WSmem::a + st * kWStageA, a_src, a_bytes, full(st));
-          bulk_g2s(sbase + WSmem::g + st * kWStageG, g_image(s), g_bytes, full(st));
-        }
+      if (prof) { t_empty += clock64() - c0; c0 = clock64(); }
+      if (s < n_stage_total && leader) {
+        const int64_t tile = tile_begin + (s >> 1) * tile_step;
+        const int half = (int)(s & 1);
+        const uint8_t* a_src = P.tape + I.a_off + tile * (int64_t)(I.a_fg * 2048) + (int64_t)half * (I.a_fg * 1024) +
+                               (int64_t)I.a_fg0 * 1024;
+        mbar_arrive_expect_tx(full(st), a_bytes + g_bytes);
+        bulk_g2s(sbase + WSmem::a + st * kWStageA, a_src, a_bytes, full(st));
+        bulk_g2s(sbase + WSmem::g + st * kWStageG, g_image(s), g_bytes, full(st));
       }
       __syncwarp();
+      if (kFused && s >= kWStages) {
+        // (item, tile) finished: the chains' back-pressure signal
+        const int64_t sp = s - kWStages;
+        if (P.consumed_total && (sp & 1) == 1 && lane == 0) atomicAdd(P.consumed_total, 1u);
+      }
+      if (prof) { t_disc += clock64() - c0; c0 = clock64(); }
+      if (kFused && (s & 1) == 1 && s + 1 < n_stage_total) acquire_tile(s + 1);
+      if (prof) t_flag += clock64() - c0;
     }
+    if (prof && lane == 0 && (cta % 37) == 0)
+      printf("dw producer cta %d item %d (%d ctas, mblk %d, gfg %d): stages %lld total %lld cyc | wait-empty %lld issue+discard %lld wait-flag %lld\n",
+             cta, it, I.n_cta, I.n_mblk, I.g_fg, (long long)n_stage_total, clock64() - t_all, t_empty, t_disc, t_flag);
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
     const bool leader = elect_one();
@@ -574,11 +649,15 @@ __device__ __forceinline__ void dw_body(const DwParams& P, uint8_t* smem, const 
     uint32_t lbo = 128 >> 4, sbo = 1024 >> 4;
     if (P.variant & 1) { const uint32_t x = lbo; lbo = sbo; sbo = x; }
     const uint64_t desc_hi = ((uint64_t)sbo << 32) | (1ull << 46);
+    const bool prof = (P.variant & 128) != 0;
+    long long t_full = 0;
 #pragma unroll 1
     for (int64_t s = 0; s < n_stage_total; ++s) {
       const int st = (int)(s % kWStages);
       const uint32_t ph = (uint32_t)((s / kWStages) & 1);
+      const long long c0 = prof ? clock64() : 0;
       mbar_wait(full(st), ph, 21);
+      if (prof) t_full += clock64() - c0;
       tc_fence_after();
       const uint32_t a_lo = (((sbase + WSmem::a + st * kWStageA) >> 4) & 0x3FFF) | (lbo << 16);
       const uint32_t g_lo = (((sbase + WSmem::g + st * kWStageG) >> 4) & 0x3FFF) | (lbo << 16);
@@ -587,7 +666,7 @@ __device__ __forceinline__ void dw_body(const DwParams& P, uint8_t* smem, const 
         for (int ks = 0; ks < ((P.variant & 4) ? 0 : 4); ++ks) {        // 64 samples = 4 x K16; a K step = 2 core matrices = 256 B
           for (int mb = 0; mb < I.n_mblk; ++mb)
             mma_ss(tmem_base + (uint32_t)(mb * 256),
-                   desc_hi | (uint64_t)(a_lo + (uint32_t)(mb * 16384 + ks * 256) / 16),
+                   desc_hi | (uint64_t)(a_lo + (uint32_t)(mb * 16384 + ks * 256) / 16),   // (one M block in the shared-SM kernel)
                    desc_hi | (uint64_t)(g_lo + (uint32_t)(ks * 256) / 16), idesc, (s | ks) ? 1u : 0u);
         }
         tc_commit(empty(st));
@@ -596,13 +675,15 @@ __device__ __forceinline__ void dw_body(const DwParams& P, uint8_t* smem, const 
     }
     if (leader) tc_commit(acc_bar);
     __syncwarp();
+    if (prof && lane == 0 && (cta % 37) == 0) printf("dw issuer   cta %d: wait-full %lld cyc\n", cta, t_full);
   } else if (warp >= 4 && warp < 8) {
     // =============================== bias column sums + final reduction ===============================
     // thread j owns feature group j / 4 of G (8 features) and every 4th sample of the half-tile:
     // one 16-byte shared-memory load per sample row, rows rotated by the feature group so that the
     // four wavefronts of a warp load are conflict free; the four sample phases meet in a shuffle at
     // the very end
-    const int j = threadIdx.x - 128;            // 0..127
+    const int j = tid - 128;                    // 0..127
+    __shared__ uint32_t s_last;
     const bool has_bias = I.b_out >= 0;
     const int fg = j >> 2, sub = j & 3;
     const bool mine = has_bias && fg < I.g_fg;
@@ -612,6 +693,26 @@ __device__ __forceinline__ void dw_body(const DwParams& P, uint8_t* smem, const 
       const int st = (int)(s % kWStages);
       const uint32_t ph = (uint32_t)((s / kWStages) & 1);
       mbar_wait(full(st), ph, 22);
+      if (kFused && !(P.variant & 8)) {
+        // The half image is in shared memory now; its global copy is dead once every item that reads it has its own.
+        // The LAST reader drops the lines from L2 - they are dirty there and would be written back to HBM otherwise.
+        // (Done by these 128 threads, 2 lines each, not by the producer: a discard is ~100s of cycles.)
+        const int64_t tile = tile_begin + (s >> 1) * tile_step;
+        bool last = true;
+        if (I.n_consumers > 1) {
+          uint32_t old = 0;
+          if (lane == 0 && warp == 4)
+            old = atomicAdd(P.consumed + ((int64_t)I.flag_row * P.n_tiles + tile) * 2 + (s & 1), 1u);
+          if (warp == 4) s_last = (__shfl_sync(0xffffffffu, old, 0) + 1 == (uint32_t)I.n_consumers) ? 1u : 0u;
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          last = s_last != 0;
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+        }
+        if (last) {
+          const uint8_t* g = P.tape + I.g_off + tile * (int64_t)(I.g_fg * 2048) + (int64_t)(s & 1) * (I.g_fg * 1024);
+          for (uint32_t off = (uint32_t)j * 128u; off < g_bytes; off += 128u * 128u) discard_l2(g + off);
+        }
+      }
       if (mine && !(P.variant & 2)) {
         const uint32_t gs = sbase + WSmem::g + st * kWStageG + fg * 1024;
 #pragma unroll 4
@@ -673,8 +774,8 @@ __device__ __forceinline__ void dw_body(const DwParams& P, uint8_t* smem, const 
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
+  cta_sync();
+  if (kWarp0 == 0 && warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
 }
@@ -682,7 +783,7 @@ __device__ __forceinline__ void dw_body(const DwParams& P, uint8_t* smem, const 
 __global__ void __launch_bounds__(kWThreads, 1) mlp_tc_bwd_dw_kernel(const __grid_constant__ DwParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  dw_body<false>(P, smem, (int)blockIdx.x);
+  dw_body<false, 0, 0, WSmem, kWStages, kWStageA>(P, smem, (int)blockIdx.x, nullptr);
 }
 
 // The training path: chain CTAs [0, n_chain) and weight-gradient CTAs [n_chain, gridDim.x) in ONE launch
@@ -692,8 +793,29 @@ __global__ void __launch_bounds__(kBThreads, 1)
 mlp_tc_bwd_fused_kernel(const __grid_constant__ BwdParams B, const __grid_constant__ DwParams W, const int n_chain) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  if ((int)blockIdx.x < n_chain) chain_body<H, true>(B, smem, (int)blockIdx.x, n_chain);
-  else dw_body<true>(W, smem, (int)blockIdx.x - n_chain);
+  if ((int)blockIdx.x < n_chain) chain_body<H, true, 2, kBSlots>(B, smem, (int)blockIdx.x, n_chain);
+  else dw_body<true, 0, 0, WSmem, kWStages, kWStageA>(W, smem, (int)blockIdx.x - n_chain, nullptr);
+}
+
+// The SAME two roles on EVERY SM (one CTA per SM, 640 threads): warps 0-11 are a one-tile-at-a-time chain (TMEM
+// columns 0-255, a 5-slot weight ring), warps 12-19 a weight-gradient GEMM with one M block per item (TMEM columns
+// 256-511, two 48 KB stages).  Why: streaming the forward tape for the GEMM needs the bulk-copy engines of ALL SMs
+// (a GEMM CTA sustains ~60-80 GB/s, tools/sm_stream_bench.cu; the tape is 4.8 GB per fine pass), and the GEMM's MMAs
+// fill the tensor pipe while the chain's single tile is in its epilogue.  Gradient images still go from the chain of
+// one CTA to the GEMM of another (an item needs every tile) through L2 with the same flags.
+constexpr int kSharedChainWarps = 12;
+template <int H>
+__global__ void __launch_bounds__(kBThreads, 1)
+mlp_tc_bwd_shared_kernel(const __grid_constant__ BwdParams B, const __grid_constant__ DwParams W) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  using CS = BSmemT<kBSlotsShared, true>;
+  uint8_t* smem_dw = smem + (CS::total + 1023) / 1024 * 1024;
+  if ((int)(threadIdx.x >> 5) < kSharedChainWarps)
+    chain_body<H, true, 1, kBSlotsShared>(B, smem, (int)blockIdx.x, (int)gridDim.x);
+  else
+    dw_body<true, kSharedChainWarps, 256, WSmemShared, kWStagesShared, kWStageAShared>(W, smem_dw, (int)blockIdx.x,
+                                                                                       smem + CS::tmem_ptr);
 }
 
 }  // namespace tc
@@ -782,8 +904,9 @@ extern "C" DEXNERF_API int dexnerf_tc_backward(const dexnerf_flexible_spec* spec
   make_tape_layout(plan, n_pairs * 2, &T);
   cudaStream_t st = (cudaStream_t)stream;
 
-  const bool fused = (what & 4) != 0;
-  DN_REQUIRE(!fused || what == 4, "tc_backward: what = 4 (the fused launch) excludes the other bits");
+  const bool shared_sm = what == 8;         // chain + GEMM in every CTA (one CTA per SM)
+  const bool fused = (what & 4) != 0 || shared_sm;
+  DN_REQUIRE(!fused || what == 4 || what == 8, "tc_backward: what = 4 / 8 (the fused launches) exclude the other bits");
   BwdParams P{};
   if ((what & 1) || fused) {
     P.weights_t = reinterpret_cast<const uint8_t*>(packed_t);
@@ -817,10 +940,11 @@ extern "C" DEXNERF_API int dexnerf_tc_backward(const dexnerf_flexible_spec* spec
     W.tape = reinterpret_cast<const uint8_t*>(tape);
     W.grads = grads;
     W.n_tiles = n_pairs * 2;
-    W.variant = variant;
+    W.variant = variant & 0xFF;
     double cost[kMaxDwItems];
-    auto add = [&](int64_t a_off, int a_fg, int a_fg0, int a_fgs, int a_rows, int64_t g_off, int g_fg, int64_t w_out,
-                   int64_t b_out, int col0, int n_cols, int ld, int flag_row) {
+    auto add1 = [&](int64_t a_off, int a_fg, int a_fg0, int a_fgs, int a_rows, int64_t g_off, int g_fg, int64_t w_out,
+                    int64_t b_out, int col0, int n_cols, int ld, int flag_row) {
+      if (W.n_items >= kMaxDwItems) { ++W.n_items; return; }
       DwItem& I = W.items[W.n_items];
       I.flag_row = flag_row; I.n_consumers = 1;
       I.a_off = a_off; I.a_fg = a_fg; I.a_fg0 = a_fg0; I.a_fgs = a_fgs; I.n_mblk = (a_fgs + 15) / 16;
@@ -831,6 +955,18 @@ extern "C" DEXNERF_API int dexnerf_tc_backward(const dexnerf_flexible_spec* spec
       cost[W.n_items] = fused ? (double)(I.n_mblk * 8 * ((g_fg * 8 > 64 ? g_fg * 8 : 64) / 2)) + 200.0
                               : (double)(a_fgs + g_fg);
       ++W.n_items;
+    };
+    // the shared-SM kernel accumulates ONE M block (128 in-features, 256 TMEM columns) per item: wider operands
+    // become two items that read the same G image and halves of the A image
+    auto add = [&](int64_t a_off, int a_fg, int a_fg0, int a_fgs, int a_rows, int64_t g_off, int g_fg, int64_t w_out,
+                   int64_t b_out, int col0, int n_cols, int ld, int flag_row) {
+      if (!shared_sm || a_fgs <= 16) {
+        add1(a_off, a_fg, a_fg0, a_fgs, a_rows, g_off, g_fg, w_out, b_out, col0, n_cols, ld, flag_row);
+        return;
+      }
+      add1(a_off, a_fg, a_fg0, 16, a_rows < 128 ? a_rows : 128, g_off, g_fg, w_out, b_out, col0, n_cols, ld, flag_row);
+      add1(a_off, a_fg, a_fg0 + 16, a_fgs - 16, a_rows - 128, g_off, g_fg, w_out + (int64_t)128 * ld, -1, col0, n_cols, ld,
+           flag_row);
     };
     const int hfg = H / 8;
     for (int l = 0; l < nl; ++l) {
@@ -867,7 +1003,7 @@ extern "C" DEXNERF_API int dexnerf_tc_backward(const dexnerf_flexible_spec* spec
     // Fused launch: the SMs are first divided between the chain and the GEMM in proportion to their tensor-pipe
     // cycles per tile (variant >> 8 overrides the chain's share for experiments).
     int n_chain = 0;
-    if (fused) {
+    if (fused && !shared_sm) {
       double chain_cost = 0.0, dw_cost = 0.0;
       for (int j = 0; j < nl - 1; ++j) chain_cost += (double)(H / 128) * ((j == 0 ? H / 2 : H) / 64) * 4 * 64 + 150.0 * (H / 128);
       for (int i = 0; i < W.n_items; ++i) dw_cost += cost[i];
@@ -877,7 +1013,8 @@ extern "C" DEXNERF_API int dexnerf_tc_backward(const dexnerf_flexible_spec* spec
       if (n_chain > n_pairs) n_chain = (int)n_pairs;
       if (n_chain < 1) n_chain = 1;
     }
-    int64_t budget = kNumSMs - n_chain;
+    int64_t budget = kNumSMs - n_chain;      // (all SMs in the shared-SM kernel: n_chain stays 0 there)
+    if (!fused && (variant >> 8) > 0) budget = variant >> 8;      // experiment: the stand-alone GEMM on fewer SMs
     if (budget < W.n_items) budget = W.n_items;
     int share[kMaxDwItems];
     for (int i = 0; i < W.n_items; ++i) share[i] = 1;
@@ -895,12 +1032,34 @@ extern "C" DEXNERF_API int dexnerf_tc_backward(const dexnerf_flexible_spec* spec
       W.items[i].cta0 = cta; W.items[i].n_cta = (int)k;
       cta += (int)k;
     }
+    W.n_cta_total = cta;
     if (fused) {
       uint8_t* flags = reinterpret_cast<uint8_t*>(tape) + T.flags;
       W.ready = reinterpret_cast<const uint32_t*>(flags);
       W.consumed = reinterpret_cast<uint32_t*>(flags) + (int64_t)(kMaxLayers + 1) * W.n_tiles;
       W.variant = variant & 0xFF;
       DN_CUDA(cudaMemsetAsync(flags, 0, (size_t)T.flag_bytes, st));
+      if (shared_sm && !(variant & 32)) {        // (variant bit 5: no back-pressure, for experiments)
+        W.consumed_total = reinterpret_cast<uint32_t*>(flags + T.flag_bytes - 128);
+        P.consumed_total = W.consumed_total;
+        P.throttle_items = W.n_items;
+        P.throttle_window = (variant >> 8) > 0 ? (variant >> 8) : kNumSMs + 24;
+      }
+      if (shared_sm) {
+        using CS = BSmemT<kBSlotsShared, true>;
+        const size_t smem = (CS::total + 1023) / 1024 * 1024 + WSmemShared::total + 1024;
+        static_assert((BSmemT<kBSlotsShared, true>::total + 1023) / 1024 * 1024 + WSmemShared::total + 1024 <= 227 * 1024,
+                      "the two role groups must fit one SM");
+        auto launch = [&](auto kernel) -> int {
+          DN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          kernel<<<kNumSMs, kBThreads, smem, st>>>(P, W);
+          return 0;
+        };
+        const int rc = (H == 256) ? launch(mlp_tc_bwd_shared_kernel<256>) : launch(mlp_tc_bwd_shared_kernel<128>);
+        if (rc) return rc;
+        DN_CHECK_LAUNCH("mlp_tc_bwd_shared");
+        return 0;
+      }
       const size_t smem = (WSmem::total > BSmem::total ? WSmem::total : BSmem::total) + 1024;
       auto launch = [&](auto kernel) -> int {
         DN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -232,8 +232,24 @@ static void resolve_only(const dexnerf_render_params* p, Resolved* r) {
   r->rf_c = f(L.rf_c); r->w_c = f(L.w_c); r->z_f = f(L.z_f); r->rf_f = f(L.rf_f);
 }
 
-static bool split_backward() {
-  static const bool v = [] { const char* e = getenv("DEXNERF_BWD"); return e && e[0] == 's'; }();
+// Which MLP backward the training path launches (DESIGN.md section 3.2 has the measurements):
+//   default / DEXNERF_BWD=split   activation-gradient chain, then weight-gradient GEMM (two launches, the gradient
+//                                 images make one HBM round trip) - the fastest of the three on a B200 today;
+//   DEXNERF_BWD=fused             one launch, chain and GEMM on disjoint SMs, images handed over through L2;
+//   DEXNERF_BWD=shared            one launch, chain and GEMM in every CTA (one per SM).
+static int backward_mode() {
+  static const int v = [] {
+    const char* e = getenv("DEXNERF_BWD");
+    if (!e) return 3;
+    if (e[0] == 'f') return 4;
+    if (e[0] == 's' && e[1] == 'h') return 8;
+    return 3;
+  }();
+  return v;
+}
+// tuning knob of the fused launches: DEXNERF_BWD_VARIANT=<n> is passed through as `variant`
+static int variant_override() {
+  static const int v = [] { const char* e = getenv("DEXNERF_BWD_VARIANT"); return e ? atoi(e) : 0; }();
   return v;
 }
 
@@ -349,7 +365,7 @@ extern "C" DEXNERF_API int dexnerf_render_fused_bwd(const dexnerf_render_params*
       if (int rc = dexnerf_volume_render_backward(rf, z, r.rd, noise, n, S, p->white_background, g_rgb, nullptr,
                                                   nullptr, d_rf_scratch, stream)) return rc;
     }
-    if (split_backward()) {     // DEXNERF_BWD=split: the two stand-alone kernels (G through HBM), for comparison
+    if (backward_mode() == 3) {
       for (int bit = 1; bit <= 2; ++bit) {
         Bracket b(p->events, ev0 + bit, st);
         if (int rc = dexnerf_tc_backward(m.spec, m.prog, m.packed, m.packed_t, tape, d_rf_scratch, n, S, grads, bit, 0,
@@ -357,9 +373,9 @@ extern "C" DEXNERF_API int dexnerf_render_fused_bwd(const dexnerf_render_params*
       }
       return 0;
     }
-    // one launch: activation-gradient chain and weight-gradient GEMM on disjoint SMs, G handed over through L2
     Bracket b(p->events, ev0 + 1, st);
-    return dexnerf_tc_backward(m.spec, m.prog, m.packed, m.packed_t, tape, d_rf_scratch, n, S, grads, 4, 0, stream);
+    return dexnerf_tc_backward(m.spec, m.prog, m.packed, m.packed_t, tape, d_rf_scratch, n, S, grads, backward_mode(),
+                               variant_override(), stream);
   };
   if (which & 1)
     if (int rc = chain(p->fine, p->tape_fine, r.rf_f, r.z_f, r.noise_f, Sf, g_rgb_fine, grads_fine, 0)) return rc;

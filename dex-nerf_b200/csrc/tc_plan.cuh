@@ -139,7 +139,7 @@ inline void make_tape_layout(const Plan& plan, int64_t n_tiles, TapeLayout* out)
     T.grad[l] = take((int64_t)L.n_out * 256);
   }
   T.ghead = take(16 * 256);
-  T.flag_bytes = (int64_t)(kMaxLayers + 1) * n_tiles * 3 * 4;
+  T.flag_bytes = (int64_t)(kMaxLayers + 1) * n_tiles * 3 * 4 + 128;    // + the consumed-total counter (last 128 B)
   T.flags = off;
   off += (T.flag_bytes + 127) / 128 * 128;
   T.total = off;

@@ -15,8 +15,8 @@ _philox_offset = [0]   # advances once per fused call that draws random numbers 
 
 LAUNCH_NAMES = ("ray_setup", "ndc_rays", "mlp_coarse", "composite_coarse", "resample_merge", "mlp_fine",
                 "composite_fine")
-# dexnerf_render_fused_bwd's event slots: slot 1 / 4 is the ONE fused MLP backward launch (the activation-gradient
-# chain alone under DEXNERF_BWD=split, which also fills slots 2 / 5 with the weight-gradient GEMM)
+# dexnerf_render_fused_bwd's event slots: slots 1 / 4 are the activation-gradient chain and 2 / 5 the weight-gradient
+# GEMM (under DEXNERF_BWD=fused / shared slot 1 / 4 is the ONE MLP backward launch and 2 / 5 stay empty)
 BWD_LAUNCH_NAMES = ("composite_bwd_fine", "mlp_bwd_fine", "mlp_bwd_dw_fine", "composite_bwd_coarse",
                     "mlp_bwd_coarse", "mlp_bwd_dw_coarse")
 

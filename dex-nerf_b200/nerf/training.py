@@ -101,10 +101,10 @@ def mlp_backward(model, prog, spec, tape, d_rf, n, S, what=3, variant=0):
     blob = tensorcore.packed_weights(model, prog, spec)
     blob_t = packed_weights_t(model, prog, spec)
     flat = torch.zeros_like(model.packed_params())
-    if what == 4:          # the fused launch (chain + weight-gradient GEMM on disjoint SMs, G through L2)
+    if what in (4, 8):     # the fused launches (chain + weight-gradient GEMM concurrently, G through L2)
         with _timed("mlp_tc_bwd_fused", n, S):
             L.check(L.lib().dexnerf_tc_backward(spec, prog, L.ptr(blob), L.ptr(blob_t), L.ptr(tape), L.ptr(d_rf),
-                                                n, S, L.ptr(flat), 4, int(variant), L.stream_ptr()), "tc_backward")
+                                                n, S, L.ptr(flat), what, int(variant), L.stream_ptr()), "tc_backward")
         return flat
     for bit, name in ((1, "mlp_tc_bwd_dx"), (2, "mlp_tc_bwd_dw")):     # one kernel per call
         if what & bit:
@@ -168,7 +168,7 @@ class FieldRender(torch.autograd.Function):
         rf, z, rd, tape = ctx.saved_tensors
         n, S = z.shape
         d_rf = volume_render_backward(rf, z, rd, ctx.noise, ctx.white, g_rgb, g_depth, g_acc)
-        flat = mlp_backward(ctx.model, ctx.prog, ctx.spec, tape, d_rf, n, S, what=4)
+        flat = mlp_backward(ctx.model, ctx.prog, ctx.spec, tape, d_rf, n, S)
         grads = unflatten_grads(ctx.model, ctx.prog, flat)
         return (None,) * 11 + tuple(grads)
 
@@ -490,8 +490,8 @@ class Trainer:
     def _accumulate(self, ro, rd, tgt, rng, n_total, after_fine=None, height=None, width=None, focal_length=None):
         """Forward + backward of one ray chunk: ONE fused forward call (6 launches: setup incl. the Philox draws,
         two queries with tape, two compositings, resampling), one loss launch, the backward of the fine
-        and then the coarse network (2 launches each: compositing backward, fused MLP backward); loss terms and
-        gradients accumulate."""
+        and then the coarse network (3 launches each: compositing backward, activation-gradient chain,
+        weight-gradient GEMM); loss terms and gradients accumulate."""
         from . import render
         ro, rd, tgt = ro.contiguous(), rd.contiguous(), tgt.contiguous()
         n = ro.shape[0]
@@ -511,7 +511,7 @@ class Trainer:
         for which in (1, 2):
             L.check(lib.dexnerf_render_fused_bwd(C.byref(p), L.ptr(g[0]), L.ptr(g[1]), L.ptr(buf["d_rf"]), L.ptr(gc),
                                                  L.ptr(gf), which, stream), "render_fused_bwd")
-            L.launch_count += 1          # compositing backward + the fused MLP backward
+            L.launch_count += 2          # compositing backward, activation-gradient chain, weight-gradient GEMM
             if which == 1 and after_fine is not None:
                 after_fine()
         del keep

@@ -171,12 +171,15 @@ DEXNERF_API int dexnerf_tc_pack_bwd(const dexnerf_flexible_spec* spec, const dex
                         const float* params, void* packed_t, void* stream);
 /* d_rf (n,S,4) = dL/d(raw rgb, sigma) per sample -> grads: fp32 buffer in the program layout of
  * `params` (Wt[in][out] | bias per op), ACCUMULATED into (zero it first).  packed = forward blob,
- * packed_t = dexnerf_tc_pack_bwd blob.  what: 4 = the training path, ONE launch in which the activation-gradient
- * chain and the weight-gradient GEMM run on disjoint SMs and hand the gradient images over through L2 (never HBM);
- * or the stand-alone kernels: bit 0 activation-gradient chain, bit 1 weight-gradient GEMM (3 = both, one after the
- * other, gradient images through HBM).  variant: 0.  (Bring-up / experiment bits of the GEMM: 1 swaps the descriptor
- * strides, 2 skips the bias column sums, 4 skips the MMAs - results invalid; variant >> 8, fused launch only:
- * number of chain CTAs instead of the cost-model split.) */
+ * packed_t = dexnerf_tc_pack_bwd blob.  what: bit 0 activation-gradient chain, bit 1 weight-gradient GEMM (3 = a
+ * full backward: the two kernels one after the other, the gradient images make one HBM round trip - the training
+ * path).  Two single-launch forms in which the images go from the chain to the GEMM through L2 with release /
+ * acquire flags (same results; slower than 3 on a B200 today, kept selectable - DESIGN.md section 3.2): 4 = chain and
+ * GEMM on disjoint SMs, 8 = chain and GEMM as two warp groups of every CTA (one CTA per SM, with back-pressure).
+ * variant: 0.  (Bring-up / experiment bits: 1 swaps the GEMM's descriptor strides, 2 skips the bias column sums,
+ * 4 skips the MMAs - results invalid; single-launch forms: 8 no L2 discard, 16 no flag waits - results invalid,
+ * 32 no back-pressure, 128 print where the GEMM's producer waits; variant >> 8: chain CTAs (what = 4) / the
+ * back-pressure window in tiles (what = 8) / CTA budget (what = 2).) */
 DEXNERF_API int dexnerf_tc_backward(const dexnerf_flexible_spec* spec, const dexnerf_mlp_program* prog,
                         const void* packed, const void* packed_t, void* tape, const float* d_rf,
                         int64_t n, int S, float* grads, int what, int variant, void* stream);
@@ -256,7 +259,8 @@ DEXNERF_API int dexnerf_render_fused_fwd(const dexnerf_render_params* p /*host*/
  * ACCUMULATED into.  d_rf_scratch: (n, Nc+Nf, 4) floats.  which: bit 0 = the fine network's chain, bit 1 = the
  * coarse network's (3 = both, fine first: its gradient buffer is complete first, so a data-parallel caller can
  * issue the two halves separately and start reducing the fine gradients while the coarse chain runs).
- * 2 launches per network: compositing backward and the fused MLP backward (dexnerf_tc_backward what = 4). */
+ * 3 launches per network: compositing backward, activation-gradient chain, weight-gradient GEMM
+ * (DEXNERF_BWD=fused / shared select the single-launch MLP backwards of dexnerf_tc_backward instead). */
 DEXNERF_API int dexnerf_render_fused_bwd(const dexnerf_render_params* p /*host*/, const float* g_rgb_coarse,
                                          const float* g_rgb_fine, float* d_rf_scratch, float* grads_coarse,
                                          float* grads_fine, int which, void* stream);

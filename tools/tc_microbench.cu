@@ -107,6 +107,15 @@ __global__ void __launch_bounds__(512, 1) bench(int variant, int N, int reps, in
               const uint32_t acc = (r | ks) ? 1u : 0u;
               if (variant == 0) mma_ss(tm + 256, hi | (uint64_t)(a_lo + ks * 256), hi | (uint64_t)(b_lo + ks * 2 * N), id, acc);
               else if (variant == 1) mma_ts(tm + 256, tm + ks * 8, hi | (uint64_t)(b_lo + ks * 2 * N), id, acc);
+              else if (variant == 4) {
+                // both operands MN-major, no swizzle, as the weight-gradient GEMM reads the tape images:
+                // LBO = 128 B (K-adjacent core matrices), SBO = 1024 B (MN-adjacent), a K step = 256 B
+                const uint64_t hi_mn = ((uint64_t)(1024 >> 4) << 32) | (1ull << 46);
+                const uint32_t id_mn = id | (1u << 15) | (1u << 16);
+                const uint32_t a_mn = ((a_smem >> 4) & 0x3FFF) | ((128u >> 4) << 16);
+                const uint32_t b_mn = ((b_smem >> 4) & 0x3FFF) | ((128u >> 4) << 16);
+                mma_ss(tm + 256, hi_mn | (uint64_t)(a_mn + (ks % 4) * 16), hi_mn | (uint64_t)(b_mn + (ks % 4) * 16), id_mn, acc);
+              }
               else if (variant == 2) mma_ss(tm + 256, desc_swz128(a_smem + (ks / 4) * 16384 + (ks % 4) * 32), desc_swz128(b_smem + (ks / 4) * N * 128 + (ks % 4) * 32), id, acc);
               else mma_ts(tm + 256, tm + ks * 8, desc_swz128(b_smem + (ks / 4) * N * 128 + (ks % 4) * 32), id, acc);
             }
@@ -133,10 +142,11 @@ int main() {
   cudaMalloc(&ld_out, 64 * sizeof(long long));
   cudaMalloc(&sink, 512 * 4);
   cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  const char* names[4] = {"SS  B no-swizzle", "TS  B no-swizzle", "SS  B 128B-swizzle", "TS  B 128B-swizzle"};
+  const char* names[5] = {"SS  B no-swizzle", "TS  B no-swizzle", "SS  B 128B-swizzle", "TS  B 128B-swizzle",
+                          "SS  A,B MN-major (dW)"};
   for (int n_ld : {0, 4, 8}) {
     for (int N : {128, 256}) {
-      for (int v = 0; v < 2; ++v) {
+      for (int v : {0, 1, 4}) {
         const int reps = 32, ksteps = 16;
         cudaMemset(ld_out, 0, 64 * sizeof(long long));
         bench<<<1, 512, 200 * 1024>>>(v, N, reps, ksteps, out, n_ld, ld_out, sink);
