@@ -38,11 +38,38 @@ static __device__ __noinline__ void barrier_timeout(int who) {
   printf("dexnerf tcgen05 kernel: barrier timeout (wait site %d, block %d, thread %d)\n", who, blockIdx.x, threadIdx.x);
   __trap();
 }
+// DEXNERF_TIGHT_POLL = 1: the poll loop as hand-written PTX (four polls per bound check, 2.75 instructions per failed
+// poll instead of the 9 of the compiled loop).  Measured on a B200 and NOT used: the faster loop polls more often, and
+// every kernel got slower (8x256 render 108 -> 118.6 ms, C4 training 5.13 -> 5.38 ms) - waiting warps take issue slots
+// and shared-memory bandwidth in proportion to their poll RATE, so the slow compiled loop is the better citizen.
+#ifndef DEXNERF_TIGHT_POLL
+#define DEXNERF_TIGHT_POLL 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int who) {
+#if DEXNERF_TIGHT_POLL
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
+      "mov.u32 n, 0;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t@p bra LAB_DONE;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t@p bra LAB_DONE;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t@p bra LAB_DONE;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t@p bra LAB_DONE;\n\t"
+      "add.u32 n, n, 4;\n\t"
+      "setp.lt.u32 p, n, %3;\n\t"
+      "@p bra LAB_WAIT;\n\t"
+      "mov.u32 %0, 0;\n\tbra LAB_END;\n\t"
+      "LAB_DONE:\n\tmov.u32 %0, 1;\n\t"
+      "LAB_END:\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity), "r"(kSpinLimit) : "memory");
+  if (!ok) barrier_timeout(who);
+#else
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > kSpinLimit) barrier_timeout(who);
   }
+#endif
 }
 // Four barrier polls issued back to back (their ~100-cycle latencies overlap); falls back to the
 // bounded sequential wait when any of them is not complete yet.
@@ -59,6 +86,18 @@ __device__ __forceinline__ void mbar_wait4(uint32_t b0, uint32_t p0, uint32_t b1
       "selp.u32 %0, 1, 0, q0;\n\t}"
       : "=r"(ok) : "r"(b0), "r"(p0), "r"(b1), "r"(p1), "r"(b2), "r"(p2), "r"(b3), "r"(p3) : "memory");
   if (!ok) { mbar_wait(b0, p0, who); mbar_wait(b1, p1, who); mbar_wait(b2, p2, who); mbar_wait(b3, p3, who); }
+}
+// Two barrier polls issued back to back (their latencies overlap); bounded sequential waits when either is pending.
+__device__ __forceinline__ void mbar_wait2(uint32_t b0, uint32_t p0, uint32_t b1, uint32_t p1, int who) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred q0, q1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 q0, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 q1, [%3], %4;\n\t"
+      "and.pred q0, q0, q1;\n\t"
+      "selp.u32 %0, 1, 0, q0;\n\t}"
+      : "=r"(ok) : "r"(b0), "r"(p0), "r"(b1), "r"(p1) : "memory");
+  if (!ok) { mbar_wait(b0, p0, who); mbar_wait(b1, p1, who); }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

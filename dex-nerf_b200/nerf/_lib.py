@@ -7,7 +7,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libdexnerf.so")
+# DEXNERF_LIB: an experiment build of the SAME library (dex-nerf_b200/build.py --define ... --out ...), tools/ only
+LIB_PATH = os.environ.get("DEXNERF_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libdexnerf.so")
 
 MAX_OPS = 16
 ENC_XYZ, ENC_DIR, BUF_A, BUF_B, OUT_RGB, OUT_SIGMA, OUT_ALL, NONE = 0, 1, 2, 3, 4, 5, 6, -1
