@@ -682,7 +682,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
 }
 
 // ------------------------------------------------------------------ host: packing
-static int64_t blob_bytes(const Plan& P) { return (int64_t)kMaxConstFloats * 4 + P.weight_bytes; }
+static int64_t blob_bytes(const Plan& P) { return (int64_t)kMaxConstFloats * 4 + P.weight_bytes + (int64_t)P.n_layers * kBiasImgBytes; }
 
 struct PackChunk { int64_t dst; int w_off; int n_out; int n0; int np; int k0; int kc; int k_valid; };
 
@@ -705,6 +705,24 @@ __global__ void pack_weights_kernel(const float* __restrict__ params, const __gr
       const int64_t off = c.dst + (int64_t)(k >> 3) * (c.np * 16) + n * 16 + (k & 7) * 2;
       *reinterpret_cast<__nv_bfloat16*>(blob + off) = __float2bfloat16_rn(w);
     }
+  }
+}
+
+// Bias images of the three-tile hidden-128 kernel (mlp_tc3.cu): the bias enters the accumulator as the first MMA of a
+// pass, ones[128 x 16] x B_l[n_out x 16], with B_l[n][0] = bf16(b[n]) and B_l[n][1] = bf16(b[n] - B_l[n][0]) (the two
+// products are exact in the fp32 accumulator; what is lost of the bias is below 2^-17 of its value), zeros elsewhere.
+__global__ void pack_bias_kernel(const float* __restrict__ params, const __grid_constant__ PackTables Q,
+                                 uint8_t* __restrict__ img) {
+  const int4 mv = Q.moves[blockIdx.x];                 // (const offset, b_off, n_out, 0): one per tensor-core layer
+  for (int n = threadIdx.x; n < kTileM; n += blockDim.x) {
+    uint4 row = make_uint4(0u, 0u, 0u, 0u);
+    if (n < mv.z) {
+      const float b = params[mv.y + n];
+      const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(b - __bfloat162float(hi));
+      row.x = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+    }
+    reinterpret_cast<uint4*>(img + (size_t)blockIdx.x * kBiasImgBytes)[n] = row;
   }
 }
 
@@ -796,6 +814,10 @@ extern "C" DEXNERF_API int dexnerf_tc_pack(const dexnerf_flexible_spec* spec, co
   DN_CHECK_LAUNCH("pack_weights");
   pack_consts_kernel<<<nmv, 128, 0, st>>>(params, tables, reinterpret_cast<float*>(packed));
   DN_CHECK_LAUNCH("pack_consts");
+  // the first n_layers moves are the layers' biases, in layer order
+  pack_bias_kernel<<<plan.n_layers, 128, 0, st>>>(params, tables, reinterpret_cast<uint8_t*>(packed) +
+                                                  (size_t)kMaxConstFloats * 4 + plan.weight_bytes);
+  DN_CHECK_LAUNCH("pack_bias");
   return 0;
 }
 
@@ -814,6 +836,7 @@ static int tc_query_impl(const dexnerf_flexible_spec* spec, const void* packed, 
   TcParams P{};
   P.consts = reinterpret_cast<const float*>(packed);
   P.weights = reinterpret_cast<const uint8_t*>(packed) + (size_t)kMaxConstFloats * 4;
+  P.bias_img = P.weights + plan.weight_bytes;
   P.ro = ro; P.rd = rd; P.vd = viewdirs; P.z = z; P.rf = rf; P.dbg = dbg;
   P.m_total = n * (int64_t)S; P.S = S;
   P.n_layers = plan.n_layers; P.hidden = spec->hidden; P.n_const = plan.n_const;

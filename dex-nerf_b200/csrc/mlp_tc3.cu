@@ -36,17 +36,21 @@ namespace tc {
 namespace three {
 
 constexpr int kNT = 3;                 // tiles in flight
-constexpr int kSlots = 8;              // weight ring (a power of two: slot = counter & 7)
+constexpr int kSlots = 6;              // weight ring
 constexpr int kTeamThreads = 256;      // 8 warps per epilogue team
 
+constexpr int kHeadFloats = 1024;      // fc_alpha / fc_rgb / fc_out weights and biases (<= 4 x 128 + 4 floats)
 struct Smem {
   static constexpr int w_slots = 0;
   static constexpr int pe_xyz = w_slots + kSlots * kSlotBytes;           // [tile]
   static constexpr int pe_dir = pe_xyz + kNT * kPeXyzBytes;              // [tile]
-  static constexpr int consts = pe_dir + kNT * kPeDirBytes;
-  static constexpr int sig = consts + kMaxConstFloats * 4;               // [tile][half][row] partial sigma
+  static constexpr int heads = pe_dir + kNT * kPeDirBytes;               // the const block from off_walpha on
+  static constexpr int sig = heads + kHeadFloats * 4;                    // [tile][half][row] partial sigma
   static constexpr int xchg = sig + kNT * 2 * kTileM * 4;                // [tile][row] float4 head partials of half 1
-  static constexpr int bars = xchg + kNT * kTileM * 16;
+  static constexpr int bias = xchg + kNT * kTileM * 16;                  // [layer] bias images (B operands, K group 0)
+  static constexpr int ones = bias + kMaxLayers * kBiasImgBytes;         // A operand of the bias MMA (K group 0)
+  static constexpr int zero = ones + kBiasImgBytes;                      // K group 1 of both: zeros
+  static constexpr int bars = zero + kBiasImgBytes;
   static constexpr int n_bars = 2 * kSlots + 6 * kNT + 2 + 2 * kNT;
   static constexpr int tmem_ptr = bars + n_bars * 8;
   static constexpr int total = tmem_ptr + 16;
@@ -64,6 +68,10 @@ __device__ __forceinline__ int B_turn(int t) { return 2 * kSlots + 5 * kNT + 2 +
 __device__ __forceinline__ int B_dfree(int b, int t) { return 2 * kSlots + 6 * kNT + 2 + b * kNT + t; }   // drained by tile t's epilogue
 
 constexpr int kH = 128;
+#ifndef DEXNERF_TC3_EPI
+#define DEXNERF_TC3_EPI 2
+#endif
+constexpr int kEpi = DEXNERF_TC3_EPI;   // epilogue_pass_wide variant (2: three 16-column buffers; 1 needs 88 registers, see below)
 // Bring-up aids (compile with -DDEXNERF_TC3_BRINGUP): a role mask (DEXNERF_TC3_STAGE), a pass limit
 // (DEXNERF_TC3_PASSES) and a clock-stamped trace of CTA 0 (DEXNERF_TC3_TRACE = address of a device or pinned-host buffer -
 // the latter survives a faulting kernel; DEXNERF_TC3_WINDOW = "lo,hi" passes): trace[role][0] = count, then pairs of
@@ -114,18 +122,36 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc3_kernel(const __grid_const
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   {
-    float* c = reinterpret_cast<float*>(smem + Smem::consts);
-    for (int i = threadIdx.x; i < P.n_const; i += kThreads) c[i] = P.consts[i];
+    // head weights (the tail of the const block); the layers' biases are MMA operands here:
+    //   D = ones[128 x 16] * B_l[n_out x 16]^T as the first MMA of every pass, ones[:, 0:2] = 1, B_l[n][0:2] = (hi, lo) of
+    //   the bias.  Both operands are ONE K group of 8 (2 KB: 16-byte rows) whose second K group is a shared block of zeros -
+    //   the descriptor's leading-dimension offset points there.
+    float* c = reinterpret_cast<float*>(smem + Smem::heads);
+    for (int i = threadIdx.x; i < P.n_const - P.off_walpha; i += kThreads) c[i] = P.consts[P.off_walpha + i];
+    uint4* b = reinterpret_cast<uint4*>(smem + Smem::bias);
+    const uint4* src = reinterpret_cast<const uint4*>(P.bias_img);
+    for (int i = threadIdx.x; i < nl * (kBiasImgBytes / 16); i += kThreads) b[i] = src[i];
+    uint4* o = reinterpret_cast<uint4*>(smem + Smem::ones);
+    for (int i = threadIdx.x; i < 2 * (kBiasImgBytes / 16); i += kThreads)      // ones, then zero
+      o[i] = i < kBiasImgBytes / 16 ? make_uint4(0x3F803F80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + Smem::tmem_ptr);
-  const float* s_const = reinterpret_cast<const float*>(smem + Smem::consts);
+  const float* s_head = reinterpret_cast<const float*>(smem + Smem::heads);   // index: const offset - off_walpha
 
   const int stage = kBringUp ? P.dbg_layer : 7;   // bring-up: which roles run (DEXNERF_TC3_STAGE)
+  // Register re-balancing (DEXNERF_TC3_EPI = 1, an experiment that did not pay): the drain of a SHARED accumulator is on
+  // the critical loop (issue -> complete -> drain -> next pass on the same accumulator), and with its whole 64-column
+  // share in registers (one tcgen05.ld round trip) the epilogue could release it ~300 instead of ~850 cycles after the
+  // pass completes.  That needs ~88 registers; setmaxnreg (control warpgroup - 32, epilogue warpgroups + 8) is accepted,
+  // but this ptxas keeps allocating at most the launch bound's 80 and spills instead: 37.5 -> 40.9 ms at 8 x 128.
+  constexpr bool kRebalance = DEXNERF_TC3_EPI == 1;
   if (warp == 0) {
     // =============================== weight producer ===============================
+    if (kRebalance) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     const bool leader = elect_one();
     uint32_t cnt = 0, tn = 0, pk0 = 0;        // pk0: first pass of the group (bring-up trace only)
 #pragma unroll 1
@@ -140,7 +166,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc3_kernel(const __grid_const
         for (int c = 0; c < nc; ++c, ++cnt) {
           const int kc = (c < L.k_main / 64) ? 64 : L.k_smem;
           const uint32_t bytes = (uint32_t)(np * kc * 2);
-          const uint32_t slot = cnt & (kSlots - 1), ph = (cnt / kSlots) & 1;
+          const uint32_t slot = cnt % kSlots, ph = (cnt / kSlots) & 1;
           trace(P, 0, (uint32_t)(c * 2), pk0 + (uint32_t)(l * kNT), tn);
           mbar_wait(bar(B_wempty(slot)), ph ^ 1, 30);
           trace(P, 0, (uint32_t)(c * 2 + 1), pk0 + (uint32_t)(l * kNT), tn);
@@ -172,15 +198,19 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc3_kernel(const __grid_const
 #else
     const int t = warp - 1;                   // my tile
 #endif
+    if (kRebalance) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     const bool leader = elect_one();
     uint32_t tn = 0;
-    uint32_t cnt = 0;                         // chunk counter = ring cursor of the current layer
+    uint32_t slot = 0, wph = 0;               // ring cursor of the current layer: slot and phase of its first chunk
     const uint64_t desc_hi = ((uint64_t)(128 >> 4) << 32) | (1ull << 46);   // SBO = 128 B, version 1
     const uint32_t slot0_lo = ((sbase + Smem::w_slots) >> 4) & 0x3FFF;
     const uint32_t wfull0 = bar(B_wfull(0)), wempty0 = bar(B_wempty(0));
     const uint32_t a_tmem = tmem_base + kTmemA + (uint32_t)(t * (kH / 2));
     const uint32_t my_turn = bar(B_turn(t)), next_turn = bar(B_turn(t + 1 == kNT ? 0 : t + 1));
     const uint32_t aready_bar = bar(B_aready(t));
+    // bias MMA operands: K group 0 = the 2 KB image, K group 1 = the zero block (leading-dimension offset = distance)
+    const uint64_t ones_desc = desc_hi | (uint64_t)((((sbase + Smem::ones) >> 4) & 0x3FFF) |
+                                                    ((uint32_t)((Smem::zero - Smem::ones) >> 4) << 16));
     const int tp = t + 1 == kNT ? 0 : t + 1;  // the tile of pass kk - 2
     uint32_t kk = (uint32_t)t, j = 0, it = 0;  // pass counter, the tile's pass index (kk = 3 j + t), group index
     TcLayer L = P.layers[0];
@@ -193,10 +223,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc3_kernel(const __grid_const
         const uint32_t b = kk & 1;
         const uint32_t d_tmem = tmem_base + kTmemD + b * 128;
         const int n_chunks = chunks_in_pass(L);
+        const uint64_t bias_desc = desc_hi | (uint64_t)((((sbase + Smem::bias + (uint32_t)l * kBiasImgBytes) >> 4) & 0x3FFF) |
+                                                        ((uint32_t)((Smem::zero - Smem::bias - l * kBiasImgBytes) >> 4) << 16));
         trace(P, 1 + t, 0, kk, tn);
         // what the pass needs besides its gate (nearly always there already)
-        for (int c = 0; c < n_chunks; ++c)
-          mbar_wait(wfull0 + 8 * ((cnt + c) & (kSlots - 1)), ((cnt + c) / kSlots) & 1, 32);
+        {
+          uint32_t sl = slot, ph = wph;
+          for (int c = 0; c < n_chunks; ++c) {
+            mbar_wait(wfull0 + 8 * sl, ph, 32);
+            if (++sl == kSlots) { sl = 0; ph ^= 1; }
+          }
+        }
         if (L.smem_src == 2) mbar_wait(bar(B_dirfull(t)), it & 1, 33);
         if (l == 0) mbar_wait(bar(B_xyzfull(t)), it & 1, 34);
         trace(P, 1 + t, 4, kk, tn);
@@ -215,14 +252,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc3_kernel(const __grid_const
         trace(P, 1 + t, 3, kk, tn);
         if (L.k_main == kH && L.smem_src == 0 && L.n_out == kH) {
           // ---- plain hidden layer: two 64-wide K chunks from the TMEM-resident activations
-          const uint32_t s0 = cnt & (kSlots - 1), s1 = (cnt + 1) & (kSlots - 1);
+          const uint32_t s0 = slot, s1 = slot + 1 == kSlots ? 0 : slot + 1;
           const uint32_t b0 = (slot0_lo + s0 * (kSlotBytes >> 4)) | (128u << 16);
           const uint32_t b1 = (slot0_lo + s1 * (kSlotBytes >> 4)) | (128u << 16);
           const uint32_t idesc = instr_desc(128);
           if (leader) {
+            mma_ss(d_tmem, ones_desc, bias_desc, idesc, 0u);            // D = bias
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-              mma_ts(d_tmem, a_tmem + (uint32_t)(ks * 8), desc_hi | (uint64_t)(b0 + (uint32_t)ks * 256), idesc, ks ? 1u : 0u);
+              mma_ts(d_tmem, a_tmem + (uint32_t)(ks * 8), desc_hi | (uint64_t)(b0 + (uint32_t)ks * 256), idesc, 1u);
             tc_commit(wempty0 + 8 * s0);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
@@ -239,19 +277,19 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc3_kernel(const __grid_const
           const int n_main = L.k_main / 64;
           const uint32_t b_lbo16 = (uint32_t)np;
           if (leader) {
-            uint32_t c = cnt;
-            for (int m = 0; m < n_main; ++m, ++c) {
-              const uint32_t slot = c & (kSlots - 1);
-              const uint32_t b_lo = (slot0_lo + slot * (kSlotBytes >> 4)) | (b_lbo16 << 16);
+            uint32_t sl = slot;
+            mma_ss(d_tmem, ones_desc, bias_desc, idesc, 0u);            // D = bias
+            for (int m = 0; m < n_main; ++m) {
+              const uint32_t b_lo = (slot0_lo + sl * (kSlotBytes >> 4)) | (b_lbo16 << 16);
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
                 mma_ts(d_tmem, a_tmem + (uint32_t)(m * 32 + ks * 8),
-                       desc_hi | (uint64_t)(b_lo + (uint32_t)ks * 2 * b_lbo16), idesc, (m | ks) ? 1u : 0u);
-              tc_commit(wempty0 + 8 * slot);
+                       desc_hi | (uint64_t)(b_lo + (uint32_t)ks * 2 * b_lbo16), idesc, 1u);
+              tc_commit(wempty0 + 8 * sl);
+              if (++sl == kSlots) sl = 0;
             }
             if (L.smem_src) {
-              const uint32_t slot = c & (kSlots - 1);
-              const uint32_t b_lo = (slot0_lo + slot * (kSlotBytes >> 4)) | (b_lbo16 << 16);
+              const uint32_t b_lo = (slot0_lo + sl * (kSlotBytes >> 4)) | (b_lbo16 << 16);
               const uint32_t a_addr = (L.smem_src == 1)
                   ? sbase + Smem::pe_xyz + (uint32_t)t * kPeXyzBytes
                   : sbase + Smem::pe_dir + (uint32_t)t * kPeDirBytes;
@@ -260,9 +298,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc3_kernel(const __grid_const
               for (int ks = 0; ks < 4; ++ks) {
                 if (ks * 16 < L.k_smem)
                   mma_ss(d_tmem, desc_hi | (uint64_t)(a_lo + (uint32_t)ks * 2 * kTileM),
-                         desc_hi | (uint64_t)(b_lo + (uint32_t)ks * 2 * b_lbo16), idesc, (n_main || ks) ? 1u : 0u);
+                         desc_hi | (uint64_t)(b_lo + (uint32_t)ks * 2 * b_lbo16), idesc, 1u);
               }
-              tc_commit(wempty0 + 8 * slot);
+              tc_commit(wempty0 + 8 * sl);
             }
             mbar_arrive(next_turn);
             tc_commit(bar(B_dfull(b)));
@@ -272,12 +310,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc3_kernel(const __grid_const
           __syncwarp();
         }
         trace(P, 1 + t, 1, kk, tn);
-        cnt += (uint32_t)n_chunks;
+        slot += (uint32_t)n_chunks;
+        if (slot >= kSlots) { slot -= kSlots; wph ^= 1; }
         L = Lnext;
       }
     }
   } else if (warp >= 4 && warp < 20) {
     // =============================== epilogue teams ===============================
+    if (kRebalance) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
     const int e = warp - 4;
     const int team = e >> 3, hs = (e >> 2) & 1, q = warp & 3;
     const int row = q * 32 + lane;
@@ -311,8 +351,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc3_kernel(const __grid_const
         // ---- last layer: ReLU, fc_rgb on the CUDA cores over this warp's 32 of the 64 outputs, final store
         float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
         const uint32_t col0 = (uint32_t)(hs * (hw / 2));
-        const uint32_t bias = sbase + Smem::consts + ((uint32_t)L.bias_off + col0) * 4;
-        const uint32_t wr = sbase + Smem::consts + ((uint32_t)P.off_wrgb + col0) * 4;
+        const uint32_t wr = sbase + Smem::heads + ((uint32_t)(P.off_wrgb - P.off_walpha) + col0) * 4;
         uint32_t v[2][16];
         tmem_ld16_issue(d_base + col0, v[0]);
         tmem_ld16_issue(d_base + col0 + 16, v[1]);
@@ -324,14 +363,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc3_kernel(const __grid_const
         for (int c = 0; c < 2; ++c) {
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
-            const float4 b4 = lds128(bias + (uint32_t)((c * 16 + i) * 4));
             const float4 r4 = lds128(wr + (uint32_t)((c * 16 + i) * 4));
             const float4 g4 = lds128(wr + (uint32_t)((hw + c * 16 + i) * 4));
             const float4 u4 = lds128(wr + (uint32_t)((2 * hw + c * 16 + i) * 4));
-            const float x0 = fmaxf(__uint_as_float(v[c][i]) + b4.x, 0.0f);
-            const float x1 = fmaxf(__uint_as_float(v[c][i + 1]) + b4.y, 0.0f);
-            const float x2 = fmaxf(__uint_as_float(v[c][i + 2]) + b4.z, 0.0f);
-            const float x3 = fmaxf(__uint_as_float(v[c][i + 3]) + b4.w, 0.0f);
+            const float x0 = fmaxf(__uint_as_float(v[c][i]), 0.0f);          // the bias is in the accumulator
+            const float x1 = fmaxf(__uint_as_float(v[c][i + 1]), 0.0f);
+            const float x2 = fmaxf(__uint_as_float(v[c][i + 2]), 0.0f);
+            const float x3 = fmaxf(__uint_as_float(v[c][i + 3]), 0.0f);
             rgb0 = fmaf(x0, r4.x, fmaf(x1, r4.y, fmaf(x2, r4.z, fmaf(x3, r4.w, rgb0))));
             rgb1 = fmaf(x0, g4.x, fmaf(x1, g4.y, fmaf(x2, g4.z, fmaf(x3, g4.w, rgb1))));
             rgb2 = fmaf(x0, u4.x, fmaf(x1, u4.y, fmaf(x2, u4.z, fmaf(x3, u4.w, rgb2))));
@@ -341,11 +379,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc3_kernel(const __grid_const
         asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
         if (hs == 0 && g < P.m_total) {
           const float4 o2 = s_xchg[t * kTileM + row];
-          const float* br = s_const + P.off_brgb;
+          const float* br = s_head + (P.off_brgb - P.off_walpha);
           const float sg = s_sig[(t * 2) * kTileM + row] + s_sig[(t * 2 + 1) * kTileM + row];
           float4 o;
           o.x = rgb0 + o2.x + br[0]; o.y = rgb1 + o2.y + br[1]; o.z = rgb2 + o2.z + br[2];
-          o.w = sg + s_const[P.off_balpha];
+          o.w = sg + s_head[P.off_balpha - P.off_walpha];
           reinterpret_cast<float4*>(P.rf)[g] = o;
         }
         mbar_arrive(bar(B_aready(t)));            // the row is finished: the tile may start its next group
@@ -353,8 +391,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc3_kernel(const __grid_const
         // ---- last trunk layer of a model without view directions: ReLU, fc_out (4 outputs) on the CUDA cores
         float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
         const uint32_t col0 = (uint32_t)(hs * 64);
-        const uint32_t bias = sbase + Smem::consts + ((uint32_t)L.bias_off + col0) * 4;
-        const uint32_t wo = sbase + Smem::consts + ((uint32_t)P.off_wrgb + col0) * 4;
+        const uint32_t wo = sbase + Smem::heads + ((uint32_t)(P.off_wrgb - P.off_walpha) + col0) * 4;
         uint32_t v[2][16];
         tmem_ld16_issue(d_base + col0, v[0]);
 #pragma unroll
@@ -367,15 +404,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc3_kernel(const __grid_const
           }
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
-            const float4 b4 = lds128(bias + (uint32_t)((c * 16 + i) * 4));
             const float4 w0 = lds128(wo + (uint32_t)((c * 16 + i) * 4));
             const float4 w1 = lds128(wo + (uint32_t)((kH + c * 16 + i) * 4));
             const float4 w2 = lds128(wo + (uint32_t)((2 * kH + c * 16 + i) * 4));
             const float4 w3 = lds128(wo + (uint32_t)((3 * kH + c * 16 + i) * 4));
-            const float x0 = fmaxf(__uint_as_float(v[c & 1][i]) + b4.x, 0.0f);
-            const float x1 = fmaxf(__uint_as_float(v[c & 1][i + 1]) + b4.y, 0.0f);
-            const float x2 = fmaxf(__uint_as_float(v[c & 1][i + 2]) + b4.z, 0.0f);
-            const float x3 = fmaxf(__uint_as_float(v[c & 1][i + 3]) + b4.w, 0.0f);
+            const float x0 = fmaxf(__uint_as_float(v[c & 1][i]), 0.0f);
+            const float x1 = fmaxf(__uint_as_float(v[c & 1][i + 1]), 0.0f);
+            const float x2 = fmaxf(__uint_as_float(v[c & 1][i + 2]), 0.0f);
+            const float x3 = fmaxf(__uint_as_float(v[c & 1][i + 3]), 0.0f);
             o0 = fmaf(x0, w0.x, fmaf(x1, w0.y, fmaf(x2, w0.z, fmaf(x3, w0.w, o0))));
             o1 = fmaf(x0, w1.x, fmaf(x1, w1.y, fmaf(x2, w1.z, fmaf(x3, w1.w, o1))));
             o2 = fmaf(x0, w2.x, fmaf(x1, w2.y, fmaf(x2, w2.z, fmaf(x3, w2.w, o2))));
@@ -386,22 +422,22 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc3_kernel(const __grid_const
         asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
         if (hs == 0 && g < P.m_total) {
           const float4 p2 = s_xchg[t * kTileM + row];
-          const float* bo = s_const + P.off_brgb;
+          const float* bo = s_head + (P.off_brgb - P.off_walpha);
           float4 o;
           o.x = o0 + p2.x + bo[0]; o.y = o1 + p2.y + bo[1]; o.z = o2 + p2.z + bo[2]; o.w = o3 + p2.w + bo[3];
           reinterpret_cast<float4*>(P.rf)[g] = o;
         }
         mbar_arrive(bar(B_aready(t)));
       } else {
-        const uint32_t bias = sbase + Smem::consts + ((uint32_t)L.bias_off + hs * 64) * 4;
-        const uint32_t wa = sbase + Smem::consts + ((uint32_t)P.off_walpha + hs * 64) * 4;
+        const uint32_t bias = 0;                // unused: the bias is in the accumulator
+        const uint32_t wa = sbase + Smem::heads + (uint32_t)(hs * 64) * 4;
         const uint32_t d_tmem = d_base + (uint32_t)(hs * 64);
         const uint32_t a_store = a_tmem + (uint32_t)(hs * 32);
         float sigma = 0.0f;
-        if (!L.relu) epilogue_pass_wide<false, false, false, false>(d_tmem, a_store, bias, wa, sigma, dfree, nullptr, nullptr, nullptr);
-        else if (L.head != 1) epilogue_pass_wide<true, false, false, false>(d_tmem, a_store, bias, wa, sigma, dfree, nullptr, nullptr, nullptr);
+        if (!L.relu) epilogue_pass_wide<false, false, false, false, false, kEpi>(d_tmem, a_store, bias, wa, sigma, dfree, nullptr, nullptr, nullptr);
+        else if (L.head != 1) epilogue_pass_wide<true, false, false, false, false, kEpi>(d_tmem, a_store, bias, wa, sigma, dfree, nullptr, nullptr, nullptr);
         else {
-          epilogue_pass_wide<true, true, false, false>(d_tmem, a_store, bias, wa, sigma, dfree, nullptr, nullptr, nullptr);
+          epilogue_pass_wide<true, true, false, false, false, kEpi>(d_tmem, a_store, bias, wa, sigma, dfree, nullptr, nullptr, nullptr);
           s_sig[(t * 2 + hs) * kTileM + row] = sigma;     // read by the final layer's epilogue (either team)
         }
         trace(P, 4 + (warp - 4), 2, ekk, tn);

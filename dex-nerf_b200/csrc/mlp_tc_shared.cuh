@@ -14,10 +14,12 @@ constexpr int kThreads = 768;   // 4 control warps + 16 epilogue warps + 4 encod
 constexpr int kEpiThreadsPerTile = 256;
 constexpr int kPeXyzBytes = kTileM * 64 * 2;  // 16 KB, K padded to 64
 constexpr int kPeDirBytes = kTileM * 32 * 2;  // 8 KB,  K padded to 32
+constexpr int kBiasImgBytes = kTileM * 16;    // 2 KB: one 16-byte row (8 bf16, the first two used) per output
 
 struct TcParams {
   const uint8_t* weights;  // chunk images, consumption order
   const float* consts;     // biases | w_alpha | b_alpha | W_rgb | b_rgb
+  const uint8_t* bias_img; // per layer 2 KB: [128 outputs][8 bf16] = (hi, lo, 0 ...) of the bias (mlp_tc3.cu: bias as an MMA)
   const float* ro; const float* rd; const float* vd; const float* z;
   float* rf;
   float* dbg;              // optional: raw accumulator dump of (dbg_layer, dbg_pass), [tile][128][128]
@@ -118,7 +120,7 @@ __device__ __forceinline__ int chunks_in_pass(const TcLayer& L) { return L.k_mai
 #ifndef DEXNERF_WIDE_EPI
 #define DEXNERF_WIDE_EPI 2
 #endif
-template <bool kRelu, bool kSig, bool kDbg, bool kTape>
+template <bool kRelu, bool kSig, bool kDbg, bool kTape, bool kBias = true, int kEpi = DEXNERF_WIDE_EPI>
 __device__ __forceinline__ void epilogue_pass_wide(uint32_t d_tmem, uint32_t a_store, uint32_t bias, uint32_t wa,
                                                    float& sigma, uint32_t dfree_bar, float* dbg_dst,
                                                    uint8_t* tape_row, uint2* tape_mask) {
@@ -133,13 +135,13 @@ __device__ __forceinline__ void epilogue_pass_wide(uint32_t d_tmem, uint32_t a_s
 #pragma unroll
     for (int i = 0; i < 16; i += 4) {
       float x0, x1, x2, x3;
-#ifdef DEXNERF_EPI_NOBIAS     // experiment (results invalid): what the epilogue costs without the bias add
-      x0 = __uint_as_float(v[i]); x1 = __uint_as_float(v[i + 1]); x2 = __uint_as_float(v[i + 2]); x3 = __uint_as_float(v[i + 3]);
-#else
-      const float4 b4 = lds128(bias + (uint32_t)((c0 + i) * 4));
-      add_f32x2(v[i], v[i + 1], b4.x, b4.y, x0, x1);
-      add_f32x2(v[i + 2], v[i + 3], b4.z, b4.w, x2, x3);
-#endif
+      if (!kBias) {      // the accumulator already holds the bias (mlp_tc3.cu adds it as an MMA)
+        x0 = __uint_as_float(v[i]); x1 = __uint_as_float(v[i + 1]); x2 = __uint_as_float(v[i + 2]); x3 = __uint_as_float(v[i + 3]);
+      } else {
+        const float4 b4 = lds128(bias + (uint32_t)((c0 + i) * 4));
+        add_f32x2(v[i], v[i + 1], b4.x, b4.y, x0, x1);
+        add_f32x2(v[i + 2], v[i + 3], b4.z, b4.w, x2, x3);
+      }
       if (kSig) {
         const float4 w4 = lds128(wa + (uint32_t)((c0 + i) * 4));
         sg[0] = fmaf(kRelu ? fmaxf(x0, 0.0f) : x0, w4.x, sg[0]);
@@ -157,7 +159,7 @@ __device__ __forceinline__ void epilogue_pass_wide(uint32_t d_tmem, uint32_t a_s
       if (kRelu) mbits[c0 >> 5] |= relu_bits16(pk) << (c0 & 16);
     }
   };
-#if DEXNERF_WIDE_EPI == 1
+  if constexpr (kEpi == 1) {
   uint32_t v[2][32];
   tmem_ld32_issue(d_tmem, v[0]);
   tmem_ld32_issue(d_tmem + 32, v[1]);
@@ -171,7 +173,7 @@ __device__ __forceinline__ void epilogue_pass_wide(uint32_t d_tmem, uint32_t a_s
     slice16(&v[h][0], h * 32, pk);
     slice16(&v[h][16], h * 32 + 16, pk);
   }
-#else
+  } else {
   uint32_t v[3][16];
   tmem_ld16_issue(d_tmem, v[0]);
   tmem_ld16_issue(d_tmem + 16, v[1]);
@@ -188,7 +190,7 @@ __device__ __forceinline__ void epilogue_pass_wide(uint32_t d_tmem, uint32_t a_s
   mbar_arrive(dfree_bar);
   slice16(v[2], 32, pk);
   slice16(v[0], 48, pk);
-#endif
+  }
   if (kSig) sigma += (sg[0] + sg[1]) + (sg[2] + sg[3]);
   if (kTape && kRelu) *tape_mask = make_uint2(mbits[0], mbits[1]);
 }
