@@ -1,6 +1,7 @@
 // tcgen05 evaluation of hidden-128 FlexibleNeRFModels (nerf/models.py:185-256 - the width every script of the
 // reference instantiates and all shipped checkpoints have) with THREE 128-sample tiles in
-// flight per SM.  Inference only; same arithmetic contract, weight images, layer table and encoders as mlp_tc.cu.
+// flight per SM.  Inference only; same arithmetic contract, weight images, layer table and encoders as mlp_tc.cu
+// (one difference: the layer bias enters the accumulator as an MMA, see below).
 //
 // Why a second kernel.  At hidden 128 an MMA pass of a tile is 8 instructions (~600 cycles), its epilogue ~1 100, and
 // the hand-offs between them another ~500, so with two tiles in flight (mlp_tc.cu) the tensor pipe waits for the
@@ -12,7 +13,7 @@
 //   TMEM   columns [0, 192): A operand of tile 0 / 1 / 2;  [256, 384): accumulator D0;  [384, 512): accumulator D1
 //   pass k (k = 0, 1, 2, ... over (tile group, layer, tile)) computes tile k % 3 into accumulator k & 1
 //
-//   warp 0        weight producer: 8-slot ring of 16 KB UMMA images, a chunk is consumed by the three tiles
+//   warp 0        weight producer: 6-slot ring of 16 KB UMMA images, a chunk is consumed by the three tiles
 //   warps 1-3     MMA issuers, one per tile (warp 2 is also the TMEM allocator): each does the waiting for its own
 //                 pass (weights, encodings, then the gate: accumulator drained by the epilogue of pass k - 2, A operand
 //                 stored by the tile's own previous epilogue) and then takes its TURN from the issuer of pass k - 1,
@@ -24,7 +25,22 @@
 //                 partial sigma dot product - travels through shared memory)
 //   warps 20-23   encoders for the NEXT group of three tiles
 //
-// With a pass every ~650 cycles each team has ~1 300 cycles per epilogue and a tile's chain may take three passes.
+// The layer biases are MMA operands: D = ones[128 x 16] x B_l[n_out x 16]^T is the first MMA of every pass, with
+// B_l[n][0:2] = (bf16(b), bf16(b - bf16(b))) - both products are exact in the fp32 accumulator, the bias loses less than
+// 2^-17 of its value - so the epilogue is load, ReLU + pack, store (no 16 shared-memory loads and 32 packed adds per warp
+// and pass).  One K group of 8 per operand (2 KB); the second K group of both is a shared block of zeros that the
+// descriptor's leading-dimension offset points to.
+//
+// Measured on a B200 (tools/mlp_sweep.py, 640 000 x 192 samples): 8 x 128 skip 3 37.5 ms = 1 085 TFLOP/s (pair kernel
+// 39.7 - 40.4), 4 x 128 23.6 ms = 875 TFLOP/s (pair kernel 23.7 - 24.4).  What bounds it now (tools/tc3_timeline.py): two
+// passes on the same accumulator are issue (~700 cycles: 9 MMAs) + completion seen by the epilogue (~290) + drain of the
+// accumulator (~850) + gate -> turn -> first MMA (~250) apart, i.e. ~1 050 cycles per pass against 576 of tensor work,
+// and the SM's issue slots are nearly all taken (ncu: 2.1 of 4 instructions per cycle with every warp a dependent
+// chain).  Tried on top and NOT kept: one issuer + scout (the control warp itself needs ~1 000 cycles per pass), two
+// issuers alternating accumulators (same), a hand-written tight barrier-poll loop (more polls per second, everything
+// slower), the whole 64-column share in registers for an early release (needs 88 registers; setmaxnreg is accepted but
+// ptxas keeps allocating 80 and spills: 40.9 ms), all sixteen epilogue warps on every pass with 32 columns each
+// (shorter drain on paper, but twice the per-pass overhead instructions on a saturated SM: 41.5 ms).
 #include <cstdio>
 #include <cstdlib>
 #include <type_traits>
