@@ -74,6 +74,46 @@ def test_tc_query_vs_bf16_emulation(layers, hidden, skip, Lx, n, S):
     assert float((got[..., 3] - full[..., 3]).abs().max()) < 2e-2 * max(1.0, float(full[..., 3].abs().max()))
 
 
+@pytest.mark.parametrize("layers,skip,viewdirs,n,S", [
+    (8, 3, True, 1, 7),            # one padded tile: two of the three tiles of the only group are empty
+    (8, 3, True, 148 * 3 * 4 + 5, 128),   # four groups per CTA plus a ragged tail (1 781 tiles on 148 SMs)
+    (4, 4, True, 777, 192),        # the as-run network, 1 166 tiles: CTAs with 3 and with 2 groups
+    (8, 3, False, 901, 64),        # without view directions (fc_out head), 451 tiles
+    (12, 5, True, 300, 64),        # the deepest network a 16-op program holds (14 tensor-core layers)
+])
+def test_three_tile_kernel_equals_the_pair_kernel(layers, skip, viewdirs, n, S):
+    """Hidden-128 inference runs on csrc/mlp_tc3.cu (three tiles in flight on two shared accumulators, one issuer per
+    tile, layer biases as an MMA); the debug-tap form of dexnerf_tc_query runs the SAME network on the pair kernel of
+    csrc/mlp_tc.cu (biases added in fp32 in the epilogue).  Same bf16 operands, same fp32 accumulation of the same
+    products - what differs is where the bias joins the sum (first instead of last, as bf16 hi + lo: < 2^-17 of its
+    value), i.e. the fp32 summation order and with it a few bf16 rounding flips of activations: the tier-1 bars of the
+    emulation test, and a mean difference below 2e-5 of the largest output.  Sizes: a single tile, several groups per CTA with a ragged
+    tail, uneven group counts; both head forms; twice in a row must be bit-identical (no race in the hand-offs:
+    a parity wait two phases ahead of its barrier once let an accumulator be overwritten before it was drained)."""
+    torch.manual_seed(layers * 131 + S)
+    model = nerf.FlexibleNeRFModel(layers, 128, skip, 10, 4, use_viewdirs=viewdirs).cuda()
+    with torch.no_grad():
+        model.fc_alpha.weight.mul_(30.0) if viewdirs else None
+    ex, ed = nerf.get_embedding_function(10, True, True), nerf.get_embedding_function(4, True, True)
+    prog = model.program(ex, ed)
+    assert tensorcore.supported(model, prog)
+    ro, rd, vd, z = (v.cuda() for v in rays(n, S, seed=n))
+    got = torch.full((n, S, 4), float("nan"), device="cuda")
+    tensorcore.query(model, prog, ro, rd, vd, z, got)
+    again = torch.full((n, S, 4), float("nan"), device="cuda")
+    tensorcore.query(model, prog, ro, rd, vd, z, again)
+    want = torch.full((n, S, 4), float("nan"), device="cuda")
+    dbg = torch.zeros(n * S * 128, device="cuda")          # raw accumulators of layer 0: selects the pair kernel
+    tensorcore.query(model, prog, ro, rd, vd, z, want, dbg=dbg, dbg_layer=0, dbg_pass=0)
+    torch.cuda.synchronize()
+    assert torch.isfinite(got).all() and torch.isfinite(want).all()
+    assert torch.equal(got, again)
+    # the bars of test_tc_query_vs_bf16_emulation, tier 1
+    assert float((got[..., :3] - want[..., :3]).abs().max()) < 1e-3
+    assert float((got[..., 3] - want[..., 3]).abs().max()) < 4e-3 * max(1.0, float(want[..., 3].abs().max()))
+    assert float((got - want).abs().mean()) < 2e-5 * max(1.0, float(want.abs().max()))
+
+
 @pytest.mark.parametrize("Lx,n,S", [(10, 37, 64), (10, 3, 192), (6, 5, 33)])
 def test_tc_query_paper_model_vs_bf16_emulation(Lx, n, S):
     """PaperNeRFModel (models.py:123-182, repaired forward) on the tensor cores: xyz-first skip layer, fc_feat

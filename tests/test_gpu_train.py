@@ -130,7 +130,13 @@ def test_forward_tape(hidden, layers, skip, Lx):
     M = n * S
     rf_inf = torch.empty_like(r["rf"])
     tensorcore.query(model, r["prog"], r["ro"], r["rd"], r["vd"], r["z"], rf_inf)
-    assert torch.equal(rf_inf, r["rf"])
+    if hidden == 256:
+        assert torch.equal(rf_inf, r["rf"])
+    else:
+        # hidden-128 inference runs on the three-tile kernel (csrc/mlp_tc3.cu), which adds a layer's bias FIRST (as an
+        # MMA), the training forward last: same products, another fp32 summation order, hence a few bf16 rounding flips
+        assert float((rf_inf[..., :3] - r["rf"][..., :3]).abs().max()) < 1e-3
+        assert float((rf_inf[..., 3] - r["rf"][..., 3]).abs().max()) < 4e-3 * max(1.0, float(r["rf"][..., 3].abs().max()))
     acts, out = emulate_forward(model, r["enc_xyz"], r["enc_dir"])
     lay, tape = r["lay"], r["tape"]
     nt = lay["n_tiles"]
