@@ -634,3 +634,91 @@ def test_training_iteration_as_run_4x128_lego_checkpoint(golden):
         num = sum(float(((p.grad.cpu() - grads[k]) ** 2).sum()) for k, p in m.named_parameters())
         den = sum(float((grads[k] ** 2).sum()) for k, p in m.named_parameters())
         assert (num / den) ** 0.5 < 4e-2, (num / den) ** 0.5
+
+
+# ------------------------------------------------------------------ convergence parity with the reference itself
+@pytest.mark.parametrize("stochastic", [False, True])
+def test_convergence_parity_with_the_reference_training_loop(tmp_path, stochastic):
+    """400 iterations of the reference's own training loop (oracle/ref_train.py: the UNMODIFIED reference staged in
+    oracle/_ref, torch eager fp32 on the same GPU, train_dexnerf_rgb.py:246-289) against nerf.Trainer (tcgen05 kernels,
+    bf16 operands, fused Adam) from the same initial weights on the same batches of a teacher-rendered scene, with
+    deterministic sampling (no jitter, no sigma noise: the only difference is the arithmetic) and with both on (each
+    side draws its own): the final losses agree and the held-out view's PSNR is within 0.3 dB - the per-tensor gradient
+    deviation of the bf16 contract (up to 12 % on early layers) does not change where training
+    goes.  Measured: 20.25 dB vs 20.25 dB deterministic, 21.25 dB vs the reference's 20.91 dB with jitter and noise."""
+    import json
+    import math
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.isdir(os.path.join(root, "oracle", "_ref", "nerf")):
+        pytest.skip("oracle/_ref is not staged (python oracle/make_ref.py where /root/reference exists)")
+    kw = dict(num_layers=4, hidden_size=128, skip_connect_every=4, num_encoding_fn_xyz=10, num_encoding_fn_dir=4)
+    torch.manual_seed(21)
+    teacher = nerf.FlexibleNeRFModel(**kw)
+    with torch.no_grad():
+        teacher.fc_alpha.weight.mul_(60.0)
+        teacher.fc_alpha.bias.fill_(0.3)
+        teacher.fc_rgb.weight.mul_(6.0)
+    teacher = teacher.cuda()
+    H = W = 24
+    focal, near, far, nc, nf = 30.0, 2.0, 6.0, 32, 32
+    ex, ed = nerf.get_embedding_function(10, True, True), nerf.get_embedding_function(4, True, True)
+    K = torch.tensor([[focal, 0, W / 2.0], [0, focal, H / 2.0], [0, 0, 1]])
+    cfg_val = make_cfg(nc, nf, near, far, False, 0.0, False)
+
+    def view(theta, phi):
+        T = O.pose_spherical_world2cam(theta, phi, 4.0)
+        ro, rd = O.get_ray_bundle(H, W, None, T, K)
+        ro, rd = ro.reshape(-1, 3).cuda(), rd.reshape(-1, 3).cuda()
+        with torch.no_grad():
+            out = nerf.run_one_iter_of_nerf(H, W, focal, teacher, teacher, ro, rd, cfg_val, mode="validation",
+                                            encode_position_fn=ex, encode_direction_fn=ed, m_thres_cand=[])
+        return ro.cpu(), rd.cpu(), out[3][..., :3].clamp(0, 1).cpu()
+
+    views = [view(th, ph) for th, ph in ((0, -30), (60, -20), (120, -35), (180, -25), (240, -30), (300, -15))]
+    ro, rd, target = (torch.cat([v[i] for v in views], 0) for i in range(3))
+    val_ro, val_rd, val_target = view(30.0, -28.0)
+    assert float(target.std()) > 0.05                                   # the scene has structure to learn
+    iters, batch = 400, 512
+    g = torch.Generator().manual_seed(9)
+    batches = [torch.randint(0, ro.shape[0], (batch,), generator=g) for _ in range(iters)]
+    torch.manual_seed(33)
+    sc, sf = nerf.FlexibleNeRFModel(**kw), nerf.FlexibleNeRFModel(**kw)
+    opts = dict(H=H, W=W, focal=focal, near=near, far=far, num_coarse=nc, num_fine=nf, perturb=stochastic,
+                noise_std=0.2 if stochastic else 0.0,
+                lr=5e-3, lr_decay=250, lr_decay_factor=0.1, seed=5)
+    data = dict(model_kwargs=kw, init_coarse=sc.state_dict(), init_fine=sf.state_dict(), options=opts, ro=ro, rd=rd,
+                target=target, batches=batches, val_ro=val_ro, val_rd=val_rd, val_target=val_target)
+    path = str(tmp_path / "run.pt")
+    torch.save(data, path)
+    env = {k: v for k, v in os.environ.items() if k != "PYTHONPATH"}
+    r = subprocess.run([sys.executable, os.path.join(root, "oracle", "ref_train.py"), "--data", path, "--device", "cuda"],
+                       capture_output=True, text=True, env=env, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = json.loads(r.stdout.strip().splitlines()[-1])
+    # this package: the same loop on nerf.Trainer
+    sc, sf = sc.cuda(), sf.cuda()
+    cfg = make_cfg(nc, nf, near, far, False, 0.2 if stochastic else 0.0, stochastic)
+    trainer = nerf.Trainer(sc, sf, cfg, ex, ed, lr=5e-3, lr_decay=250, lr_decay_factor=0.1)
+    ro_d, rd_d, tg_d = ro.cuda(), rd.cuda(), target.cuda()
+    losses = []
+    for idx in batches:
+        idx = idx.cuda()
+        losses.append(float(trainer.step(ro_d[idx], rd_d[idx], tg_d[idx])[0]))
+    trainer.sync_to_modules()
+    with torch.no_grad():
+        out = nerf.run_one_iter_of_nerf(H, W, focal, sc, sf, val_ro.cuda(), val_rd.cuda(), cfg_val, mode="validation",
+                                        encode_position_fn=ex, encode_direction_fn=ed, m_thres_cand=[])
+    mse = float(torch.nn.functional.mse_loss(out[3][..., :3], val_target.cuda()))
+    psnr = -10.0 * math.log10(mse)
+    final = sum(losses[-20:]) / 20
+    print("convergence: reference final loss %.5f val PSNR %.2f dB | this package final loss %.5f val PSNR %.2f dB"
+          % (ref["final_loss"], ref["val_psnr"], final, psnr))
+    assert ref["losses"][0] > 4 * ref["final_loss"] and losses[0] > 4 * final        # both really trained
+    assert abs(math.log(final / ref["final_loss"])) < 0.25                           # same loss level (+-25 %)
+    if stochastic:      # each side draws its own jitter and noise: no worse than the reference by 0.3 dB, and close
+        assert psnr > ref["val_psnr"] - 0.3 and abs(psnr - ref["val_psnr"]) < 1.0, (psnr, ref["val_psnr"])
+    else:               # deterministic sampling: measured 20.25 dB against 20.25 dB, final loss 0.02705 against 0.02705
+        assert abs(psnr - ref["val_psnr"]) < 0.3, (psnr, ref["val_psnr"])
