@@ -99,6 +99,25 @@ class _ProgramModule(torch.nn.Module):
             self.__dict__["_packed_cache"] = cache
         return cache[1]
 
+    def invalidate(self):
+        """Drop the packed fp32 buffer and the bf16 weight images derived from it.  The caches are keyed on
+        (data_ptr, Tensor._version) of every parameter, which covers optimizer steps, `copy_`, `load_state_dict`
+        and `.to()`; in-place writes THROUGH `.data` (`p.data.mul_(...)`, EMA or clipping code) do not bump
+        `_version` - call this after such an edit.  `load_state_dict` and `_apply` (`.to()`, `.cuda()`, `.half()`...)
+        call it themselves."""
+        for k in ("_packed_cache", "_tc_cache", "_tc_cache_t"):
+            self.__dict__.pop(k, None)
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate()
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self.invalidate()
+        return out
+
     # -- nn.Module API -------------------------------------------------------------------
     def forward(self, x):
         xin = L.dev_f32(x, "x")

@@ -201,6 +201,30 @@ def test_tc_weights_repack_after_update():
     assert torch.equal(a[..., 3], b[..., 3])
 
 
+def test_invalidate_after_an_in_place_edit_through_data():
+    """`p.data.mul_()` does not bump Tensor._version, so the (data_ptr, _version) key of the packed-parameter cache
+    cannot see it: the documented contract is model.invalidate() after such an edit (load_state_dict / .to() call it
+    themselves)."""
+    torch.manual_seed(2)
+    model = nerf.FlexibleNeRFModel(4, 128, 4, 10, 4).cuda()
+    ex, ed = nerf.get_embedding_function(10, True, True), nerf.get_embedding_function(4, True, True)
+    prog = model.program(ex, ed)
+    ro, rd, vd, z = (v.cuda() for v in rays(9, 32, seed=1))
+    a = torch.empty(9, 32, 4, device="cuda")
+    tensorcore.query(model, prog, ro, rd, vd, z, a)
+    model.fc_rgb.weight.data.mul_(3.0)                       # invisible to the cache key
+    model.invalidate()
+    b = torch.empty(9, 32, 4, device="cuda")
+    tensorcore.query(model, prog, ro, rd, vd, z, b)
+    assert float((a[..., :3] - b[..., :3]).abs().max()) > 1e-3 and torch.equal(a[..., 3], b[..., 3])
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    sd["fc_rgb.weight"] = sd["fc_rgb.weight"] / 3.0
+    model.load_state_dict(sd)                                # invalidates by itself
+    c = torch.empty(9, 32, 4, device="cuda")
+    tensorcore.query(model, prog, ro, rd, vd, z, c)
+    assert float((a - c).abs().max()) < 1e-5
+
+
 def test_unsupported_models_fall_to_fp32_kernel():
     m = nerf.FlexibleNeRFModel(5, 32, 2, 6, 4).cuda()
     assert not tensorcore.supported(m, m.program())
