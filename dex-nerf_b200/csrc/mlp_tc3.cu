@@ -40,7 +40,9 @@
 // issuers alternating accumulators (same), a hand-written tight barrier-poll loop (more polls per second, everything
 // slower), the whole 64-column share in registers for an early release (needs 88 registers; setmaxnreg is accepted but
 // ptxas keeps allocating 80 and spills: 40.9 ms), all sixteen epilogue warps on every pass with 32 columns each
-// (shorter drain on paper, but twice the per-pass overhead instructions on a saturated SM: 41.5 ms).
+// (shorter drain on paper, but twice the per-pass overhead instructions: 41.5 ms), one polling warp per epilogue team
+// and per encoder group with the others blocked on a named barrier (bar.sync costs no issue slots; no gain: 38.4 / 23.5
+// ms - the spinning warps take slots nobody else wanted, the limit is the latency of the dependent chains).
 #include <cstdio>
 #include <cstdlib>
 #include <type_traits>

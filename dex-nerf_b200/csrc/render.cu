@@ -59,9 +59,12 @@ struct SetupArgs {
   uint64_t seed, offset;
 };
 
+constexpr int kSetupTable = 1024;     // coarse samples per ray the depth tables hold
+
 __global__ void __launch_bounds__(256) ray_setup_kernel(const SetupArgs a) {
   __shared__ float s_rinv[9];
   __shared__ float s_org[3];
+  __shared__ float s_lower[kSetupTable], s_diff[kSetupTable];
   const bool camera = a.ro_in == nullptr;
   if (camera) {
     if (threadIdx.x == 0) camera_inverse(a.T, s_rinv, s_org);
@@ -93,17 +96,53 @@ __global__ void __launch_bounds__(256) ray_setup_kernel(const SetupArgs a) {
     }
   }
   const Philox rng(a.seed);
-  // ---- per coarse sample: depth (+ jitter), coarse sigma noise
+  // ---- per coarse sample: depth (+ jitter), coarse sigma noise.  The linspace depth, and with jitter the lower bound
+  // and the width of the stratum, depend on the sample index only: one table per CTA (the same operations, hence the
+  // same bits, as stratified_depth), then four consecutive samples of a ray per thread and 16-byte stores with
+  // 32-bit index arithmetic - the first version spent its time in a 64-bit modulo per sample (0.22 ms for the 41 M
+  // depths of a C2 frame, 0.13 of the HBM peak).
   const int64_t total_c = a.n * a.Nc;
-  for (int64_t e = tid; e < total_c; e += nth) {
-    const int i = (int)(e % a.Nc);
-    float t = 0.0f;
-    uint4 x = make_uint4(0, 0, 0, 0);
-    const bool draw = (a.perturb && !a.t_rand_in) || a.noise_c_out;
-    if (draw) x = rng((uint64_t)e, 0u, a.offset);
-    if (a.perturb) t = a.t_rand_in ? a.t_rand_in[e] : uniform01(x.x);
-    a.z[e] = stratified_depth(a.near, a.far, a.Nc, a.lindisp, i, a.perturb != 0, t);
-    if (a.noise_c_out) a.noise_c_out[e] = normal01(x.y, x.z) * a.noise_std;
+  const bool draw = (a.perturb && !a.t_rand_in) || a.noise_c_out;
+  if (a.Nc <= kSetupTable && a.Nc % 4 == 0 && total_c < (int64_t)1 << 32) {
+    for (int i = threadIdx.x; i < a.Nc; i += blockDim.x) {
+      const float v = coarse_depth(a.near, a.far, a.Nc, a.lindisp, i);
+      float lower = v, diff = 0.0f;
+      if (a.perturb) {
+        const float prev = i > 0 ? coarse_depth(a.near, a.far, a.Nc, a.lindisp, i - 1) : v;
+        const float next = i < a.Nc - 1 ? coarse_depth(a.near, a.far, a.Nc, a.lindisp, i + 1) : v;
+        lower = i > 0 ? __fmul_rn(0.5f, __fadd_rn(v, prev)) : v;
+        const float upper = i < a.Nc - 1 ? __fmul_rn(0.5f, __fadd_rn(next, v)) : v;
+        diff = __fsub_rn(upper, lower);
+      }
+      s_lower[i] = lower; s_diff[i] = diff;
+    }
+    __syncthreads();
+    const uint32_t quads = (uint32_t)(total_c >> 2), step = (uint32_t)nth, nc = (uint32_t)a.Nc;
+    for (uint32_t q = (uint32_t)tid; q < quads; q += step) {
+      const uint32_t e0 = q << 2, i0 = e0 % nc;
+      float zz[4], nz[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float t = 0.0f;
+        uint4 x = make_uint4(0, 0, 0, 0);
+        if (draw) x = rng((uint64_t)(e0 + k), 0u, a.offset);
+        if (a.perturb) t = a.t_rand_in ? a.t_rand_in[e0 + k] : uniform01(x.x);
+        zz[k] = a.perturb ? __fadd_rn(s_lower[i0 + k], __fmul_rn(s_diff[i0 + k], t)) : s_lower[i0 + k];
+        nz[k] = a.noise_c_out ? normal01(x.y, x.z) * a.noise_std : 0.0f;
+      }
+      reinterpret_cast<float4*>(a.z)[q] = make_float4(zz[0], zz[1], zz[2], zz[3]);
+      if (a.noise_c_out) reinterpret_cast<float4*>(a.noise_c_out)[q] = make_float4(nz[0], nz[1], nz[2], nz[3]);
+    }
+  } else {
+    for (int64_t e = tid; e < total_c; e += nth) {
+      const int i = (int)(e % a.Nc);
+      float t = 0.0f;
+      uint4 x = make_uint4(0, 0, 0, 0);
+      if (draw) x = rng((uint64_t)e, 0u, a.offset);
+      if (a.perturb) t = a.t_rand_in ? a.t_rand_in[e] : uniform01(x.x);
+      a.z[e] = stratified_depth(a.near, a.far, a.Nc, a.lindisp, i, a.perturb != 0, t);
+      if (a.noise_c_out) a.noise_c_out[e] = normal01(x.y, x.z) * a.noise_std;
+    }
   }
   // ---- per fine draw: u
   if (a.u_out) {
