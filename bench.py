@@ -426,8 +426,12 @@ def run_train(args, dist, rank, world, dev, quiet=False):
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "C4: NeRF training iteration, 4096 rays per GPU drawn from the C2 800x800 bundle, train "
                                "mode (perturb, sigma noise 0.2), two 8x256 skip-4 FlexibleNeRFModels, mse(coarse)+mse(fine), "
-                               "Adam lr 5e-3 with exponential decay; gradients all-reduced with NCCL when N > 1",
+                               "Adam lr 5e-3 with exponential decay; N > 1: gradient mean + Adam in one kernel over NVLink peer "
+                               "memory (NCCL all-reduce with DEXNERF_P2P=0 or the autograd API)",
                    "rays_per_step": rays, "parallelism": "dp%d" % world,
+                   "gradient_exchange": ("none (1 GPU)" if world == 1 else
+                                         ("fused P2P all-reduce + Adam kernel (csrc/p2p.cu)" if api == "trainer" and
+                                          getattr(trainer, "_p2p", None) is not None else "NCCL all-reduce")),
                    "api": "nerf.Trainer (flat buffers, fused Adam)" if api == "trainer"
                           else "run_one_iter_of_nerf(mode='train') autograd + torch.optim.Adam",
                    "l2": "the per-step forward tape (5.3 KB/sample, 5.6 GB per step) exceeds the 126 MB L2"},

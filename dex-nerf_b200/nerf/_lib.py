@@ -85,6 +85,13 @@ _SIGS = {
     "dexnerf_adam_step_zero_grad": (C.c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _L, _F, _P]),
     "dexnerf_pack_params": (C.c_int, [C.POINTER(Program), _P, _P, _P]),
     "dexnerf_adam_step": (C.c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _L, _F, _P]),
+    "dexnerf_p2p_alloc": (C.c_int, [_L, C.POINTER(C.c_void_p)]),
+    "dexnerf_p2p_free": (C.c_int, [_P]),
+    "dexnerf_p2p_export": (C.c_int, [_P, _P]),
+    "dexnerf_p2p_open": (C.c_int, [_P, C.POINTER(C.c_void_p)]),
+    "dexnerf_p2p_close": (C.c_int, [_P]),
+    "dexnerf_adam_step_allreduce": (C.c_int, [_P, _P, _P, _P, _L, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int,
+                                              C.c_int, C.c_uint32, _F, _F, _F, _F, _L, _F, _P]),
     "dexnerf_depth_error_metrics": (C.c_int, [_P, _P, _P, _L, _I, _P, _P, _P, _P]),
     "dexnerf_depth_error_image": (C.c_int, [_P, _P, _P, _I, _I, _F, _P, _P]),
     "dexnerf_render_workspace_bytes": (C.c_int64, [_L, _I, _I]),

@@ -9,6 +9,8 @@ to the model parameters only - depths are detached exactly where the reference d
 (train_utils.py:170) and ray origins / directions never require grad in the reference scripts."""
 import ctypes as C
 
+import os
+
 import torch
 
 from . import _lib as L
@@ -212,6 +214,17 @@ def train_step(model_coarse, model_fine, optimizer, ro, rd, target, cfg, encode_
 # ---------------------------------------------------------------------------------------------------
 # Trainer: the training iteration without per-tensor glue
 # ---------------------------------------------------------------------------------------------------
+class _DeviceMemory:
+    """A raw device allocation as a __cuda_array_interface__ object (float32 vector)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
+
+
+def _wrap_device_memory(ptr, n, dev):
+    return torch.as_tensor(_DeviceMemory(ptr, n), device=dev)
+
+
 class Trainer:
     """The reference's training iteration (train_dexnerf_rgb.py:246-289) on FLAT buffers.
 
@@ -263,6 +276,9 @@ class Trainer:
             self.views.append((off, n))
             off += n
         self.grads = torch.zeros_like(self.params)
+        self._p2p = None             # data-parallel step over NVLink peer memory (see _setup_p2p)
+        if self.world > 1 and os.environ.get("DEXNERF_P2P", "1") != "0":
+            self._setup_p2p(dev, total)
         self.exp_avg = torch.zeros_like(self.params)
         self.exp_avg_sq = torch.zeros_like(self.params)
         self.loss = torch.zeros(3, dtype=torch.float32, device=dev)     # total, coarse, fine
@@ -274,6 +290,81 @@ class Trainer:
             self.blobs.append(torch.empty(L.lib().dexnerf_tc_packed_bytes(spec), dtype=torch.uint8, device=dev))
             self.blobs_t.append(torch.empty(L.lib().dexnerf_tc_packed_bwd_bytes(spec), dtype=torch.uint8, device=dev))
         self._repack()
+
+    # -- NVLink peer memory ------------------------------------------------------------------
+    def _setup_p2p(self, dev, total):
+        """One process per GPU: two IPC-exportable gradient buffers (they ping-pong between steps) and a flag array per
+        rank, every rank's mapped into every process.  With them a training step needs no NCCL call: the fused
+        all-reduce + Adam kernel (csrc/p2p.cu) reads the peers' gradients directly.  Falls back to the NCCL all-reduce
+        (self._p2p = None) when the ranks are not all P2P peers on one node or the handles cannot be opened."""
+        import torch.distributed as dist
+        rank = dist.get_rank(self.group)
+        lib = L.lib()
+        ok = total % 4 == 0 and self.world <= 8
+        if ok:
+            me = dev.index if dev.index is not None else torch.cuda.current_device()
+            devs = [None] * self.world
+            dist.all_gather_object(devs, (os.uname().nodename, me), group=self.group)
+            ok = len({d[0] for d in devs}) == 1 and len({d[1] for d in devs}) == self.world
+            ok = ok and all(d[1] == me or torch.cuda.can_device_access_peer(me, d[1]) for d in devs)
+        flags_ok = [None] * self.world
+        dist.all_gather_object(flags_ok, bool(ok), group=self.group)
+        if not all(flags_ok):
+            return
+        own, handles = [], []
+        for nbytes in (total * 4, total * 4, 256):          # gradient buffer 0, gradient buffer 1, flags
+            ptr = C.c_void_p()
+            L.check(lib.dexnerf_p2p_alloc(nbytes, C.byref(ptr)), "p2p_alloc")
+            h = C.create_string_buffer(64)
+            L.check(lib.dexnerf_p2p_export(ptr, h), "p2p_export")
+            own.append(ptr.value)
+            handles.append(h.raw)
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, handles, group=self.group)
+        table = []                                           # table[r] = (grads0, grads1, flags) of rank r, valid here
+        opened = []
+        try:
+            for r in range(self.world):
+                if r == rank:
+                    table.append(tuple(own))
+                    continue
+                ptrs = []
+                for h in everyone[r]:
+                    q = C.c_void_p()
+                    L.check(lib.dexnerf_p2p_open(C.create_string_buffer(h, 64), C.byref(q)), "p2p_open")
+                    ptrs.append(q.value)
+                    opened.append(q.value)
+                table.append(tuple(ptrs))
+            opened_ok = True
+        except L.DexNerfError:
+            opened_ok = False
+        all_ok = [None] * self.world
+        dist.all_gather_object(all_ok, opened_ok, group=self.group)
+        if not all(all_ok):
+            for q in opened:
+                lib.dexnerf_p2p_close(q)
+            for q in own:
+                lib.dexnerf_p2p_free(q)
+            return
+        gbufs = [_wrap_device_memory(own[k], total, dev) for k in (0, 1)]
+        arr = lambda k: (C.c_void_p * self.world)(*[table[r][k] for r in range(self.world)])
+        self._p2p = dict(rank=rank, own=own, opened=opened, gbufs=gbufs, peer_grads=(arr(0), arr(1)), peer_flags=arr(2),
+                         token=0)
+        self.grads = gbufs[0]
+
+    def close(self):
+        """Unmap the peers' buffers and free this rank's (after a barrier: nobody may still be reading them)."""
+        if self._p2p is not None:
+            import torch.distributed as dist
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+            p, self._p2p = self._p2p, None
+            self.grads = p["gbufs"][0].clone()
+            for q in p["opened"]:
+                L.lib().dexnerf_p2p_close(q)
+            dist.barrier(group=self.group)
+            for q in p["own"]:
+                L.lib().dexnerf_p2p_free(q)
 
     # -- parameter plumbing -------------------------------------------------------------------
     def _flat(self, buf, i):
@@ -454,7 +545,7 @@ class Trainer:
         n_total = ro.shape[0]
         chunk = int(getattr(opt, "chunksize", n_total) or n_total)
         self.loss.zero_()
-        if self.keep_grads:
+        if self.keep_grads and self._p2p is None:
             self.grads.zero_()        # otherwise the previous Adam launch has already cleared them
         starts = list(range(0, n_total, chunk))
         pending = []
@@ -464,20 +555,35 @@ class Trainer:
             # the fine network's backward runs first: on the last chunk its gradients are final as soon as its
             # weight-gradient GEMM is enqueued, so their all-reduce overlaps the coarse network's backward
             after_fine = None
-            if self.world > 1 and start == starts[-1]:
+            if self.world > 1 and self._p2p is None and start == starts[-1]:
                 after_fine = lambda: pending.append(self._allreduce_async(self._flat(self.grads, 1)))
             self._accumulate(ro[sl], rd[sl], tgt[sl], sub, n_total, after_fine, height, width, focal_length)
-        if self.world > 1:
+        if self.world > 1 and self._p2p is None:
             pending.append(self._allreduce_async(self._flat(self.grads, 0)))
             for work in pending:
                 work.wait()              # stream-level wait: the Adam launch below is ordered after both
         # Adam with the script's schedule: iteration i steps with the rate set after iteration i-1 (:283-289)
         lr = self._lr_now
         self.adam_steps += 1
-        adam = L.lib().dexnerf_adam_step if self.keep_grads else L.lib().dexnerf_adam_step_zero_grad
-        L.check(adam(L.ptr(self.params), L.ptr(self.grads), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq),
-                     self.params.numel(), lr, self.betas[0], self.betas[1], self.eps, self.adam_steps, 1.0 / self.world,
-                     L.stream_ptr()), "adam_step")
+        if self._p2p is not None:
+            # ONE kernel: barrier over NVLink flags, sum of every rank's gradients (P2P loads, rank order), Adam,
+            # and the other gradient buffer cleared for the next step (csrc/p2p.cu)
+            p = self._p2p
+            cur = p["token"] & 1
+            p["token"] += 1
+            nxt = p["gbufs"][cur ^ 1]
+            L.check(L.lib().dexnerf_adam_step_allreduce(
+                L.ptr(self.params), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq), L.ptr(nxt), self.params.numel(),
+                p["peer_grads"][cur], p["peer_flags"], p["rank"], self.world, p["token"], lr, self.betas[0],
+                self.betas[1], self.eps, self.adam_steps, 1.0 / self.world, L.stream_ptr()), "adam_step_allreduce")
+            if self.keep_grads:
+                self.last_grads = p["gbufs"][cur]        # this rank's own gradients of the step (not the mean)
+            self.grads = nxt
+        else:
+            adam = L.lib().dexnerf_adam_step if self.keep_grads else L.lib().dexnerf_adam_step_zero_grad
+            L.check(adam(L.ptr(self.params), L.ptr(self.grads), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq),
+                         self.params.numel(), lr, self.betas[0], self.betas[1], self.eps, self.adam_steps,
+                         1.0 / self.world, L.stream_ptr()), "adam_step")
         self._lr_now = learning_rate(self.lr, self.iteration, self.lr_decay, self.lr_decay_factor)
         self.iteration += 1
         self._repack()

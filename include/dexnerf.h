@@ -306,6 +306,27 @@ DEXNERF_API int dexnerf_adam_step_zero_grad(float* params, float* grads, float* 
                                 float lr, float beta1, float beta2, float eps, int64_t step, float grad_scale,
                                 void* stream);
 
+/* ---- Data-parallel training over NVLink peer memory (one process per GPU).
+ * Replaces, for the flat-buffer trainer, the pair "ncclAllReduce of the gradients, then optimizer.step()"
+ * (train_dexnerf_rgb.py:278-281 on every rank of a data-parallel run) by ONE kernel that reads every rank's gradient
+ * buffer directly (P2P loads), sums in rank order, applies torch.optim.Adam's update and clears the next step's buffer.
+ * dexnerf_p2p_alloc: a zeroed cudaMalloc allocation that CUDA IPC can export; _export writes the 64-byte
+ * cudaIpcMemHandle_t, _open maps a peer's handle into this process (peer access enabled lazily), _close unmaps it. */
+DEXNERF_API int dexnerf_p2p_alloc(int64_t bytes, void** ptr);
+DEXNERF_API int dexnerf_p2p_free(void* ptr);
+DEXNERF_API int dexnerf_p2p_export(void* ptr, void* handle64);
+DEXNERF_API int dexnerf_p2p_open(const void* handle64, void** ptr);
+DEXNERF_API int dexnerf_p2p_close(void* ptr);
+/* peer_grads[r] / peer_flags[r] (HOST arrays of `world` device pointers valid on this GPU; entry `rank` is the local
+ * buffer): every rank's gradient buffer of THIS step (n floats) and every rank's flag array (`world` uint32, from
+ * dexnerf_p2p_alloc).  The gradient buffers ping-pong between steps: `zero_next` is the LOCAL buffer the next step
+ * accumulates into; it is cleared here.  `token` must grow by one per call, the same on every rank, starting at 1.
+ * n must be a multiple of 4; `step` is Adam's step count (from 1); grad_scale = 1 / world for the mean. */
+DEXNERF_API int dexnerf_adam_step_allreduce(float* params, float* exp_avg, float* exp_avg_sq, float* zero_next, int64_t n,
+                                const void* const* peer_grads, void* const* peer_flags, int rank, int world,
+                                uint32_t token, float lr, float beta1, float beta2, float eps, int64_t step,
+                                float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
