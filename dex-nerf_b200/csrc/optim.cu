@@ -81,6 +81,36 @@ __global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, f
   }
 }
 
+// The same update on four consecutive parameters per thread (16-byte loads and stores; the flat buffers are 16-byte
+// aligned and a multiple of four long): the scalar form ran at 0.5 TB/s (68 us for the 1.19 M parameters of the two
+// 8x256 networks - more than the compositing and resampling kernels of a training iteration together).
+template <bool kZero>
+__global__ void __launch_bounds__(256) adam_step_vec4_kernel(float4* __restrict__ p, float4* __restrict__ g,
+                                                             float4* __restrict__ m, float4* __restrict__ v, int64_t n4,
+                                                             float beta1, float beta2, float eps, float step_size,
+                                                             float bc2_sqrt, float grad_scale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 gg = g[i];
+    float4 pp = p[i], mm = m[i], vv = v[i];
+    if (kZero) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float gs[4] = {gg.x, gg.y, gg.z, gg.w};
+    float* ps[4] = {&pp.x, &pp.y, &pp.z, &pp.w};
+    float* ms[4] = {&mm.x, &mm.y, &mm.z, &mm.w};
+    float* vs[4] = {&vv.x, &vv.y, &vv.z, &vv.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gi = __fmul_rn(gs[k], grad_scale);
+      const float mi = __fmaf_rn(1.0f - beta1, __fsub_rn(gi, *ms[k]), *ms[k]);
+      const float vi = __fmaf_rn(__fmul_rn(1.0f - beta2, gi), gi, __fmul_rn(*vs[k], beta2));
+      const float denom = __fadd_rn(__fdiv_rn(sqrtf(vi), bc2_sqrt), eps);
+      *ps[k] = __fsub_rn(*ps[k], __fmul_rn(step_size, __fdiv_rn(mi, denom)));
+      *ms[k] = mi;
+      *vs[k] = vi;
+    }
+    p[i] = pp; m[i] = mm; v[i] = vv;
+  }
+}
+
 }  // namespace dexnerf
 
 using namespace dexnerf;
@@ -137,6 +167,22 @@ static int adam_impl(float* params, float* grads, float* exp_avg, float* exp_avg
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   const float step_size = (float)((double)lr / bc1);
   const float bc2_sqrt = (float)sqrt(bc2);
+  const bool vec = n % 4 == 0 && ((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) |
+                                   reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0;
+  if (vec) {
+    int64_t vb = ceil_div64(n / 4, 256);
+    if (vb > kNumSMs * 8) vb = kNumSMs * 8;
+    auto p4 = reinterpret_cast<float4*>(params), g4 = reinterpret_cast<float4*>(grads);
+    auto m4 = reinterpret_cast<float4*>(exp_avg), v4 = reinterpret_cast<float4*>(exp_avg_sq);
+    if (zero)
+      adam_step_vec4_kernel<true><<<(int)vb, 256, 0, (cudaStream_t)stream>>>(p4, g4, m4, v4, n / 4, beta1, beta2, eps,
+                                                                            step_size, bc2_sqrt, grad_scale);
+    else
+      adam_step_vec4_kernel<false><<<(int)vb, 256, 0, (cudaStream_t)stream>>>(p4, g4, m4, v4, n / 4, beta1, beta2, eps,
+                                                                             step_size, bc2_sqrt, grad_scale);
+    DN_CHECK_LAUNCH("adam_step");
+    return 0;
+  }
   int64_t blocks = ceil_div64(n, 256 * 4);
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
   if (zero)
