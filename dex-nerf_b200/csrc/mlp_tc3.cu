@@ -31,7 +31,7 @@
 // and pass).  One K group of 8 per operand (2 KB); the second K group of both is a shared block of zeros that the
 // descriptor's leading-dimension offset points to.
 //
-// Measured on a B200 (tools/mlp_sweep.py, 640 000 x 192 samples): 8 x 128 skip 3 37.5 ms = 1 085 TFLOP/s (pair kernel
+// Measured on a B200 (tools/mlp_sweep.py, 640 000 x 192 samples): 8 x 128 skip 3 36.7 ms = 1 108 TFLOP/s (pair kernel
 // 39.7 - 40.4), 4 x 128 23.6 ms = 875 TFLOP/s (pair kernel 23.7 - 24.4).  What bounds it now (tools/tc3_timeline.py): two
 // passes on the same accumulator are issue (~700 cycles: 9 MMAs) + completion seen by the epilogue (~290) + drain of the
 // accumulator (~850) + gate -> turn -> first MMA (~250) apart, i.e. ~1 050 cycles per pass against 576 of tensor work,
@@ -86,6 +86,9 @@ __device__ __forceinline__ int B_turn(int t) { return 2 * kSlots + 5 * kNT + 2 +
 __device__ __forceinline__ int B_dfree(int b, int t) { return 2 * kSlots + 6 * kNT + 2 + b * kNT + t; }   // drained by tile t's epilogue
 
 constexpr int kH = 128;
+#ifndef DEXNERF_TC3_TURN_FIRST
+#define DEXNERF_TC3_TURN_FIRST 1
+#endif
 #ifndef DEXNERF_TC3_EPI
 #define DEXNERF_TC3_EPI 2
 #endif
@@ -261,11 +264,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc3_kernel(const __grid_const
         // an issuer polling early could still be TWO drains ahead - a false "complete", found the hard way)
         const uint32_t jp = (t == kNT - 1) ? j : j - 1;
         const uint32_t dfree_bar = bar(B_dfree((int)b, tp));
+#if DEXNERF_TC3_TURN_FIRST
+        // my turn first (pass kk - 1 is issued one pass before the accumulator of pass kk - 2 is drained, so it is
+        // normally there), the gate last: nothing but the fence stands between the drain and the first MMA
+        if (kk) mbar_wait(my_turn, (t ? j : j - 1) & 1, 40);
+        trace(P, 1 + t, 2, kk, tn);
+        if (j) mbar_wait2(dfree_bar, (jp >> 1) & 1, aready_bar, (j - 1) & 1, 35);
+        else if (kk >= 2) mbar_wait(dfree_bar, (jp >> 1) & 1, 35);
+#else
         if (j) mbar_wait2(dfree_bar, (jp >> 1) & 1, aready_bar, (j - 1) & 1, 35);
         else if (kk >= 2) mbar_wait(dfree_bar, (jp >> 1) & 1, 35);
         trace(P, 1 + t, 2, kk, tn);
         // my turn: pass kk - 1 has been issued
         if (kk) mbar_wait(my_turn, (t ? j : j - 1) & 1, 40);
+#endif
         tc_fence_after();
         trace(P, 1 + t, 3, kk, tn);
         if (L.k_main == kH && L.smem_src == 0 && L.n_out == kH) {
