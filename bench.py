@@ -664,9 +664,36 @@ def main():
     # NVLink (nerf.gather_rows: rgb + the T Dex planes + expected depth + acc of the fine pass, what a consumer
     # of the frame reads) and rank 0 copies the full planes to pinned host memory
     ms_gathered, gathered_bytes = None, None
+    ms_shared = None
     if dist is not None:
         from nerf.sharding import gather_rows
         full_pin = None
+        # (a) nerf.SharedFrame: every rank's compositing kernel writes its rows straight into rank 0's frame over
+        # NVLink peer memory - no collective; rank 0 copies the assembled planes to pinned host memory
+        try:
+            shared = nerf.SharedFrame(H, W, len(THRESHOLDS))
+        except L.DexNerfError:
+            shared = None
+        if shared is not None:
+            shared_pin = torch.empty(shared.planes.shape, dtype=torch.float32).pin_memory() if rank == 0 else None
+            row0_, rows_ = nerf.row_block(H, rank, world)
+
+            def shared_step():
+                nerf.render_camera(H, W, T_pin.to(dev, non_blocking=True), K_pin.to(dev, non_blocking=True), mc, mf, cfg,
+                                   mode="validation", encode_position_fn=ex, encode_direction_fn=ed,
+                                   m_thres_cand=THRESHOLDS, row_start=row0_, row_count=rows_, frame=shared)
+                shared.wait()
+                if rank == 0:
+                    shared_pin.copy_(shared.planes, non_blocking=True)
+            for _ in range(2):
+                shared_step()
+            barrier()
+            e0.record()
+            for _ in range(args.steps):
+                shared_step()
+            e1.record()
+            barrier()
+            ms_shared = reduce_max(e0.elapsed_time(e1) / args.steps)
 
         def gathered_step():
             nonlocal full_pin
@@ -727,6 +754,13 @@ def main():
             k: {"ms": ms, "bytes": nbytes, "achieved_gbs": nbytes / (ms * 1e-3) / 1e9,
                 "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / pk["hbm"]} for k, ms, nbytes in hbm_log}
         line["kernel_ms_per_launch"] = {k: round(v, 4) for k, v in sorted(per_launch.items())}
+        if ms_shared is not None:
+            line["e2e_shared_frame"] = {"value": rays / (ms_shared * 1e-3), "unit": "rays/s", "ms_per_step": ms_shared,
+                                        "frame_bytes": H * W * (5 + len(THRESHOLDS)) * 4,
+                                        "what": "nerf.SharedFrame: the fine pass's planes written by every rank's "
+                                                "compositing kernel straight into rank 0's frame over NVLink peer "
+                                                "memory (no collective), barrier, rank 0 copies the frame to pinned "
+                                                "host memory"}
         if ms_gathered is not None:
             line["e2e_gathered"] = {"value": rays / (ms_gathered * 1e-3), "unit": "rays/s", "ms_per_step": ms_gathered,
                                     "gathered_bytes_per_step": gathered_bytes,

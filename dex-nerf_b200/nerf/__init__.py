@@ -15,7 +15,7 @@ from .nerf_helpers import (cumprod_exclusive, gather_cdf_util, get_embedding_fun
                            sample_pdf_2)
 from .train_utils import (get_precision, predict_and_render_radiance, render_camera, run_network,
                           run_one_iter_of_nerf, sample_pdf, set_precision)
-from .sharding import allreduce_gradients, gather_rows, row_block
+from .sharding import SharedFrame, allreduce_gradients, gather_rows, row_block
 from .training import Trainer, learning_rate, train_step
 from .datasets import load_blender_data, load_llff_data, load_messytable_data
 from .eval_utils import (cast_to_image, compute_err_metric, depth_error_img, dex_depth_error_metrics, pose_spherical, render_path,

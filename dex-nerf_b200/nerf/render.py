@@ -147,7 +147,7 @@ def _ptr_at(t, row, row_floats):
 
 
 def render_rays(height, width, focal_length, model_coarse, model_fine, ro, rd, options, mode, embed_fn, embeddirs_fn,
-                thr, T, rng, precision, camera=None):
+                thr, T, rng, precision, camera=None, out=None):
     """All chunks of one run_one_iter_of_nerf call through the fused entry.  ro, rd: contiguous (n,3) CUDA fp32 -
     or None with camera = (T_w2c, K, row0, rows) (ray generation inside the setup launch).
     Returns [rgb_c, depth_c, acc_c, rgb_f, depth_f, acc_f, dex (T,n) or None] as flat tensors."""
@@ -163,6 +163,16 @@ def render_rays(height, width, focal_length, model_coarse, model_fine, ro, rd, o
             torch.empty((n_total,), dtype=torch.float32, device=dev), torch.empty((n_total, 3), dtype=torch.float32, device=dev),
             torch.empty((n_total,), dtype=torch.float32, device=dev), torch.empty((n_total,), dtype=torch.float32, device=dev),
             torch.empty((T, n_total), dtype=torch.float32, device=dev) if T else None]
+    dex_stride = n_total
+    if out is not None:
+        # fine-pass planes written in place, e.g. straight into another GPU's frame (nerf.SharedFrame.outputs):
+        # [rgb (n,3), depth (n,), acc (n,), first Dex plane (n,) or None, floats between Dex planes]
+        for k, t in enumerate(out[:4]):
+            if t is not None and (t.dtype != torch.float32 or not t.is_contiguous() or t.shape[0] != n_total):
+                raise ValueError("render_rays: out[%d] must be a contiguous float32 tensor of %d rays" % (k, n_total))
+        outs[3], outs[4], outs[5] = out[0], out[1], out[2]
+        if T:
+            outs[6], dex_stride = out[3], int(out[4])
     if n_total == 0:
         return outs
     use_viewdirs = bool(options.nerf.use_viewdirs)
@@ -180,7 +190,7 @@ def render_rays(height, width, focal_length, model_coarse, model_fine, ro, rd, o
     fill_common(p, opt, options, use_viewdirs, height, width, focal_length, thr, T)
     p.coarse, p.fine = ref_c, ref_f
     p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
-    p.dex_stride = n_total
+    p.dex_stride = dex_stride
     for start in range(0, n_total, chunk):
         n = min(chunk, n_total - start)
         p.n = n

@@ -228,7 +228,7 @@ def _fused_ok(model_coarse, model_fine, mode, embed_fn, embeddirs_fn):
 
 
 def _run_fused(height, width, focal_length, model_coarse, model_fine, ro_in, rd_in, options, mode, embed_fn,
-               embeddirs_fn, m_thres_cand, rng, camera=None):
+               embeddirs_fn, m_thres_cand, rng, camera=None, out=None):
     """run_one_iter_of_nerf as one C-ABI call per ray chunk (6 launches; no torch kernel)."""
     from . import render
     opt = getattr(options.nerf, mode)
@@ -246,8 +246,13 @@ def _run_fused(height, width, focal_length, model_coarse, model_fine, ro_in, rd_
     if (camera is None and rd.shape[0] == 0) or (camera is not None and shape[0] * shape[1] == 0):
         return ()      # no rays -> no ray chunks -> the reference's zip(*[]) is empty (train_utils.py:252-282)
     outs = render.render_rays(height, width, focal_length, model_coarse, model_fine, ro, rd, options, mode, embed_fn,
-                              embeddirs_fn, thr, T, rng, _precision, camera=camera)
-    images = outs[:6] + [outs[6][t] for t in range(T)]
+                              embeddirs_fn, thr, T, rng, _precision, camera=camera, out=out)
+    if out is not None and T:      # the Dex planes live in the shared frame, out[4] floats apart
+        n = outs[3].shape[0]
+        images = outs[:6] + [torch.as_strided(outs[6], (n,), (1,), outs[6].storage_offset() + t * int(out[4]))
+                             for t in range(T)]
+    else:
+        images = outs[:6] + [outs[6][t] for t in range(T)]
     if mode == "validation":
         shapes = [shape, shape[:-1], shape[:-1]] * 2 + [shape[:-1]] * T
         images = [image.view(s) for image, s in zip(images, shapes)]
@@ -256,24 +261,34 @@ def _run_fused(height, width, focal_length, model_coarse, model_fine, ro_in, rd_
 
 def render_camera(height, width, tform_cam2world, intrinsic, model_coarse, model_fine, options, mode="validation",
                   encode_position_fn=None, encode_direction_fn=None, m_thres_cand=None, row_start=0, row_count=None,
-                  rng=None):
+                  rng=None, frame=None):
     """get_ray_bundle + run_one_iter_of_nerf for one camera in ONE fused call per chunk (extension): the rays of
     image rows [row_start, row_start + row_count) are generated inside the setup launch from the world->cam
     extrinsic and the intrinsic (same quirks as get_ray_bundle, nerf_helpers.py:67-112), so a frame is
-    6 launches.  Returns run_one_iter_of_nerf's tuple, shaped (rows, width[, 3]) in validation mode."""
+    6 launches.  Returns run_one_iter_of_nerf's tuple, shaped (rows, width[, 3]) in validation mode.
+    `frame` (a nerf.SharedFrame): the fine pass's planes of these rows are written straight into the frame held by
+    the root rank - over NVLink from the compositing kernel itself - instead of into local tensors."""
     from .nerf_helpers import _small_to_device
     T = _small_to_device(tform_cam2world, "tform_cam2world", (4, 4))
     K = _small_to_device(intrinsic, "intrinsic", (3, 3))
     rows = int(height) - int(row_start) if row_count is None else int(row_count)
     if not _fused_ok(model_coarse, model_fine, mode, encode_position_fn, encode_direction_fn):
+        if frame is not None:
+            raise L.DexNerfError("render_camera(frame=...) needs the fused render path (tensor-core or fp32 kernel models "
+                                 "with nerf.get_embedding_function encoders)")
         from .nerf_helpers import get_ray_bundle
         ro, rd = get_ray_bundle(height, width, None, T, K, row_start=row_start, row_count=rows)
         return run_one_iter_of_nerf(height, width, K[0, 0], model_coarse, model_fine, ro, rd, options, mode=mode,
                                     encode_position_fn=encode_position_fn, encode_direction_fn=encode_direction_fn,
                                     m_thres_cand=m_thres_cand, rng=rng)
     focal = float(K[0, 0]) if options.dataset.no_ndc is False else 0.0     # only ndc_rays reads it (a host sync)
+    out = None
+    if frame is not None:
+        if (int(height), int(width)) != (frame.H, frame.W) or len(list(m_thres_cand)) != frame.T:
+            raise ValueError("render_camera: the SharedFrame was made for another frame size / threshold count")
+        out = frame.outputs(row_start, rows)
     return _run_fused(height, width, focal, model_coarse, model_fine, None, None, options, mode, encode_position_fn,
-                      encode_direction_fn, m_thres_cand, rng, camera=(T, K, int(row_start), rows))
+                      encode_direction_fn, m_thres_cand, rng, camera=(T, K, int(row_start), rows), out=out)
 
 
 def run_one_iter_of_nerf(height, width, focal_length, model_coarse, model_fine, ray_origins, ray_directions,
