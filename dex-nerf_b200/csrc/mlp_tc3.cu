@@ -214,11 +214,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc3_kernel(const __grid_const
     // that the passes enter the tensor pipe strictly in order (interleaved, two passes would both finish late, and the
     // MMA -> epilogue -> MMA chain of a tile is what matters).  Power-of-two ring (slot = counter & 7), one elected
     // block per pass, straight-line code for plain H -> H layers.
-#ifdef DEXNERF_TC3_SWAP
-    const int t = warp == 1 ? 0 : (warp == 2 ? 2 : 1);   // experiment: warp 2 (the allocator) issues tile 2
-#else
     const int t = warp - 1;                   // my tile
-#endif
     if (kRebalance) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     const bool leader = elect_one();
     uint32_t tn = 0;
