@@ -42,7 +42,11 @@
 // ptxas keeps allocating 80 and spills: 40.9 ms), all sixteen epilogue warps on every pass with 32 columns each
 // (shorter drain on paper, but twice the per-pass overhead instructions: 41.5 ms), one polling warp per epilogue team
 // and per encoder group with the others blocked on a named barrier (bar.sync costs no issue slots; no gain: 38.4 / 23.5
-// ms - the spinning warps take slots nobody else wanted, the limit is the latency of the dependent chains).
+// ms - the spinning warps take slots nobody else wanted, the limit is the latency of the dependent chains), and
+// HALF passes: every layer as two N = 64 passes into five rotating 64-column accumulators (192 + 320 = 512 columns: five
+// half passes between two uses of an accumulator instead of two full ones).  Built and run: 50.3 / 29.6 ms - a TMEM-A
+// tcgen05.mma costs ~65-75 cycles whether N is 64 or 128 (the 128 x 16 A operand is read per instruction), so halving N
+// doubles the tensor time.
 #include <cstdio>
 #include <cstdlib>
 #include <type_traits>

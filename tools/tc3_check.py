@@ -10,7 +10,7 @@ from oracle import nerf_oracle as O
 
 TRACE = None
 if os.environ.get("TC3_TRACE"):
-    TRACE = torch.zeros(32 * 256, dtype=torch.int32).pin_memory()
+    TRACE = torch.zeros(32 * 512, dtype=torch.int32).pin_memory()
     os.environ["DEXNERF_TC3_TRACE"] = str(TRACE.data_ptr())
 n, S = int(sys.argv[1]) if len(sys.argv) > 1 else 50, int(sys.argv[2]) if len(sys.argv) > 2 else 128
 torch.manual_seed(0)
@@ -30,10 +30,15 @@ for name, model in (("8x128", nerf.FlexibleNeRFModel(8, 128, 3, 10, 4)), ("4x128
     except Exception as exc:
         print("FAULT:", str(exc).splitlines()[0])
         if TRACE is not None:
-            for role in range(24):
-                r = TRACE[role * 256:(role + 1) * 256].tolist()
-                if r[0]:
-                    print("role %2d:" % role, " ".join("%d:%d.%d" % (v >> 16, (v & 0xFFFF) >> 4, v & 15) for v in r[1:1 + r[0]]))
+            t = TRACE.view(-1, 512)
+            for role in range(t.shape[0]):
+                n = int(t[role, 0])
+                if n:      # pairs of (code << 16 | pass - window start, clock)
+                    ws = [int(t[role, 1 + 2 * i]) & 0xFFFFFFFF for i in range(min(n, 250))]
+                    line = "role %2d: " % role + " ".join("%d@%d" % (w >> 16, w & 0xFFFF) for w in ws)
+                    print(line)
+                    with open(os.environ.get("TC3_TRACE_FILE", "/tmp/tc3_trace.txt"), "a") as f:
+                        f.write(line + "\n")
         os._exit(1)
     pts = (ro[:, None] + rd[:, None] * z[..., None]).reshape(-1, 3).cpu()
     x = O.positional_encoding(pts, 10)
