@@ -102,10 +102,24 @@ class SharedFrame:
             self._own, base, handle = ptr.value, ptr.value, [h.raw]
         dist.broadcast_object_list(handle, src=dist.get_global_rank(group, self.root) if group is not None else self.root,
                                    group=group)
+        opened = True
         if self.rank != self.root:
             q = C.c_void_p()
-            L.check(lib.dexnerf_p2p_open(C.create_string_buffer(handle[0], 64), C.byref(q)), "p2p_open")
-            self._mapped, base = q.value, q.value
+            if lib.dexnerf_p2p_open(C.create_string_buffer(handle[0], 64), C.byref(q)) == 0:
+                self._mapped, base = q.value, q.value
+            else:
+                opened = False
+        everyone = [None] * self.world            # all ranks succeed or all give up (nobody may wait alone later)
+        dist.all_gather_object(everyone, opened, group=group)
+        if not all(everyone):
+            if self._mapped:
+                lib.dexnerf_p2p_close(self._mapped)
+            dist.barrier(group=group)
+            if self._own:
+                lib.dexnerf_p2p_free(self._own)
+            self._own = self._mapped = None
+            raise L.DexNerfError("SharedFrame: a rank could not map the root's frame (CUDA IPC): "
+                                 + lib.dexnerf_last_error().decode())
         flat = torch.as_tensor(_DeviceMemory(base, self.numel), device=self.device)
         self.rgb = flat[:3 * hw].view(self.H, self.W, 3)
         self.depth = flat[3 * hw:4 * hw].view(self.H, self.W)
