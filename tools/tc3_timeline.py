@@ -44,7 +44,7 @@ print("producer (per layer: chunk c -> [slot wait begins, slot free = load issue
 for l in range(nl):
     d = ev.get((l * 3, 0), {})
     print("  layer %2d: " % l + "  ".join("c%d %s -> %s" % (c, ("%6d" % rel(d[2 * c])) if 2 * c in d else "-", ("%6d" % rel(d[2 * c + 1])) if 2 * c + 1 in d else "-") for c in range(3) if 2 * c in d))
-print("pass layer tile acc | issuer of the tile: at the pass -> weights / enc ok -> gate open -> its turn -> issued | epilogue team: first warp sees D .. last warp done (last arithmetic end)")
+print("pass layer tile acc | issuer of the tile: at the pass -> weights / enc ok -> its turn -> gate open -> issued | epilogue team: first warp sees D .. last warp done (last arithmetic end)")
 prev_issue = None
 for k in range(nl * 3):
     iss = ev.get((k, 1 + k % 3), {})
