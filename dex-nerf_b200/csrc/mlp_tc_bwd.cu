@@ -517,6 +517,14 @@ struct WSmemT {
   static constexpr int total = tmem_ptr + 16;
 };
 using WSmem = WSmemT<kWStages, kWStageA, kWStageG>;
+// The stand-alone weight-gradient GEMM packs its ring per item: a stage is as large as the item's operands
+// (n_mblk x 16 KB of A + g_fg KB of G) and the 192 KB hold as many stages as fit, up to 8.  An item with small
+// operands (the heads: 18 KB per stage; the direction encoding: 32 KB) is otherwise bound by the latency of three
+// small copies in flight, and the kernel ends with its slowest CTA.
+constexpr int kWPackedStages = 8;
+constexpr int kWRingBytes = kWStages * (kWStageA + kWStageG);
+using WSmemPacked = WSmemT<kWPackedStages, kWRingBytes / kWPackedStages / 2, kWRingBytes / kWPackedStages / 2>;
+static_assert(WSmemPacked::bars == kWRingBytes, "the packed ring is the same 192 KB");
 // the weight-gradient GEMM when it shares the SM with the chain: ONE M block per item (256 TMEM columns), so a stage
 // is 16 KB of A (16 feature groups x 64 samples) + 32 KB of G, two stages
 constexpr int kWStagesShared = 2;
@@ -541,10 +549,11 @@ __device__ __forceinline__ void discard_l2(const uint8_t* p) {
 // idle).  kWarp0 > 0 (shared-SM kernel): our 8 warps start at warp kWarp0, the TMEM allocation belongs to the chain
 // group (*shared_tmem holds its base) and we use the columns from kCol0 on; the other warps of the CTA only meet us
 // at the two CTA-wide barriers.
-template <bool kFused, int kWarp0, int kCol0, typename WS, int kStages, int kStageA>
+// kPacked: the ring geometry follows the item (WSmemPacked above); otherwise kStages stages of kStageA + kWStageG bytes.
+template <bool kFused, int kWarp0, int kCol0, typename WS, int kStages, int kStageA, bool kPacked = false>
 __device__ __forceinline__ void dw_body(const DwParams& P, uint8_t* smem, const int cta, const uint8_t* shared_tmem) {
   using WSmem = WS;
-  constexpr int kWStages = kStages;
+  constexpr int kWStages = kStages;        // (kPacked: the maximum)
   constexpr int kWStageA = kStageA;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bars = sbase + WSmem::bars;
@@ -568,7 +577,16 @@ __device__ __forceinline__ void dw_body(const DwParams& P, uint8_t* smem, const 
   const int64_t n_my_tiles = (has_item && tile_end > tile_begin) ? (tile_end - tile_begin + tile_step - 1) / tile_step : 0;
   const int64_t n_stage_total = n_my_tiles * 2;     // half-tiles
   const uint32_t a_bytes = (uint32_t)I.a_fgs * 1024u, g_bytes = (uint32_t)I.g_fg * 1024u;
+  // ring geometry: stage st holds A at a_base + st * a_stride and G at g_base + st * g_stride
+  const uint32_t a_slot = (uint32_t)I.n_mblk * 16384u;
+  const uint32_t packed_stage = a_slot + g_bytes;
+  int n_st = kWStages;
+  if (kPacked) { n_st = (int)((uint32_t)kWRingBytes / packed_stage); n_st = n_st > kWStages ? kWStages : n_st; }
+  const uint32_t a_stride = kPacked ? packed_stage : (uint32_t)kWStageA, g_stride = kPacked ? packed_stage : (uint32_t)kWStageG;
+  const uint32_t a_base = sbase + WSmem::a, g_base = kPacked ? a_base + a_slot : sbase + WSmem::g;
+  constexpr int kZeroBytes = kPacked ? kWRingBytes : kWStages * kWStageA;
 
+  const long long t_body = (P.variant & 128) ? clock64() : 0;
   if (tid == 0) {
     for (int s = 0; s < kWStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1 + 128); }
     mbar_init(acc_bar, 1);
@@ -579,7 +597,7 @@ __device__ __forceinline__ void dw_body(const DwParams& P, uint8_t* smem, const 
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   // the MMA reads 16 feature groups per M block even when the image has fewer: keep the tail finite
-  for (int i = tid; i < kWStages * kWStageA / 16; i += n_group)
+  for (int i = tid; i < kZeroBytes / 16; i += n_group)
     reinterpret_cast<uint4*>(smem + WSmem::a)[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async();
   tc_fence_before();
@@ -609,9 +627,9 @@ __device__ __forceinline__ void dw_body(const DwParams& P, uint8_t* smem, const 
     if (kFused && n_stage_total > 0) acquire_tile(0);
     // fused: kWStages extra rounds drain the ring so that the last images are discarded too
 #pragma unroll 1
+    int st = 0;
+    uint32_t ph = 0;
     for (int64_t s = 0; s < n_stage_total + (kFused ? kWStages : 0); ++s) {
-      const int st = (int)(s % kWStages);
-      const uint32_t ph = (uint32_t)((s / kWStages) & 1);
       long long c0 = prof ? clock64() : 0;
       mbar_wait(empty(st), ph ^ 1, 20);
       if (prof) { t_empty += clock64() - c0; c0 = clock64(); }
@@ -621,8 +639,8 @@ __device__ __forceinline__ void dw_body(const DwParams& P, uint8_t* smem, const 
         const uint8_t* a_src = P.tape + I.a_off + tile * (int64_t)(I.a_fg * 2048) + (int64_t)half * (I.a_fg * 1024) +
                                (int64_t)I.a_fg0 * 1024;
         mbar_arrive_expect_tx(full(st), a_bytes + g_bytes);
-        bulk_g2s(sbase + WSmem::a + st * kWStageA, a_src, a_bytes, full(st));
-        bulk_g2s(sbase + WSmem::g + st * kWStageG, g_image(s), g_bytes, full(st));
+        bulk_g2s(a_base + st * a_stride, a_src, a_bytes, full(st));
+        bulk_g2s(g_base + st * g_stride, g_image(s), g_bytes, full(st));
       }
       __syncwarp();
       if (kFused && s >= kWStages) {
@@ -633,6 +651,7 @@ __device__ __forceinline__ void dw_body(const DwParams& P, uint8_t* smem, const 
       if (prof) { t_disc += clock64() - c0; c0 = clock64(); }
       if (kFused && (s & 1) == 1 && s + 1 < n_stage_total) acquire_tile(s + 1);
       if (prof) t_flag += clock64() - c0;
+      if (++st == n_st) { st = 0; ph ^= 1u; }
     }
     if (prof && lane == 0 && (cta % 37) == 0)
       printf("dw producer cta %d item %d (%d ctas, mblk %d, gfg %d): stages %lld total %lld cyc | wait-empty %lld issue+discard %lld wait-flag %lld\n",
@@ -652,15 +671,15 @@ __device__ __forceinline__ void dw_body(const DwParams& P, uint8_t* smem, const 
     const bool prof = (P.variant & 128) != 0;
     long long t_full = 0;
 #pragma unroll 1
+    int st = 0;
+    uint32_t ph = 0;
     for (int64_t s = 0; s < n_stage_total; ++s) {
-      const int st = (int)(s % kWStages);
-      const uint32_t ph = (uint32_t)((s / kWStages) & 1);
       const long long c0 = prof ? clock64() : 0;
       mbar_wait(full(st), ph, 21);
       if (prof) t_full += clock64() - c0;
       tc_fence_after();
-      const uint32_t a_lo = (((sbase + WSmem::a + st * kWStageA) >> 4) & 0x3FFF) | (lbo << 16);
-      const uint32_t g_lo = (((sbase + WSmem::g + st * kWStageG) >> 4) & 0x3FFF) | (lbo << 16);
+      const uint32_t a_lo = (((a_base + st * a_stride) >> 4) & 0x3FFF) | (lbo << 16);
+      const uint32_t g_lo = (((g_base + st * g_stride) >> 4) & 0x3FFF) | (lbo << 16);
       if (leader) {
 #pragma unroll
         for (int ks = 0; ks < ((P.variant & 4) ? 0 : 4); ++ks) {        // 64 samples = 4 x K16; a K step = 2 core matrices = 256 B
@@ -672,26 +691,30 @@ __device__ __forceinline__ void dw_body(const DwParams& P, uint8_t* smem, const 
         tc_commit(empty(st));
       }
       __syncwarp();
+      if (++st == n_st) { st = 0; ph ^= 1u; }
     }
     if (leader) tc_commit(acc_bar);
     __syncwarp();
     if (prof && lane == 0 && (cta % 37) == 0) printf("dw issuer   cta %d: wait-full %lld cyc\n", cta, t_full);
   } else if (warp >= 4 && warp < 8) {
     // =============================== bias column sums + final reduction ===============================
-    // thread j owns feature group j / 4 of G (8 features) and every 4th sample of the half-tile:
-    // one 16-byte shared-memory load per sample row, rows rotated by the feature group so that the
-    // four wavefronts of a warp load are conflict free; the four sample phases meet in a shuffle at
-    // the very end
+    // Column sums on the legacy tensor path: ones[16 x 16] x G[16 samples x 8 features] with mma.sync m16n8k16 gives,
+    // in every row of the result, the sum over the 16 samples - four of them per feature group and 64-sample stage,
+    // the B fragments straight from the image with ldmatrix.trans (a row of the image = one sample's 8 features =
+    // 16 bytes).  Warp w owns the feature groups [8 w, 8 w + 8): 16 LDSM + 32 HMMA per stage instead of the ~270
+    // load / unpack / add instructions per thread the CUDA-core form took (it held the stage's slot longer than the MMAs
+    // did and cost the kernel 8 %).
     const int j = tid - 128;                    // 0..127
     __shared__ uint32_t s_last;
     const bool has_bias = I.b_out >= 0;
-    const int fg = j >> 2, sub = j & 3;
-    const bool mine = has_bias && fg < I.g_fg;
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int bw = warp - 4;                    // 0..3
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    int st = 0;
+    uint32_t ph = 0;
 #pragma unroll 1
     for (int64_t s = 0; s < n_stage_total; ++s) {
-      const int st = (int)(s % kWStages);
-      const uint32_t ph = (uint32_t)((s / kWStages) & 1);
       mbar_wait(full(st), ph, 22);
       if (kFused && !(P.variant & 8)) {
         // The half image is in shared memory now; its global copy is dead once every item that reads it has its own.
@@ -713,32 +736,42 @@ __device__ __forceinline__ void dw_body(const DwParams& P, uint8_t* smem, const 
           for (uint32_t off = (uint32_t)j * 128u; off < g_bytes; off += 128u * 128u) discard_l2(g + off);
         }
       }
-      if (mine && !(P.variant & 2)) {
-        const uint32_t gs = sbase + WSmem::g + st * kWStageG + fg * 1024;
-#pragma unroll 4
-        for (int r = 0; r < 16; ++r) {
-          const uint32_t row = (uint32_t)(4 * r + sub + fg) & 63u;
-          uint32_t v0, v1, v2, v3;
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(gs + row * 16));
-          acc[0] += __uint_as_float(v0 << 16); acc[1] += __uint_as_float(v0 & 0xFFFF0000u);
-          acc[2] += __uint_as_float(v1 << 16); acc[3] += __uint_as_float(v1 & 0xFFFF0000u);
-          acc[4] += __uint_as_float(v2 << 16); acc[5] += __uint_as_float(v2 & 0xFFFF0000u);
-          acc[6] += __uint_as_float(v3 << 16); acc[7] += __uint_as_float(v3 & 0xFFFF0000u);
+      if (has_bias && !(P.variant & 2)) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int fg = bw * 8 + i;
+          if (fg < I.g_fg) {                       // warp-uniform
+            const uint32_t gs = g_base + st * g_stride + fg * 1024 + (uint32_t)lane * 16;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {  // samples [32 half, 32 half + 32): two K steps of 16
+              uint32_t b0, b1, b2, b3;
+              asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(gs + (uint32_t)half * 512));
+              const uint32_t one2 = 0x3F803F80u;    // (1.0, 1.0) in bf16
+              asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %4, %4, %4}, {%5, %6}, "
+                           "{%0, %1, %2, %3};"
+                           : "+f"(acc[i][0]), "+f"(acc[i][1]), "+f"(acc[i][2]), "+f"(acc[i][3]) : "r"(one2), "r"(b0), "r"(b1));
+              asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %4, %4, %4}, {%5, %6}, "
+                           "{%0, %1, %2, %3};"
+                           : "+f"(acc[i][0]), "+f"(acc[i][1]), "+f"(acc[i][2]), "+f"(acc[i][3]) : "r"(one2), "r"(b2), "r"(b3));
+            }
+          }
         }
       }
       mbar_arrive(empty(st));
+      if (++st == n_st) { st = 0; ph ^= 1u; }
     }
-    if (has_bias) {                              // warp-uniform: all lanes take part in the shuffles
+    const long long t_loop_end = (P.variant & 128) ? clock64() : 0;
+    if (has_bias && lane < 4) {                  // row 0 of the result: lanes 0..3 hold features 2 lane, 2 lane + 1
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 1);
-        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 2);
-      }
-      if (mine && sub == 0) {
+        const int fg = bw * 8 + i;
+        if (fg < I.g_fg) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int cc = fg * 8 + i - I.col0;
-          if (cc >= 0 && cc < I.n_cols) red_add_f32(P.grads + I.b_out + cc, acc[i]);
+          for (int c = 0; c < 2; ++c) {
+            const int cc = fg * 8 + lane * 2 + c - I.col0;
+            if (cc >= 0 && cc < I.n_cols) red_add_f32(P.grads + I.b_out + cc, acc[i][c]);
+          }
         }
       }
     }
@@ -771,10 +804,16 @@ __device__ __forceinline__ void dw_body(const DwParams& P, uint8_t* smem, const 
         }
       }
     }
+    if ((P.variant & 128) && tid == 128 && (cta % 37) == 0)
+      printf("dw cta %d: start -> stream loop done %lld cyc, column sums + accumulator reduction %lld cyc\n", cta,
+             t_loop_end - t_body, clock64() - t_loop_end);
   }
 
   tc_fence_before();
   cta_sync();
+  if ((P.variant & 128) && tid == 128)
+    printf("dw cta %3d item %2d (%2d ctas, A %2d fg, G %2d fg): %5lld stages, body %lld cyc\n", cta, it, I.n_cta, I.a_fgs, I.g_fg,
+           (long long)n_stage_total, clock64() - t_body);
   if (kWarp0 == 0 && warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
@@ -783,7 +822,7 @@ __device__ __forceinline__ void dw_body(const DwParams& P, uint8_t* smem, const 
 __global__ void __launch_bounds__(kWThreads, 1) mlp_tc_bwd_dw_kernel(const __grid_constant__ DwParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  dw_body<false, 0, 0, WSmem, kWStages, kWStageA>(P, smem, (int)blockIdx.x, nullptr);
+  dw_body<false, 0, 0, WSmemPacked, kWPackedStages, kWStageA, true>(P, smem, (int)blockIdx.x, nullptr);
 }
 
 // The training path: chain CTAs [0, n_chain) and weight-gradient CTAs [n_chain, gridDim.x) in ONE launch
@@ -1071,7 +1110,7 @@ extern "C" DEXNERF_API int dexnerf_tc_backward(const dexnerf_flexible_spec* spec
       DN_CHECK_LAUNCH("mlp_tc_bwd_fused");
       return 0;
     }
-    const size_t smem = WSmem::total + 1024;
+    const size_t smem = WSmemPacked::total + 1024;
     DN_CUDA(cudaFuncSetAttribute(mlp_tc_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     mlp_tc_bwd_dw_kernel<<<cta, kWThreads, smem, st>>>(W);
     DN_CHECK_LAUNCH("mlp_tc_bwd_dw");

@@ -36,6 +36,53 @@ __global__ void __launch_bounds__(128, 1) tma_stream(const uint8_t* src, size_t 
   }
 }
 
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+
+// The weight-gradient GEMM's ring without the GEMM: a producer warp, `n_cons` consumer warps that wait for a stage and
+// hand the slot back (full -> consumer -> empty -> producer: two polling hops per slot instead of the one above), two
+// source streams per stage (A and G images, `chunk` bytes each).
+__global__ void __launch_bounds__(256, 1) tma_ring(const uint8_t* src, size_t bytes_per_cta, int chunk, int stages, int n_cons,
+                                                   int two_streams) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bars[32];
+  const uint32_t sb = smem_u32(smem), bb = smem_u32(bars);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(bb + 8 * s, 1); mbar_init(bb + 128 + 8 * s, n_cons * 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const size_t per_stage = two_streams ? 2 * (size_t)chunk : (size_t)chunk;
+  const size_t n = bytes_per_cta / per_stage;
+  const uint8_t* p = src + (size_t)blockIdx.x * bytes_per_cta;
+  const uint8_t* q = p + bytes_per_cta / 2;
+  if (warp == 0) {
+    for (size_t i = 0; i < n; ++i) {
+      const int st = (int)(i % stages);
+      const uint32_t ph = (uint32_t)((i / stages) & 1);
+      mbar_wait(bb + 128 + 8 * st, ph ^ 1);
+      if (lane == 0) {
+        mbar_expect(bb + 8 * st, (uint32_t)per_stage);
+        if (two_streams) {
+          bulk_g2s(sb + st * 2 * chunk, p + i * chunk, chunk, bb + 8 * st);
+          bulk_g2s(sb + st * 2 * chunk + chunk, q + i * chunk, chunk, bb + 8 * st);
+        } else {
+          bulk_g2s(sb + st * chunk, p + i * chunk, chunk, bb + 8 * st);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp <= n_cons) {
+    for (size_t i = 0; i < n; ++i) {
+      const int st = (int)(i % stages);
+      const uint32_t ph = (uint32_t)((i / stages) & 1);
+      mbar_wait(bb + 8 * st, ph);
+      mbar_arrive(bb + 128 + 8 * st);
+    }
+  }
+}
+
 // each thread keeps `kDepth` 16-byte loads in flight; results are stored to shared memory (like a real loader)
 template <int kDepth>
 __global__ void __launch_bounds__(1024, 1) ldg_stream(const uint4* src, size_t vec_per_cta, uint32_t* sink) {
@@ -53,10 +100,20 @@ __global__ void __launch_bounds__(1024, 1) ldg_stream(const uint4* src, size_t v
   if (acc == 0x12345678u) sink[0] = acc;
 }
 
+__global__ void fill_random(uint4* p, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t h = (uint32_t)i * 2654435761u ^ (uint32_t)(i >> 32);
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    p[i] = make_uint4(h, h * 3266489917u, h ^ 0x9E3779B9u, h * 668265263u);
+  }
+}
+
 int main() {
   const size_t total = (size_t)8 << 30;
   uint8_t* buf; uint32_t* sink;
   cudaMalloc(&buf, total); cudaMalloc(&sink, 4); cudaMemset(buf, 1, total);
+  fill_random<<<148 * 8, 256>>>((uint4*)buf, total / 16);   // (constant data would flatter the memory system)
+  cudaDeviceSynchronize();
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   const int ctas[] = {1, 8, 37, 74, 111, 148};
   printf("%-34s", "path");
@@ -80,6 +137,11 @@ int main() {
   report("TMA bulk 32 KB x 6 stages", [&](int c, size_t per) { tma_stream<<<c, 128, 192 * 1024 + 1024>>>(buf, per, 32768, 6); });
   report("TMA bulk 16 KB x 12 stages", [&](int c, size_t per) { tma_stream<<<c, 128, 192 * 1024 + 1024>>>(buf, per, 16384, 12); });
   report("TMA bulk 4 KB x 48 stages (16 bars)", [&](int c, size_t per) { tma_stream<<<c, 128, 64 * 1024 + 1024>>>(buf, per, 4096, 16); });
+  cudaFuncSetAttribute(tma_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  report("ring 64 KB x 3, 1 consumer warp", [&](int c, size_t per) { tma_ring<<<c, 256, 192 * 1024 + 1024>>>(buf, per, 65536, 3, 1, 0); });
+  report("ring 64 KB x 3, 5 consumer warps", [&](int c, size_t per) { tma_ring<<<c, 256, 192 * 1024 + 1024>>>(buf, per, 65536, 3, 5, 0); });
+  report("ring (32+32) KB x 3, 5 cons. warps", [&](int c, size_t per) { tma_ring<<<c, 256, 192 * 1024 + 1024>>>(buf, per, 32768, 3, 5, 1); });
+  report("ring (16+16) KB x 6, 5 cons. warps", [&](int c, size_t per) { tma_ring<<<c, 256, 192 * 1024 + 1024>>>(buf, per, 16384, 6, 5, 1); });
   cudaFuncSetAttribute(ldg_stream<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   cudaFuncSetAttribute(ldg_stream<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   cudaFuncSetAttribute(ldg_stream<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
