@@ -16,6 +16,7 @@ oracle/make_ref.py and shipped to the GPU box; the oracle port only if that copy
 bounded sample of the same workload.
 """
 import argparse
+import datetime
 import json
 import os
 import statistics
@@ -139,22 +140,24 @@ def state_dicts():
 
 
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    QUERY = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.proc, self.idx = None, gpu_index
+    def __init__(self, gpu_index, period_ms=100):
+        self.proc, self.idx, self.period_ms = None, gpu_index, period_ms
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, window=None):
+        """window = (t0, t1) in time.time() seconds: keep only the samples taken inside it (the sampler may have been
+        started earlier so that its start-up is not inside the timed region)."""
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         self.proc.terminate()
@@ -169,6 +172,13 @@ class ClockSampler:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
+            if window is not None:
+                try:
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                except ValueError:
+                    continue
+                if ts < window[0] - 0.05 or ts > window[1] + 0.05:
+                    continue
             try:
                 sm.append(float(f[1])); smax.append(float(f[2]))
             except ValueError:
@@ -344,26 +354,36 @@ def run_train(args, dist, rank, world, dev, quiet=False):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt.item())
 
+    # The clock sampler (an nvidia-smi process) starts BEFORE the warm-up and gets 0.4 s to initialise: forking it and
+    # its NVML start-up inside a ~100 ms timed region of 4 ms steps would cost the launching thread more than a step.
+    sampler = ClockSampler(dev.index or 0, period_ms=int(os.environ.get("DEXNERF_BENCH_SMI_MS", "25")))
+    if rank == 0 and sampler.period_ms > 0:
+        sampler.start()
+    time.sleep(0.4)
     for i in range(max(args.warmup, 3)):
         step(sel_dev[i % n_batches], tgt_dev[i % n_batches])
-    sampler = ClockSampler(dev.index or 0)
     barrier()
-    if rank == 0:
-        sampler.start()
-    TR.event_log = []
     from nerf import render as RD
-    if api == "trainer":
-        trainer.timing = (RD.Events(), RD.Events())      # per-launch events recorded by the library (last step is read)
     launches0 = L.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
     e0.record()
     for i in range(args.steps):
         step(sel_dev[i % n_batches], tgt_dev[i % n_batches])
     e1.record()
     barrier()
+    t_wall1 = time.time()
     launches = L.launch_count - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop((t_wall0, t_wall1)) if rank == 0 else None
     ms_dev = reduce_max(e0.elapsed_time(e1) / args.steps)
+    # per-kernel times: events recorded by the library around every launch - in steps of their own AFTER the timed
+    # region (the ~40 event records per step cost launch gaps, they do not belong in `value`)
+    TR.event_log = []
+    if api == "trainer":
+        trainer.timing = (RD.Events(), RD.Events())
+    for i in range(2):
+        step(sel_dev[i % n_batches], tgt_dev[i % n_batches])
+    torch.cuda.synchronize(dev)
     log, TR.event_log = TR.event_log, None
     parts = {}
     for name, a, b, n, S in log:
