@@ -158,8 +158,8 @@ __device__ __forceinline__ void bwd_epilogue_pass(uint32_t d_tmem, uint32_t a_pa
         x2 = fmaf(dsig, w4.z, x2); x3 = fmaf(dsig, w4.w, x3);
       }
       if (use_mask) {
-        x0 = (bits >> i) & 1u ? x0 : 0.0f;       x1 = (bits >> (i + 1)) & 1u ? x1 : 0.0f;
-        x2 = (bits >> (i + 2)) & 1u ? x2 : 0.0f; x3 = (bits >> (i + 3)) & 1u ? x3 : 0.0f;
+        x0 = (bits >> relu_bit_pos(i)) & 1u ? x0 : 0.0f;     x1 = (bits >> relu_bit_pos(i + 1)) & 1u ? x1 : 0.0f;
+        x2 = (bits >> relu_bit_pos(i + 2)) & 1u ? x2 : 0.0f; x3 = (bits >> relu_bit_pos(i + 3)) & 1u ? x3 : 0.0f;
       }
       if (kHold) {
         held[c * 8 + i / 2] = pack_bf16(x0, x1, false);
@@ -353,8 +353,8 @@ __device__ __forceinline__ void chain_body(const BwdParams& P, uint8_t* smem, co
             const int k = c * 16 + i;
             float x0 = fmaf(d.x, wr[k], fmaf(d.y, wr[hw + k], d.z * wr[2 * hw + k]));
             float x1 = fmaf(d.x, wr[k + 1], fmaf(d.y, wr[hw + k + 1], d.z * wr[2 * hw + k + 1]));
-            x0 = (bits >> i) & 1u ? x0 : 0.0f;
-            x1 = (bits >> (i + 1)) & 1u ? x1 : 0.0f;
+            x0 = (bits >> relu_bit_pos(i)) & 1u ? x0 : 0.0f;
+            x1 = (bits >> relu_bit_pos(i + 1)) & 1u ? x1 : 0.0f;
             pk[i / 2] = pack_bf16(x0, x1, false);
           }
           tmem_st8(a_tmem + (uint32_t)(col0 / 2 + c * 8), pk);
@@ -626,9 +626,9 @@ __device__ __forceinline__ void dw_body(const DwParams& P, uint8_t* smem, const 
     long long t_empty = 0, t_flag = 0, t_disc = 0, t_all = prof ? clock64() : 0;
     if (kFused && n_stage_total > 0) acquire_tile(0);
     // fused: kWStages extra rounds drain the ring so that the last images are discarded too
-#pragma unroll 1
     int st = 0;
     uint32_t ph = 0;
+#pragma unroll 1
     for (int64_t s = 0; s < n_stage_total + (kFused ? kWStages : 0); ++s) {
       long long c0 = prof ? clock64() : 0;
       mbar_wait(empty(st), ph ^ 1, 20);
@@ -670,9 +670,9 @@ __device__ __forceinline__ void dw_body(const DwParams& P, uint8_t* smem, const 
     const uint64_t desc_hi = ((uint64_t)sbo << 32) | (1ull << 46);
     const bool prof = (P.variant & 128) != 0;
     long long t_full = 0;
-#pragma unroll 1
     int st = 0;
     uint32_t ph = 0;
+#pragma unroll 1
     for (int64_t s = 0; s < n_stage_total; ++s) {
       const long long c0 = prof ? clock64() : 0;
       mbar_wait(full(st), ph, 21);

@@ -93,17 +93,10 @@ __device__ __forceinline__ void encode_row_std(const float (&x)[3], int dim, boo
   }
 }
 
-// ReLU bits of eight packed bf16 pairs (values are >= +0 after cvt.relu): bit 2i / 2i+1 = lo / hi
-__device__ __forceinline__ uint32_t relu_bits16(const uint32_t* w) {
-  uint32_t m = 0;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    m |= ((w[i] & 0x7FFFu) ? 1u : 0u) << (2 * i);
-    m |= ((w[i] & 0x7FFF0000u) ? 1u : 0u) << (2 * i + 1);
-  }
-  return m;
-}
 __device__ __forceinline__ void stg128(uint8_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+#ifdef DEXNERF_EXP_NO_TAPE_STG      // experiment (tools/README.md): the forward kernel with tape minus its activation stores
+  if (a == 0x12345678u && b == 0x9ABCDEF0u)
+#endif
   *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d);
 }
 

@@ -158,7 +158,11 @@ def test_forward_tape(hidden, layers, skip, Lx):
             slots = 2 * ((width + 127) // 128)      # two 64-column (or narrower) blocks per 128-wide pass
             words = tape[lay["mask"][l]: lay["mask"][l] + nt * slots * 1024].view(torch.int64).view(nt, slots, 128)
             cols = width // slots
-            bits = ((words[..., None] >> torch.arange(cols, device="cuda")) & 1).bool()    # tile, slot, row, col
+            # column f of a 64-column slot: 32-bit word f >> 5, 16-bit slice (f >> 4) & 1, and inside the slice the
+            # even columns at bits 7..0, the odd ones at bits 15..8 (relu_bit_pos in csrc/mlp_tc_shared.cuh)
+            f = torch.arange(cols, device="cuda")
+            pos = (f >> 4) * 16 + (f & 1) * 8 + 7 - ((f & 15) >> 1)
+            bits = ((words[..., None] >> pos) & 1).bool()    # tile, slot, row, col
             bits = bits.permute(0, 2, 1, 3).reshape(nt * 128, width)[:M]
             assert torch.equal(bits, img > 0), l
 

@@ -1,6 +1,8 @@
 """Per-source-line executed-instruction table from an .ncu-rep captured with --import-source on.
 
-    python tools/ncu_lines.py report.ncu-rep kernel-regex units [top]
+    python tools/ncu_lines.py report.ncu-rep kernel-regex units [top] [samples]
+
+A fifth argument `samples` sorts by stall samples instead of executed instructions.
 
 `units` = the number of work units (rays) the launch processed, so the table reads "warp
 instructions per ray"."""
@@ -10,6 +12,7 @@ import sys
 
 rep, kern, units = sys.argv[1], sys.argv[2], float(sys.argv[3])
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+by_samples = len(sys.argv) > 5 and sys.argv[5] == "samples"
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass",
                       "--kernel-name", "regex:" + kern], capture_output=True, text=True).stdout
 agg, stall, cur, hdr = {}, {}, None, None
@@ -34,5 +37,5 @@ for r in csv.reader(out.splitlines()):
     stall[key] = stall.get(key, 0) + sm
 tot, stot = sum(agg.values()), max(1, sum(stall.values()))
 print("total warp instructions %d = %.1f per unit" % (tot, tot / units))
-for k, v in sorted(agg.items(), key=lambda kv: -kv[1])[:top]:
+for k, v in sorted(agg.items(), key=lambda kv: -(stall[kv[0]] if by_samples else kv[1]))[:top]:
     print("%7.1f  %4.1f%% samples  %s:%d  %s" % (v / units, 100.0 * stall[k] / stot, k[0], k[1], k[2]))
