@@ -921,6 +921,9 @@ extern "C" DEXNERF_API int dexnerf_tc_tape_layout(const dexnerf_flexible_spec* s
 }
 
 // what: bit 0 = run the dX chain, bit 1 = run the weight-gradient GEMM (both for a training step)
+// variant: bits 0-7 bring-up switches of the GEMM, bits 8-15 the number of SMs the GEMM may use (0 = all; in the
+// single-launch kernels the chain's share / the throttle window), bits 16-23 the number of SMs of the chain (0 = all) -
+// the training driver runs the fine network's GEMM and the coarse network's chain side by side with them.
 extern "C" DEXNERF_API int dexnerf_tc_backward(const dexnerf_flexible_spec* spec, const dexnerf_mlp_program* prog,
                                                const void* packed, const void* packed_t, void* tape,
                                                const float* d_rf, int64_t n, int S, float* grads, int what,
@@ -962,7 +965,9 @@ extern "C" DEXNERF_API int dexnerf_tc_backward(const dexnerf_flexible_spec* spec
     P.ready = fused ? reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(tape) + T.flags) : nullptr;
   }
   if (what & 1) {
-    const int grid = (int)(n_pairs < kNumSMs ? n_pairs : kNumSMs);
+    int sms = (variant >> 16) & 0xFF;
+    if (sms <= 0 || sms > kNumSMs) sms = kNumSMs;
+    const int grid = (int)(n_pairs < sms ? n_pairs : sms);
     const size_t smem = BSmem::total + 1024;
     auto launch = [&](auto kernel) -> int {
       DN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1047,13 +1052,13 @@ extern "C" DEXNERF_API int dexnerf_tc_backward(const dexnerf_flexible_spec* spec
       for (int j = 0; j < nl - 1; ++j) chain_cost += (double)(H / 128) * ((j == 0 ? H / 2 : H) / 64) * 4 * 64 + 150.0 * (H / 128);
       for (int i = 0; i < W.n_items; ++i) dw_cost += cost[i];
       n_chain = (int)(kNumSMs * chain_cost / (chain_cost + dw_cost) + 0.5);
-      if ((variant >> 8) > 0) n_chain = variant >> 8;
+      if (((variant >> 8) & 0xFF) > 0) n_chain = (variant >> 8) & 0xFF;
       if (n_chain > kNumSMs - W.n_items) n_chain = kNumSMs - W.n_items;
       if (n_chain > n_pairs) n_chain = (int)n_pairs;
       if (n_chain < 1) n_chain = 1;
     }
     int64_t budget = kNumSMs - n_chain;      // (all SMs in the shared-SM kernel: n_chain stays 0 there)
-    if (!fused && (variant >> 8) > 0) budget = variant >> 8;      // experiment: the stand-alone GEMM on fewer SMs
+    if (!fused && ((variant >> 8) & 0xFF) > 0) budget = (variant >> 8) & 0xFF;      // the stand-alone GEMM on fewer SMs
     if (budget < W.n_items) budget = W.n_items;
     int share[kMaxDwItems];
     for (int i = 0; i < W.n_items; ++i) share[i] = 1;
@@ -1082,7 +1087,7 @@ extern "C" DEXNERF_API int dexnerf_tc_backward(const dexnerf_flexible_spec* spec
         W.consumed_total = reinterpret_cast<uint32_t*>(flags + T.flag_bytes - 128);
         P.consumed_total = W.consumed_total;
         P.throttle_items = W.n_items;
-        P.throttle_window = (variant >> 8) > 0 ? (variant >> 8) : kNumSMs + 24;
+        P.throttle_window = ((variant >> 8) & 0xFF) > 0 ? ((variant >> 8) & 0xFF) : kNumSMs + 24;
       }
       if (shared_sm) {
         using CS = BSmemT<kBSlotsShared, true>;

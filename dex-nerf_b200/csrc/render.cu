@@ -292,6 +292,35 @@ static int variant_override() {
   return v;
 }
 
+// The two networks' backwards are independent (the resampled depths carry no gradient, train_utils.py:166), and their
+// kernels look complementary: the weight-gradient GEMM reads (tensor pipe 24 % busy, nothing written), the
+// activation-gradient chain computes and writes.  With DEXNERF_BWD_SPLIT=k the driver runs the FINE network's GEMM on
+// 148 - k SMs and, on a second stream, the COARSE network's compositing backward + chain on the other k at the same
+// time; the coarse GEMM follows on all SMs.  Measured on a B200 (C4, ms per iteration): off 4.62, k = 32 4.69, 40 4.87,
+// 48 4.94, 56 4.94 - the GEMM slows down by as much as the chain takes (1.47 -> 1.71 ms at k = 32), because both are
+// bound by the same HBM (10.2 GB in that window = 6 TB/s of mixed traffic).  Hence OFF by default (k = 0).
+static int overlap_split() {
+  static const int v = [] {
+    const char* e = getenv("DEXNERF_BWD_SPLIT");
+    const int k = e ? atoi(e) : 0;
+    return (k < 0 || k > kNumSMs - 16) ? 0 : k;
+  }();
+  return v;
+}
+struct SideStream { cudaStream_t st = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+static SideStream* side_stream() {
+  static SideStream per_device[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideStream& s = per_device[dev];
+  if (!s.st) {
+    if (cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess) { s.st = nullptr; return nullptr; }
+    cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming);
+  }
+  return &s;
+}
+
 static int query(const dexnerf_model_ref& m, const Resolved& r, const float* z, int64_t n, int S, float* rf,
                  void* tape, cudaStream_t st) {
   DN_REQUIRE(m.prog, "render: model program is null");
@@ -416,6 +445,46 @@ extern "C" DEXNERF_API int dexnerf_render_fused_bwd(const dexnerf_render_params*
     return dexnerf_tc_backward(m.spec, m.prog, m.packed, m.packed_t, tape, d_rf_scratch, n, S, grads, backward_mode(),
                                variant_override(), stream);
   };
+  const int k = overlap_split();
+  SideStream* side = (which == 3 && backward_mode() == 3 && k > 0 && n * (int64_t)Nc >= (int64_t)k * 256) ? side_stream() : nullptr;
+  if (side) {
+    // main stream: compositing backward (fine), chain (fine), GEMM (fine, 148 - k SMs), [join], GEMM (coarse)
+    // side stream: [fork after the fine chain - it has read the shared d_rf scratch], compositing backward (coarse),
+    //              chain (coarse, k SMs)
+    DN_REQUIRE(g_rgb_fine && g_rgb_coarse && grads_fine && grads_coarse, "render_fused_bwd: null gradient pointer");
+    {
+      Bracket b(p->events, 0, st);
+      if (int rc = dexnerf_volume_render_backward(r.rf_f, r.z_f, r.rd, r.noise_f, n, Sf, p->white_background, g_rgb_fine,
+                                                  nullptr, nullptr, d_rf_scratch, stream)) return rc;
+    }
+    {
+      Bracket b(p->events, 1, st);
+      if (int rc = dexnerf_tc_backward(p->fine.spec, p->fine.prog, p->fine.packed, p->fine.packed_t, p->tape_fine,
+                                       d_rf_scratch, n, Sf, grads_fine, 1, 0, stream)) return rc;
+    }
+    DN_CUDA(cudaEventRecord(side->fork, st));
+    DN_CUDA(cudaStreamWaitEvent(side->st, side->fork, 0));
+    {
+      Bracket b(p->events, 2, st);
+      if (int rc = dexnerf_tc_backward(p->fine.spec, p->fine.prog, p->fine.packed, p->fine.packed_t, p->tape_fine,
+                                       d_rf_scratch, n, Sf, grads_fine, 2, (kNumSMs - k) << 8, stream)) return rc;
+    }
+    {
+      Bracket b(p->events, 3, side->st);
+      if (int rc = dexnerf_volume_render_backward(r.rf_c, r.z_c, r.rd, r.noise_c, n, Nc, p->white_background,
+                                                  g_rgb_coarse, nullptr, nullptr, d_rf_scratch, side->st)) return rc;
+    }
+    {
+      Bracket b(p->events, 4, side->st);
+      if (int rc = dexnerf_tc_backward(p->coarse.spec, p->coarse.prog, p->coarse.packed, p->coarse.packed_t,
+                                       p->tape_coarse, d_rf_scratch, n, Nc, grads_coarse, 1, k << 16, side->st)) return rc;
+    }
+    DN_CUDA(cudaEventRecord(side->join, side->st));
+    DN_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+    Bracket b(p->events, 5, st);
+    return dexnerf_tc_backward(p->coarse.spec, p->coarse.prog, p->coarse.packed, p->coarse.packed_t, p->tape_coarse,
+                               d_rf_scratch, n, Nc, grads_coarse, 2, 0, stream);
+  }
   if (which & 1)
     if (int rc = chain(p->fine, p->tape_fine, r.rf_f, r.z_f, r.noise_f, Sf, g_rgb_fine, grads_fine, 0)) return rc;
   if (which & 2)

@@ -614,10 +614,12 @@ class Trainer:
                                           L.ptr(g[0]), L.ptr(g[1]), L.ptr(self.loss), stream), "mse_loss_pair")
         p.events = ev[1].pointer() if ev else None
         gc, gf = self._flat(self.grads, 0), self._flat(self.grads, 1)
-        for which in (1, 2):
+        # Without a hook between the two networks ONE call runs both backwards, the coarse network's chain on a second
+        # stream next to the fine network's weight-gradient GEMM (render.cu: DEXNERF_BWD_SPLIT).
+        for which in ((3,) if after_fine is None else (1, 2)):
             L.check(lib.dexnerf_render_fused_bwd(C.byref(p), L.ptr(g[0]), L.ptr(g[1]), L.ptr(buf["d_rf"]), L.ptr(gc),
                                                  L.ptr(gf), which, stream), "render_fused_bwd")
-            L.launch_count += 2          # compositing backward, activation-gradient chain, weight-gradient GEMM
+            L.launch_count += 2 * (2 if which == 3 else 1)   # compositing backward, activation-gradient chain, weight-gradient GEMM
             if which == 1 and after_fine is not None:
                 after_fine()
         del keep

@@ -2,6 +2,8 @@
 tensor-core forward, the activation-gradient chain, the weight-gradient GEMM and the whole
 training iteration against the reference-generated gradients (tests/golden/train_grads.npz) and
 the CPU oracle.  Tolerances are written at each comparison."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -10,6 +12,8 @@ import nerf
 from nerf import _lib as L
 from nerf import tensorcore, training
 from oracle import nerf_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = pytest.mark.gpu
 t = torch.from_numpy
@@ -321,6 +325,73 @@ def test_single_launch_backwards_equal_the_two_kernels(hidden, layers, skip, n, 
     # A second fused launch on the same tape must give the same result again (flags are re-armed per launch).
     again = training.mlp_backward(model, prog, spec, tape2, d_rf, n, S, what=what)
     assert rel_err(again, want) < 1e-4
+
+
+def test_backward_kernels_on_a_subset_of_the_sms():
+    """`variant` bits 8-15 / 16-23 of dexnerf_tc_backward: the weight-gradient GEMM on 100 SMs and the chain on 40 give
+    the gradients of the full-width launches (another split-K partition: fp32 summation order only)."""
+    torch.manual_seed(5)
+    model = nerf.FlexibleNeRFModel(8, 256, 4, 10, 4).cuda()
+    ex, ed = nerf.get_embedding_function(10, True, True), nerf.get_embedding_function(4, True, True)
+    prog = model.program(ex, ed)
+    spec = tensorcore.spec_for(model, prog)
+    n, S = 300, 192
+    g = torch.Generator().manual_seed(2)
+    ro, rd = (torch.randn(n, 3, generator=g) * 0.3).cuda(), torch.randn(n, 3, generator=g).cuda()
+    vd = rd / rd.norm(dim=-1, keepdim=True)
+    z = torch.sort(2 + 4 * torch.rand(n, S, generator=g), dim=-1).values.cuda()
+    d_rf = (torch.randn(n, S, 4, generator=g) * 0.05).cuda()
+    rf, tape = training.query_train(model, prog, spec, ro, rd, vd, z)
+    tape2 = tape.clone()
+    want = training.mlp_backward(model, prog, spec, tape, d_rf, n, S, what=3)
+    training.mlp_backward(model, prog, spec, tape2, d_rf, n, S, what=1, variant=40 << 16)
+    got = training.mlp_backward(model, prog, spec, tape2, d_rf, n, S, what=2, variant=100 << 8)
+    assert torch.equal(tape2, tape)              # the chain's gradient images do not depend on the grid
+    assert rel_err(got, want) < 1e-4
+
+
+SPLIT_WORKER = r'''
+import os, sys, torch
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "dex-nerf_b200"))
+import nerf
+torch.manual_seed(3)
+mc, mf = nerf.FlexibleNeRFModel(8, 256, 4, 10, 4).cuda(), nerf.FlexibleNeRFModel(8, 256, 4, 10, 4).cuda()
+mode = dict(chunksize=1 << 20, perturb=True, num_coarse=64, num_fine=128, white_background=False,
+            radiance_field_noise_std=0.2, lindisp=False)
+cfg = nerf.CfgNode(dict(dataset=dict(no_ndc=True, near=2.0, far=6.0), nerf=dict(use_viewdirs=True, train=dict(mode), validation=dict(mode))))
+ex, ed = nerf.get_embedding_function(10, True, True), nerf.get_embedding_function(4, True, True)
+g = torch.Generator().manual_seed(5)
+n = 512
+ro = (torch.randn(n, 3, generator=g) * 0.2).cuda(); rd = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1).cuda()
+tgt = torch.rand(n, 3, generator=g).cuda()
+rng = dict(t_rand=torch.rand(n, 64, generator=g).cuda(), u=torch.rand(n, 128, generator=g).cuda(),
+           noise_coarse=(0.2 * torch.randn(n, 64, generator=g)).cuda(), noise_fine=(0.2 * torch.randn(n, 192, generator=g)).cuda())
+tr = nerf.Trainer(mc, mf, cfg, ex, ed)
+losses = [float(tr.step(ro, rd, tgt, rng=rng)[0]) for _ in range(3)]
+torch.cuda.synchronize()
+torch.save(dict(losses=losses, params=tr.params.cpu()), sys.argv[1])
+'''
+
+
+def test_trainer_with_the_two_backwards_side_by_side(tmp_path):
+    """DEXNERF_BWD_SPLIT=40 (render.cu: the fine network's weight-gradient GEMM on 108 SMs next to the coarse network's
+    compositing backward + chain on 40, second stream, fork / join events) against the default order: the same losses
+    and parameters after three iterations, up to the summation order of the weight gradients."""
+    import subprocess
+    import sys
+    script = tmp_path / "split_worker.py"
+    script.write_text("ROOT = %r\n" % ROOT + SPLIT_WORKER)
+    outs = []
+    for k in ("0", "40"):
+        path = str(tmp_path / ("out%s.pt" % k))
+        r = subprocess.run([sys.executable, str(script), path], capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, DEXNERF_BWD_SPLIT=k))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        outs.append(torch.load(path))
+    a, b = outs
+    assert all(abs(x - y) < 1e-5 for x, y in zip(a["losses"], b["losses"])), (a["losses"], b["losses"])
+    diff = (a["params"] - b["params"]).abs()
+    assert float((diff > 2e-4).float().mean()) < 0.02        # Adam steps of entries with |grad| ~ eps aside
 
 
 # ------------------------------------------------------------------ whole training iteration
