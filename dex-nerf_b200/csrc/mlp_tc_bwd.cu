@@ -504,6 +504,14 @@ struct DwParams {
   const uint32_t* ready;   // fused launch: [kMaxLayers + 1][n_tiles] image-complete counters written by the chain CTAs
   uint32_t* consumed;      // fused launch: [kMaxLayers + 1][n_tiles][2] readers done with a half image
   uint32_t* consumed_total;   // shared-SM kernel: (item, tile) units finished - the chains' back-pressure signal
+  // Stand-alone kernel: fc_alpha's gradient rides on the item of the layer that reads the same activations (the
+  // feature layer): dW_alpha[k] = sum_s X[s][k] d_sigma[s] is a WEIGHTED column sum of the A image, taken by the
+  // column-sum warps with mma.sync (d_sigma as the 16 identical rows of the first operand).  A separate item would
+  // stream that image - 4.5 % of the kernel's bytes - a second time.
+  int head_item;              // item that carries the head, -1: none
+  int head_rows;              // in-features of fc_alpha
+  int64_t head_g_off;         // tape offset of the [d rgb, d sigma, 0 ...] image (2 feature groups per tile half)
+  int64_t head_w, head_b;     // float offsets of fc_alpha's weight / bias gradient
   DwItem items[kMaxDwItems];
 };
 
@@ -522,7 +530,8 @@ using WSmem = WSmemT<kWStages, kWStageA, kWStageG>;
 // operands (the heads: 18 KB per stage; the direction encoding: 32 KB) is otherwise bound by the latency of three
 // small copies in flight, and the kernel ends with its slowest CTA.
 constexpr int kWPackedStages = 8;
-constexpr int kWRingBytes = kWStages * (kWStageA + kWStageG);
+constexpr int kWHeadBytes = 1024;    // feature group 0 of a [d rgb, d sigma, ...] half image (see DwParams::head_item)
+constexpr int kWRingBytes = kWStages * (kWStageA + kWStageG + 2048);
 using WSmemPacked = WSmemT<kWPackedStages, kWRingBytes / kWPackedStages / 2, kWRingBytes / kWPackedStages / 2>;
 static_assert(WSmemPacked::bars == kWRingBytes, "the packed ring is the same 192 KB");
 // the weight-gradient GEMM when it shares the SM with the chain: ONE M block per item (256 TMEM columns), so a stage
@@ -579,7 +588,9 @@ __device__ __forceinline__ void dw_body(const DwParams& P, uint8_t* smem, const 
   const uint32_t a_bytes = (uint32_t)I.a_fgs * 1024u, g_bytes = (uint32_t)I.g_fg * 1024u;
   // ring geometry: stage st holds A at a_base + st * a_stride and G at g_base + st * g_stride
   const uint32_t a_slot = (uint32_t)I.n_mblk * 16384u;
-  const uint32_t packed_stage = a_slot + g_bytes;
+  const bool with_head = kPacked && it == P.head_item;       // CTA-uniform
+  const uint32_t packed_stage = a_slot + g_bytes + (with_head ? (uint32_t)kWHeadBytes : 0u);
+  const uint32_t h_base = sbase + WSmem::a + a_slot + g_bytes;      // (with_head) + st * packed_stage
   int n_st = kWStages;
   if (kPacked) { n_st = (int)((uint32_t)kWRingBytes / packed_stage); n_st = n_st > kWStages ? kWStages : n_st; }
   const uint32_t a_stride = kPacked ? packed_stage : (uint32_t)kWStageA, g_stride = kPacked ? packed_stage : (uint32_t)kWStageG;
@@ -638,9 +649,11 @@ __device__ __forceinline__ void dw_body(const DwParams& P, uint8_t* smem, const 
         const int half = (int)(s & 1);
         const uint8_t* a_src = P.tape + I.a_off + tile * (int64_t)(I.a_fg * 2048) + (int64_t)half * (I.a_fg * 1024) +
                                (int64_t)I.a_fg0 * 1024;
-        mbar_arrive_expect_tx(full(st), a_bytes + g_bytes);
+        mbar_arrive_expect_tx(full(st), a_bytes + g_bytes + (with_head ? (uint32_t)kWHeadBytes : 0u));
         bulk_g2s(a_base + st * a_stride, a_src, a_bytes, full(st));
         bulk_g2s(g_base + st * g_stride, g_image(s), g_bytes, full(st));
+        if (with_head)
+          bulk_g2s(h_base + st * packed_stage, P.tape + P.head_g_off + tile * 4096 + (int64_t)half * 2048, kWHeadBytes, full(st));
       }
       __syncwarp();
       if (kFused && s >= kWStages) {
@@ -708,9 +721,13 @@ __device__ __forceinline__ void dw_body(const DwParams& P, uint8_t* smem, const 
     __shared__ uint32_t s_last;
     const bool has_bias = I.b_out >= 0;
     const int bw = warp - 4;                    // 0..3
-    float acc[8][4];
+    float acc[4][4], hacc[4][4];                // column sums of G; (with_head) fc_alpha's weight gradient
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    for (int i = 0; i < 4; ++i) {
+      acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+      hacc[i][0] = hacc[i][1] = hacc[i][2] = hacc[i][3] = 0.f;
+    }
+    float hbias = 0.f;                          // ... and its bias gradient (lanes 0-3 of the first warp)
     int st = 0;
     uint32_t ph = 0;
 #pragma unroll 1
@@ -736,43 +753,84 @@ __device__ __forceinline__ void dw_body(const DwParams& P, uint8_t* smem, const 
           for (uint32_t off = (uint32_t)j * 128u; off < g_bytes; off += 128u * 128u) discard_l2(g + off);
         }
       }
-      if (has_bias && !(P.variant & 2)) {
+      // One mma.sync m16n8k16 per 16 FEATURES and 16 samples: the first operand is the transposed image slice
+      // [16 features x 16 samples] (ldmatrix.x4.trans: feature groups 2 j and 2 j + 1, two runs of 8 samples), the second
+      // [16 samples x 8] is all ones for the column sums (every column of the result is the sum) or the head image
+      // [d rgb, d sigma, 0 ...] for fc_alpha (column 3 of the result).  Warp w owns the feature-group pairs
+      // [4 w, 4 w + 4): 16 LDSM + 16 HMMA per stage and image.  A legacy HMMA keeps the SM sub-partition's tensor pipe
+      // for ~32 cycles (measured: 64 per warp and stage already exceed the ~2 400 cycles a stage takes to stream), so the
+      // form with the features on N (8 per instruction) was twice too expensive to carry the head as well.
+      const uint32_t lm_off = (uint32_t)((lane >> 3) & 1) * 1024u + (uint32_t)((lane >> 4) * 8 + (lane & 7)) * 16u;
+      auto column_mma = [&](float (&d)[4][4], const uint32_t img, const int n_fg, const bool head, const uint32_t himg) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int fg = bw * 8 + i;
-          if (fg < I.g_fg) {                       // warp-uniform
-            const uint32_t gs = g_base + st * g_stride + fg * 1024 + (uint32_t)lane * 16;
+        for (int ks = 0; ks < 4; ++ks) {
+          uint32_t b0 = 0x3F803F80u, b1 = 0x3F803F80u;      // (1.0, 1.0) in bf16
+          if (head)
+            asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];"
+                         : "=r"(b0), "=r"(b1) : "r"(himg + (uint32_t)(ks * 16 + (lane & 15)) * 16u));
+          uint32_t a[4][4];
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {  // samples [32 half, 32 half + 32): two K steps of 16
-              uint32_t b0, b1, b2, b3;
+          for (int i = 0; i < 4; ++i)
+            if ((bw * 4 + i) * 2 < n_fg)              // warp-uniform
               asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
-                           : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(gs + (uint32_t)half * 512));
-              const uint32_t one2 = 0x3F803F80u;    // (1.0, 1.0) in bf16
-              asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %4, %4, %4}, {%5, %6}, "
+                           : "=r"(a[i][0]), "=r"(a[i][1]), "=r"(a[i][2]), "=r"(a[i][3])
+                           : "r"(img + (uint32_t)(bw * 4 + i) * 2048u + (uint32_t)ks * 256u + lm_off));
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if ((bw * 4 + i) * 2 < n_fg)
+              asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
                            "{%0, %1, %2, %3};"
-                           : "+f"(acc[i][0]), "+f"(acc[i][1]), "+f"(acc[i][2]), "+f"(acc[i][3]) : "r"(one2), "r"(b0), "r"(b1));
-              asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %4, %4, %4}, {%5, %6}, "
-                           "{%0, %1, %2, %3};"
-                           : "+f"(acc[i][0]), "+f"(acc[i][1]), "+f"(acc[i][2]), "+f"(acc[i][3]) : "r"(one2), "r"(b2), "r"(b3));
-            }
-          }
+                           : "+f"(d[i][0]), "+f"(d[i][1]), "+f"(d[i][2]), "+f"(d[i][3])
+                           : "r"(a[i][0]), "r"(a[i][1]), "r"(a[i][2]), "r"(a[i][3]), "r"(b0), "r"(b1));
+        }
+      };
+      if (has_bias && !(P.variant & 2)) column_mma(acc, g_base + st * g_stride, I.g_fg, false, 0u);
+      if (with_head) {
+        const uint32_t himg = h_base + st * packed_stage;
+        column_mma(hacc, a_base + st * a_stride, I.a_fgs, true, himg);
+        if (bw == 0) {       // fc_alpha's bias gradient: the sum of d sigma (column 3: bytes 6-7 of a sample's 16), two samples per lane
+          uint32_t v0, v1;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v0) : "r"(himg + (uint32_t)lane * 16u + 6u));
+          asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v1) : "r"(himg + (uint32_t)(lane + 32) * 16u + 6u));
+          hbias += __uint_as_float(v0 << 16) + __uint_as_float(v1 << 16);
         }
       }
       mbar_arrive(empty(st));
       if (++st == n_st) { st = 0; ph ^= 1u; }
     }
     const long long t_loop_end = (P.variant & 128) ? clock64() : 0;
-    if (has_bias && lane < 4) {                  // row 0 of the result: lanes 0..3 hold features 2 lane, 2 lane + 1
+    // result rows g = lane / 4 and g + 8 of feature-group pair j: feature g of groups 2 j and 2 j + 1
+    if (has_bias && (lane & 3) == 0) {           // every column holds the sum: take column 0
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int fg = bw * 8 + i;
+      for (int i = 0; i < 4; ++i) {
+        const int fg = (bw * 4 + i) * 2;
         if (fg < I.g_fg) {
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const int cc = fg * 8 + lane * 2 + c - I.col0;
-            if (cc >= 0 && cc < I.n_cols) red_add_f32(P.grads + I.b_out + cc, acc[i][c]);
+          for (int h = 0; h < 2; ++h) {
+            const int cc = (fg + h) * 8 + (lane >> 2) - I.col0;
+            if (cc >= 0 && cc < I.n_cols) red_add_f32(P.grads + I.b_out + cc, acc[i][2 * h]);
           }
         }
+      }
+    }
+    if (with_head) {
+      if ((lane & 3) == 1) {                     // column 3 = d sigma: the second value of the lanes with lane % 4 == 1
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int fg = (bw * 4 + i) * 2;
+          if (fg < I.a_fgs) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int k = (fg + h) * 8 + (lane >> 2);
+              if (k < P.head_rows) red_add_f32(P.grads + P.head_w + k, hacc[i][2 * h + 1]);
+            }
+          }
+        }
+      }
+      if (bw == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) hbias += __shfl_xor_sync(0xffffffffu, hbias, o);
+        if (lane == 0) red_add_f32(P.grads + P.head_b, hbias);
       }
     }
     // ---- accumulators -> global (one thread per in-feature row, TMEM lane = row within the M block)
@@ -1013,6 +1071,9 @@ extern "C" DEXNERF_API int dexnerf_tc_backward(const dexnerf_flexible_spec* spec
            flag_row);
     };
     const int hfg = H / 8;
+    W.head_item = -1;
+    // stand-alone kernel: fc_alpha rides on the item that streams the same activations (DwParams::head_item)
+    const bool merge_alpha = !fused && !(variant & 32);
     for (int l = 0; l < nl; ++l) {
       const TcLayer& L = plan.layers[l].tc;
       const dexnerf_op& op = prog->ops[plan.layers[l].prog_op];
@@ -1020,6 +1081,7 @@ extern "C" DEXNERF_API int dexnerf_tc_backward(const dexnerf_flexible_spec* spec
       int64_t w_row = op.w_off;
       bool bias_done = false;
       if (L.k_main) {      // hidden-input part: rows [0, H) of Wt
+        if (merge_alpha && l - 1 == nl - 3 && W.head_item < 0 && W.n_items < kMaxDwItems) W.head_item = W.n_items;
         add(T.act[l - 1], hfg, 0, hfg, H, T.grad[l], gfg, w_row, op.b_off, 0, L.n_out, L.n_out, l);
         bias_done = true;
         w_row += (int64_t)H * L.n_out;
@@ -1032,7 +1094,14 @@ extern "C" DEXNERF_API int dexnerf_tc_backward(const dexnerf_flexible_spec* spec
     {   // heads: fc_alpha reads the last trunk output, fc_rgb the dir-layer output; G = [d rgb, d sigma, 0..]
       const dexnerf_op& oa = prog->ops[plan.op_alpha];
       const dexnerf_op& orgb = prog->ops[plan.op_rgb];
-      add(T.act[nl - 3], hfg, 0, hfg, H, T.ghead, 2, oa.w_off, oa.b_off, 3, 1, 1, kMaxLayers);
+      if (W.head_item >= 0) {
+        W.head_rows = H; W.head_g_off = T.ghead; W.head_w = oa.w_off; W.head_b = oa.b_off;
+        // its CTAs take ~2 700 cycles per stage where the others stream theirs in ~2 250 (per-CTA clocks, tools/dw_profile.py):
+        // the 32 legacy HMMAs per warp and stage of the column-sum warps are what paces them
+        cost[W.head_item] = (cost[W.head_item] + 1.0) * 1.2;
+      } else {
+        add(T.act[nl - 3], hfg, 0, hfg, H, T.ghead, 2, oa.w_off, oa.b_off, 3, 1, 1, kMaxLayers);
+      }
       add(T.act[nl - 1], hfg / 2, 0, hfg / 2, H / 2, T.ghead, 2, orgb.w_off, orgb.b_off, 0, 3, 3, kMaxLayers);
     }
     DN_REQUIRE(W.n_items <= kMaxDwItems, "tc_backward: too many weight-gradient items");
