@@ -460,7 +460,8 @@ def run_train(args, dist, rank, world, dev, quiet=False):
         "gpu_launches": launches,
         # The training step is bound by the TAPE traffic: per 128-sample tile the
         # forward writes 666 KB, the activation-gradient chain writes 612 KB (+ 34 KB of masks read) and the
-        # weight-gradient GEMM reads 1 424 KB - 2 736 KB of algorithmic HBM bytes against 0.46 GFLOP.
+        # weight-gradient GEMM reads 1 358 KB (1 424 KB before fc_alpha's gradient moved into the feature layer's item)
+        # - 2 670 KB of algorithmic HBM bytes against 0.46 GFLOP.
         "roofline": {"bound": "hbm", "kernel": "mlp_tc train fwd + bwd_dx + bwd_dw (fine pass, 192 samples/ray)",
                      "achieved": None, "peak": pk["hbm"], "unit": "GB/s", "peak_source": pk["source"] + " HBM copy",
                      "traffic": train_traffic(), "kernel_ms": {k: round(v, 4) for k, v in sorted(parts.items())},
@@ -501,7 +502,7 @@ def run_train(args, dist, rank, world, dev, quiet=False):
             print(json.dumps(line))
         return line
     if fw_ms and dx_ms and dw_ms:
-        tape_bytes = TRAIN_RAYS * (NC + NF) / 128.0 * (666.0 + 646.0 + 1424.0) * 1024.0
+        tape_bytes = TRAIN_RAYS * (NC + NF) / 128.0 * (666.0 + 646.0 + 1358.0) * 1024.0
         r = line["roofline"]
         r["bytes_per_launch"] = tape_bytes
         r["achieved"] = tape_bytes / ((fw_ms + dx_ms + dw_ms) * 1e-3) / 1e9
@@ -523,7 +524,7 @@ def run_train(args, dist, rank, world, dev, quiet=False):
         f = TRAIN_RAYS * (NC + NF) * 2.0 * (128 * 256 + 8 * 256 * 256)      # dir^T(feat part) + fc_feat^T + 7 trunk^T
         per["mlp_tc_bwd_dx"] = entry(dx_ms, f, 646.0, "hbm write + tensor")
     if dw_ms:
-        per["mlp_tc_bwd_dw"] = entry(dw_ms, flop_fine, 1424.0, "hbm read")
+        per["mlp_tc_bwd_dw"] = entry(dw_ms, flop_fine, 1358.0, "hbm read")
     line["roofline"]["kernels"] = per
     if not quiet:
         print(json.dumps(line))
