@@ -1,5 +1,6 @@
-import sys, torch
-sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/dex-nerf_b200')
+import os, sys, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'dex-nerf_b200'))
 import nerf
 from nerf import training, tensorcore
 torch.manual_seed(0)
