@@ -176,10 +176,13 @@ DEXNERF_API int dexnerf_tc_pack_bwd(const dexnerf_flexible_spec* spec, const dex
  * path).  Two single-launch forms in which the images go from the chain to the GEMM through L2 with release /
  * acquire flags (same results; slower than 3 on a B200 today, kept selectable - DESIGN.md section 3.2): 4 = chain and
  * GEMM on disjoint SMs, 8 = chain and GEMM as two warp groups of every CTA (one CTA per SM, with back-pressure).
- * variant: 0.  (Bring-up / experiment bits: 1 swaps the GEMM's descriptor strides, 2 skips the bias column sums,
- * 4 skips the MMAs - results invalid; single-launch forms: 8 no L2 discard, 16 no flag waits - results invalid,
- * 32 no back-pressure, 128 print where the GEMM's producer waits; variant >> 8: chain CTAs (what = 4) / the
- * back-pressure window in tiles (what = 8) / CTA budget (what = 2).) */
+ * variant: 0.  Bits 8-15: SMs the weight-gradient GEMM may use (what = 2; 0 = all), bits 16-23: SMs of the chain
+ * (what = 1; 0 = all) - the results do not depend on either (the chain's images bit for bit, the GEMM's sums up to
+ * their fp32 order).  (Bring-up / experiment bits: 1 swaps the GEMM's descriptor strides, 2 skips the bias column
+ * sums, 4 skips the MMAs - results invalid; 32 (what = 2) keeps fc_alpha's gradient a work item of its own instead
+ * of folding it into the feature layer's; 128 prints per-CTA clocks of the GEMM; single-launch forms: 8 no L2
+ * discard, 16 no flag waits - results invalid, 32 no back-pressure, bits 8-15 chain CTAs (what = 4) / the
+ * back-pressure window in tiles (what = 8).) */
 DEXNERF_API int dexnerf_tc_backward(const dexnerf_flexible_spec* spec, const dexnerf_mlp_program* prog,
                         const void* packed, const void* packed_t, void* tape, const float* d_rf,
                         int64_t n, int S, float* grads, int what, int variant, void* stream);
@@ -260,7 +263,9 @@ DEXNERF_API int dexnerf_render_fused_fwd(const dexnerf_render_params* p /*host*/
  * coarse network's (3 = both, fine first: its gradient buffer is complete first, so a data-parallel caller can
  * issue the two halves separately and start reducing the fine gradients while the coarse chain runs).
  * 3 launches per network: compositing backward, activation-gradient chain, weight-gradient GEMM
- * (DEXNERF_BWD=fused / shared select the single-launch MLP backwards of dexnerf_tc_backward instead). */
+ * (DEXNERF_BWD=fused / shared select the single-launch MLP backwards of dexnerf_tc_backward instead;
+ * DEXNERF_BWD_SPLIT=k with which = 3 runs the coarse network's compositing backward + chain on k SMs and a second
+ * stream next to the fine network's GEMM on the other 148 - k: same results, measured slower on a B200, off). */
 DEXNERF_API int dexnerf_render_fused_bwd(const dexnerf_render_params* p /*host*/, const float* g_rgb_coarse,
                                          const float* g_rgb_fine, float* d_rf_scratch, float* grads_coarse,
                                          float* grads_fine, int which, void* stream);
