@@ -519,10 +519,10 @@ def run_train(args, dist, rank, world, dev, quiet=False):
                 "tensor_frac_of_sustained_peak": flop / (ms * 1e-3) / 1e12 / pk["tf_sustained"],
                 "gbs": b / (ms * 1e-3) / 1e9, "hbm_frac_of_peak": b / (ms * 1e-3) / 1e9 / pk["hbm"], "bytes": b}
     if fw_ms:
-        per["mlp_tc_train_fwd"] = entry(fw_ms, flop_fine, 666.0, "hbm write + tensor")
+        per["mlp_tc_train_fwd"] = entry(fw_ms, flop_fine, 666.0, "crossbar write port (32 B/clk/SM) + tensor")
     if dx_ms:
         f = TRAIN_RAYS * (NC + NF) * 2.0 * (128 * 256 + 8 * 256 * 256)      # dir^T(feat part) + fc_feat^T + 7 trunk^T
-        per["mlp_tc_bwd_dx"] = entry(dx_ms, f, 646.0, "hbm write + tensor")
+        per["mlp_tc_bwd_dx"] = entry(dx_ms, f, 646.0, "crossbar write port (32 B/clk/SM) + tensor")
     if dw_ms:
         per["mlp_tc_bwd_dw"] = entry(dw_ms, flop_fine, 1358.0, "hbm read")
     line["roofline"]["kernels"] = per
