@@ -253,3 +253,42 @@ def test_bench_scene_tables_are_consistent():
     assert mc.hidden_size == 128 and len(mc.layers_xyz) == 7 and mc.skip_connect_every == 3
     assert bench.FLOP_PER_EVAL == 2 * sum(p.numel() for k, p in mc.named_parameters() if k.endswith("weight"))
     assert float(mc.fc_alpha.weight.abs().max()) > 10.0          # the x1000 scale that makes sigma cross thresholds
+
+
+def test_bench_clock_sampler_keeps_the_samples_of_the_timed_window():
+    """bench.py's ClockSampler (an `nvidia-smi -lms` process) may be started before the warm-up; stop(window) keeps
+    only the samples whose timestamps fall inside the timed region and collects the throttle reasons seen there."""
+    import datetime
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod2", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    def stamp(t):
+        return datetime.datetime.fromtimestamp(t).strftime("%Y/%m/%d %H:%M:%S.%f")[:-3]
+
+    t0 = 1_700_000_000.0
+    lines = [
+        "%s, 345, 1965, 180.0, 0x0, Not Active, Not Active, Not Active, Not Active" % stamp(t0 - 0.30),   # idle, before
+        "%s, 1965, 1965, 700.0, 0x4, Not Active, Not Active, Not Active, Active" % stamp(t0 + 0.01),
+        "%s, 1950, 1965, 900.0, 0x4, Not Active, Not Active, Not Active, Active" % stamp(t0 + 0.05),
+        "%s, 1935, 1965, 950.0, 0x0, Not Active, Not Active, Not Active, Not Active" % stamp(t0 + 0.09),
+        "%s, 400, 1965, 200.0, 0x0, Active, Not Active, Not Active, Not Active" % stamp(t0 + 0.40),        # after
+        "garbage line",
+    ]
+
+    class FakeProc:
+        def terminate(self):
+            pass
+
+        def communicate(self, timeout=None):
+            return "\n".join(lines) + "\n", ""
+
+    s = bench.ClockSampler(0, period_ms=25)
+    s.proc = FakeProc()
+    got = s.stop((t0, t0 + 0.10))
+    assert got["samples"] == 3 and got["sm_mhz"] == 1950.0 and got["sm_max_mhz"] == 1965.0
+    assert got["reasons"] == ["sw_power_cap"]                      # the hw_slowdown sample lies outside the window
+    s.proc = FakeProc()
+    everything = s.stop()
+    assert everything["samples"] == 5 and everything["reasons"] == ["hw_slowdown", "sw_power_cap"]
