@@ -292,3 +292,41 @@ def test_bench_clock_sampler_keeps_the_samples_of_the_timed_window():
     s.proc = FakeProc()
     everything = s.stop()
     assert everything["samples"] == 5 and everything["reasons"] == ["hw_slowdown", "sw_power_cap"]
+
+
+def test_built_library_carries_the_tensor_core_instructions():
+    """The SASS of the built library (cuobjdump, no GPU needed): the MLP kernels issue tcgen05.mma (UTCHMMA) with TMEM
+    loads / stores and bulk copies, the weight-gradient GEMM additionally the legacy HMMA + LDSM of its column sums -
+    i.e. the product path is the hand-written sm_100a code, not a library or CUDA-core fallback."""
+    import collections
+    import re
+    import shutil
+    import subprocess
+    from nerf import _lib as L
+    if shutil.which("cuobjdump") is None or not os.path.exists(L.LIB_PATH):
+        pytest.skip("cuobjdump or the built library is not available")
+    out = subprocess.run(["cuobjdump", "-sass", L.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    kernels, cur = {}, None
+    for line in out.splitlines():
+        m = re.match(r"\s*Function : (\S+)", line)
+        if m:
+            cur = kernels.setdefault(m.group(1), collections.Counter())
+            continue
+        m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
+        if m and cur is not None:
+            cur[m.group(1)] += 1
+    assert "sm_100a" in out or "sm_100" in out
+
+    def find(fragment):
+        hits = [c for name, c in kernels.items() if fragment in name]
+        assert hits, fragment
+        return hits
+
+    for frag in ("mlp_tc_kernel", "mlp_tc3_kernel", "mlp_tc_bwd_dx_kernel", "mlp_tc_bwd_dw_kernel"):
+        for c in find(frag):
+            assert c["UTCHMMA"] > 0 and c["UBLKCP"] > 0 and c["SYNCS"] > 0, frag       # tcgen05.mma, cp.async.bulk, mbarriers
+    for frag in ("mlp_tc_kernel", "mlp_tc3_kernel", "mlp_tc_bwd_dx_kernel"):
+        for c in find(frag):
+            assert c["LDTM"] > 0 and c["STTM"] > 0, frag                                # activations stay in TMEM
+    for c in find("mlp_tc_bwd_dw_kernel"):
+        assert c["HMMA"] > 0 and c["LDSM"] > 0 and c["LDTM"] > 0
